@@ -1,0 +1,33 @@
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+def random_golden_files():
+    return sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "random_*.npz")))
+
+
+@pytest.fixture(scope="session")
+def fixtures_golden():
+    return load_golden("fixtures.npz")
+
+
+@pytest.fixture(scope="session")
+def edge_golden():
+    return load_golden("edge.npz")
