@@ -89,12 +89,14 @@ def inside_outside_single(p: torch.Tensor, pts: torch.Tensor, clamp: bool, fix_z
     a, e, t, q = p[0:3], p[3:5], p[5:8], p[8:12]
     rot = mat_from_quaternion(conjugate(q))
     tr = torch.matmul(rot, t)
-    cs = torch.einsum("ij,j...->i...", rot, pts)
+    cs = torch.einsum("ij,jabc->iabc" if pts.dim() == 4 else "ij,ja->ia", rot, pts)
     A1 = torch.pow((cs[0] - tr[0]) / a[0], 2)
     B1 = torch.pow((cs[1] - tr[1]) / a[1], 2)
     C1 = torch.pow((cs[2] - tr[2]) / a[2], 2)
-    if fix_zero:
-        A1, B1, C1 = _fix(A1), _fix(B1), _fix(C1)
+    if fix_zero:                    # same in-place masked add as the reference (classes.py:171-173)
+        A1[A1 == 0] += ZERO_FIX
+        B1[B1 == 0] += ZERO_FIX
+        C1[C1 == 0] += ZERO_FIX
     A = torch.pow(A1, 1 / e[1])
     B = torch.pow(B1, 1 / e[1])
     C = torch.pow(C1, 1 / e[0])

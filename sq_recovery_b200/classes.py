@@ -1,0 +1,135 @@
+"""Drop-in replacements for the loss classes of the reference's ``torch/classes.py``.
+
+Same class names, constructor signatures, public attributes, call signatures and autograd behaviour
+(SURVEY 8b); the per-sample Python loop of ~1.5 k fp64 tensor ops is replaced by one fused CUDA kernel per call
+(csrc/sqloss.cu through include/sqloss.h).  Swap in with
+
+    from sq_recovery_b200.classes import ExplicitLoss, ImplicitLoss, IoUAccuracy, LeastSquares
+
+There is no CPU path: ``device`` must be a CUDA device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import functional as Fn
+
+_ZERO_FIX = 1e-4        # torch/classes.py:126, :221
+
+
+def _cuda_device(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"sq_recovery_b200 runs on CUDA devices only (got device={device!r}); "
+                           "there is no CPU fallback")
+    return dev
+
+
+def _preprocess_sq(p: torch.Tensor) -> torch.Tensor:
+    """Clamp a to [0.05, 1], e to [0.1, 1], t to [0, 1]; q untouched (torch/classes.py:129-136)."""
+    a, e, t, q = torch.split(p, (3, 2, 3, 4), dim=-1)
+    return torch.cat([a.clamp(0.05, 1), e.clamp(0.1, 1), t.clamp(0, 1), q], dim=-1)
+
+
+class _GridLoss:
+    """Shared bookkeeping: the reference stores these attributes on every loss object."""
+
+    def _setup(self, render_size, device, reduce, axis, fix_zero):
+        self.render_size = render_size
+        self.render_type = np.float64
+        self.eps = 1e-8
+        self.reduce = reduce
+        self.device = _cuda_device(device)
+        self._axis = axis                       # the reference's 1-D coordinate table, fp64
+        self._n = int(len(axis))
+        self._step = float(axis[1] - axis[0]) if len(axis) > 1 else 1.0
+        self._z0 = _ZERO_FIX if fix_zero else 0.0
+        self._xyz = None
+        Fn._lib.lib()                           # fail at construction time if libsqloss.so is missing
+
+    @property
+    def xyz(self) -> torch.Tensor:
+        """(3, n, n, n) fp64 meshgrid like the reference's attribute; built on first access (the kernels
+        generate grid points from indices and never read it)."""
+        if self._xyz is None:
+            r = torch.tensor(self._axis)
+            grid = torch.stack(torch.meshgrid([r, r, r], indexing="ij")).to(self.device)
+            if self._z0:
+                grid[grid == 0] += self._z0
+            self._xyz = grid
+        return self._xyz
+
+    preprocess_sq = staticmethod(_preprocess_sq)
+
+
+class ExplicitLoss(_GridLoss):
+    """MSE x 100 between the occupancy grids of true and predicted parameters (torch/classes.py:109-201)."""
+
+    def __init__(self, render_size, device, reduce=True):
+        step = 1 / render_size
+        axis = np.arange(0, 1 + step, step).astype(np.float64)          # classes.py:122-123 (n = R+1, R+2 for R=24,96)
+        self._setup(render_size, device, reduce, axis, fix_zero=True)
+        self._step = step
+
+    def occupancy(self, p):
+        """(B, n, n, n) sigmoid(5 (1 - F)) (classes.py:138-189), fp32, no autograd."""
+        return Fn.field(p, self._n, self._step, self._z0, 1, 5.0)
+
+    def __call__(self, true, pred):
+        return Fn.ExplicitLossFn.apply(true, pred, self._n, self._step, self._z0, 5.0, 100.0)
+
+
+class ImplicitLoss(_GridLoss):
+    """MAE between the input depth image and a soft depth render of the predicted SQ (torch/classes.py:203-295)."""
+
+    def __init__(self, render_size, device, tau=1, sigmoid_sharpness=100, reduce=True):
+        axis = np.linspace(0, 1, render_size).astype(np.float64)        # classes.py:218
+        self._setup(render_size, device, reduce, axis, fix_zero=True)
+        self.tau = tau
+        self.sigmoid_sharpness = sigmoid_sharpness
+
+    def depth_projection(self, p):
+        """(B, R, R) depth render in image orientation (classes.py:232-282), fp32, no autograd."""
+        return Fn.depth_projection(p, self._n, self._step, self._z0, float(self.tau), float(self.sigmoid_sharpness))
+
+    def __call__(self, true, pred):
+        return Fn.ImplicitLossFn.apply(true, pred, self._n, self._step, self._z0, float(self.tau),
+                                       float(self.sigmoid_sharpness))
+
+
+class LeastSquares(_GridLoss):
+    """Solina-Bajcsy energy on the points back-projected from the depth image (torch/classes.py:297-371)."""
+
+    def __init__(self, render_size, device, reduce=True):
+        self._setup(render_size, device, reduce, np.array([0.0, 1.0]), fix_zero=False)
+
+    @property
+    def xyz(self):
+        raise AttributeError("LeastSquares has no grid (torch/classes.py:303-308)")
+
+    def __call__(self, true, pred):
+        return Fn.LeastSquaresFn.apply(true, pred, int(self.render_size))
+
+
+class IoUAccuracy(_GridLoss):
+    """IoU of the binarised (F <= 1) grids of true and predicted parameters (torch/classes.py:374-447)."""
+
+    def __init__(self, render_size, device, reduce=True, full=False):
+        axis = np.linspace(0, 1, render_size).astype(np.float64)        # classes.py:389
+        self._setup(render_size, device, reduce, axis, fix_zero=False)
+        self.full = full
+
+    def ins_outs(self, p):
+        """(B, R, R, R) inside-outside values F (classes.py:394-426), fp32, no autograd."""
+        return Fn.field(p, self._n, self._step, 0.0, 0)
+
+    def counts(self, true, pred):
+        """Per-sample (intersection, union) voxel counts, int64."""
+        return Fn.iou_counts(true, pred, self._n, self._step, 0.0)
+
+    def __call__(self, true, pred):
+        inter, union = self.counts(true, pred)
+        if not self.reduce:
+            return inter.double() / union.double()                      # classes.py:441-445
+        return torch.sum(inter) / torch.sum(union)                      # classes.py:437-439 (batch-wide ratio)

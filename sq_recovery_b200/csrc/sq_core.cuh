@@ -1,0 +1,521 @@
+// Per-point core of the superquadric inside-outside losses (B200 / sm_100a).
+//
+// What the reference computes per sample and grid point (torch/classes.py:142-184, 236-274, 398-424, 322-351;
+// torch/quaternion.py:19-21, 46-67), restated for one thread walking one grid column along z:
+//
+//   M = mat(conj(q)),  s = (M (g - t)) / a                       (a,e,t clamped; q NOT normalised)
+//   A = |sx|^(2/e2)  B = |sy|^(2/e2)  C = |sz|^(2/e1)            (s == 0 -> |s| := 1e-2, the "A1 += 1e-4" fix-up)
+//   D = A + B   E = D^(e2/e1)   G = E + C   F = G^e1
+//
+// Numeric plan (DESIGN.md "precision"): the affine geometry is formed in fp64 once per column and carried
+// along z as a two-float (hi, lo) pair, so s has only its own final fp32 rounding; every pow is
+// ex2(p * lg2(x)) on the MUFU pipe; all derivative factors are written as ratios bounded by 1
+// (C/G, A/D, ...) so nothing overflows for points that carry gradient.
+//
+// Everything here is SQ_HD (host + device) on purpose: tests/emu compiles this same header with g++ to check
+// the forward/backward algebra against the oracle on the CPU.  The product never runs the host build.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SQ_HD __host__ __device__ __forceinline__
+#else
+#define SQ_HD inline
+#endif
+
+namespace sq {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr double kLn2 = 0.6931471805599453;
+constexpr float kAbsFix = 1e-2f;          // |s| used when s == 0  (s^2 := 1e-4, classes.py:171-173)
+constexpr float kActive = 40.0f;          // |log2 of the sigmoid odds| beyond which o(1-o) < 2^-40 is dropped
+
+// ---------------------------------------------------------------- MUFU primitives
+SQ_HD float ex2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+    return exp2f(x);
+#endif
+}
+SQ_HD float lg2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+    return log2f(x);
+#endif
+}
+SQ_HD float rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+    return 1.0f / x;
+#endif
+}
+
+// lg2|x| and 2^-|x| with the sign handling folded into the MUFU operand (MUFU.LG2 |R|, MUFU.EX2 -|R|).  Written
+// with the non-.ftz abs/neg so ptxas can fold them; the arithmetic fabsf() under -ftz costs an FADD on the FMA
+// pipe, which the MUFU ops contend with (profiles/peaks_r01.json).
+SQ_HD float lg2_abs(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("{\n .reg .f32 t;\n abs.f32 t, %1;\n lg2.approx.ftz.f32 %0, t;\n}" : "=f"(y) : "f"(x)); return y;
+#else
+    return log2f(fabsf(x));
+#endif
+}
+SQ_HD float ex2_neg_abs(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("{\n .reg .f32 t;\n abs.f32 t, %1;\n neg.f32 t, t;\n ex2.approx.ftz.f32 %0, t;\n}" : "=f"(y) : "f"(x)); return y;
+#else
+    return exp2f(-fabsf(x));
+#endif
+}
+
+// ---------------------------------------------------------------- grid
+// Every grid the reference builds is uniform: arange(0, 1+1/R, 1/R) (classes.py:122-123) or linspace(0,1,R)
+// (:218, :389), i.e. coordinate(i) = i*step, with coordinate 0 replaced by 1e-4 for Explicit/Implicit (:126,:221).
+struct Grid {
+    int n;          // points per axis
+    double step;    // spacing
+    double z0;      // coordinate of index 0 (1e-4 with the zero fix-up, else 0)
+};
+SQ_HD double grid_coord(const Grid& g, int i) { return i == 0 ? g.z0 : (double)i * g.step; }
+
+// ---------------------------------------------------------------- per-sample constants
+struct Sample {
+    // fp64 geometry: rows of M pre-divided by a_i, so s = Ms (g - t)
+    double Ms[9];
+    double t[3];
+    // fp32 constants of the point loop
+    float dh[3], dl[3];       // Ms[i][2] * step, split hi/lo: s_i(c) = base_i + d_i * cf(c)
+    float cf0;                // z0 / step: the (non-integer) "index" of plane 0
+    float pxy, pz;            // 2/e2, 2/e1
+    float e21, e1;            // e2/e1, e1
+    // for the finalize step
+    double M[9];              // un-scaled rotation
+    double a[3], e[2], q[4];
+    float mask[8];            // clamp sub-gradient masks for a(3), e(2), t(3): 1 inside or on the boundary, else 0
+};
+
+SQ_HD void split2(double v, float& hi, float& lo) { hi = (float)v; lo = (float)(v - (double)hi); }
+
+// p: 12 raw parameters [a1 a2 a3 e1 e2 t1 t2 t3 qx qy qz qw].  clamp per classes.py:129-136 (IoU: no clamp, :398).
+SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, Sample& S) {
+    const double lo[8] = {0.05, 0.05, 0.05, 0.1, 0.1, 0.0, 0.0, 0.0};
+    double v[8];
+    for (int i = 0; i < 8; ++i) {
+        double x = p[i];
+        float m = 1.0f;
+        if (clamp) {
+            if (x < lo[i]) { x = lo[i]; m = 0.0f; }
+            if (x > 1.0) { x = 1.0; m = 0.0f; }
+        }
+        v[i] = x;
+        S.mask[i] = m;
+    }
+    for (int i = 0; i < 3; ++i) { S.a[i] = v[i]; S.t[i] = v[5 + i]; }
+    S.e[0] = v[3]; S.e[1] = v[4];
+    for (int i = 0; i < 4; ++i) S.q[i] = p[8 + i];
+    // M = mat(conj(q)) = mat(q)^T   (quaternion.py:19-21, 46-67)
+    const double x = -p[8], y = -p[9], z = -p[10], w = p[11];
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    S.M[0] = 1.0 - (tyy + tzz); S.M[1] = txy - twz;         S.M[2] = txz + twy;
+    S.M[3] = txy + twz;         S.M[4] = 1.0 - (txx + tzz); S.M[5] = tyz - twx;
+    S.M[6] = txz - twy;         S.M[7] = tyz + twx;         S.M[8] = 1.0 - (txx + tyy);
+    for (int i = 0; i < 3; ++i) {
+        const double ia = 1.0 / S.a[i];
+        for (int j = 0; j < 3; ++j) S.Ms[3 * i + j] = S.M[3 * i + j] * ia;
+        split2(S.Ms[3 * i + 2] * g.step, S.dh[i], S.dl[i]);
+    }
+    S.cf0 = (float)(g.z0 / g.step);
+    S.pxy = (float)(2.0 / S.e[1]);
+    S.pz = (float)(2.0 / S.e[0]);
+    S.e21 = (float)(S.e[1] / S.e[0]);
+    S.e1 = (float)S.e[0];
+}
+
+// s at plane "index" 0 for the column through grid point (ia, ib): base_i = Ms_i . ((gx,gy,0) - t), as hi/lo floats
+SQ_HD void column_base(const Sample& S, const Grid& g, int ia, int ib, float* bh, float* bl) {
+    const double dx = grid_coord(g, ia) - S.t[0], dy = grid_coord(g, ib) - S.t[1], dz = -S.t[2];
+    for (int i = 0; i < 3; ++i)
+        split2(S.Ms[3 * i] * dx + S.Ms[3 * i + 1] * dy + S.Ms[3 * i + 2] * dz, bh[i], bl[i]);
+}
+
+// ---------------------------------------------------------------- forward at one point
+// The pow chain is evaluated in the log2 domain with the two sums done as log-sum-exp:
+//   lA = (2/e2) lg2|sx|   lB = (2/e2) lg2|sy|   lC = (2/e1) lg2|sz|
+//   lD = lg2(A + B) = max(lA, lB) + lg2(1 + 2^-|lA - lB|)
+//   lE = (e2/e1) lD
+//   lG = lg2(E + C) = max(lE, lC) + lg2(1 + 2^-|lE - lC|)
+//   F  = 2^(e1 lG)
+// Nothing under- or overflows before the last step (A = |s|^(2/e2) leaves fp32 range for |s| < 0.01 at e2 = 0.1,
+// and such points DO carry gradient through E = D^(e2/e1) when e2/e1 is small), the ratios A/D, E/G needed by the
+// backward come out of the same two exponentials, and it is 8 MUFU ops per F instead of the 10 of five pows.
+struct Fwd {
+    float sx, sy, sz;
+    float d1, t1, h1;         // lA - lB, 2^-|d1|, lg2(1 + t1)
+    float d2, t2, h2;         // lE - lC, 2^-|d2|, lg2(1 + t2)
+    float lG, F;
+    bool zx, zy, zz;          // exact-zero flags (fix-up applied)
+};
+
+template <bool FIX>
+SQ_HD void point_forward(const Sample& S, float sx, float sy, float sz, Fwd& f) {
+    f.sx = sx; f.sy = sy; f.sz = sz;
+    float mx = sx, my = sy, mz = sz;
+    if (FIX) {
+        f.zx = (sx == 0.0f); f.zy = (sy == 0.0f); f.zz = (sz == 0.0f);
+        mx = f.zx ? kAbsFix : mx; my = f.zy ? kAbsFix : my; mz = f.zz ? kAbsFix : mz;
+    } else {
+        f.zx = f.zy = f.zz = false;
+    }
+    const float lA = S.pxy * lg2_abs(mx);
+    const float lB = S.pxy * lg2_abs(my);
+    const float lC = S.pz * lg2_abs(mz);
+    f.d1 = lA - lB;
+    f.t1 = ex2_neg_abs(f.d1);
+    f.h1 = lg2(1.0f + f.t1);
+    const float lE = S.e21 * (fmaxf(lA, lB) + f.h1);
+    f.d2 = lE - lC;
+    f.t2 = ex2_neg_abs(f.d2);
+    f.h2 = lg2(1.0f + f.t2);
+    f.lG = fmaxf(lE, lC) + f.h2;
+    f.F = ex2(S.e1 * f.lG);
+}
+
+// occupancy o = sigmoid(k (1 - F)) = 1 / (1 + 2^(kl (F - 1))),  kl = k log2(e).   classes.py:187, :274
+SQ_HD float occupancy(float F, float kl, float& odds_log2, float& eo) {
+    odds_log2 = fmaf(F, kl, -kl);
+    eo = ex2(odds_log2);
+    return rcp(1.0f + eo);
+}
+
+// ---------------------------------------------------------------- backward at one point
+// Derivative of F (times a caller weight W) with respect to the scaled coordinates s, the sizes and the shapes.
+// With cG = C/G, eG = E/G, aD = A/D, bD = B/D (each pair sums to 1; the larger one is 1/(1+t), the smaller t/(1+t)):
+//   dF/dsz = 2 F cG / sz        dF/dsx = 2 F eG aD / sx        dF/dsy = 2 F eG bD / sy
+//   dF/da3 = -2 F cG / a3       dF/da1 = -2 F eG aD / a1       dF/da2 = -2 F eG bD / a2
+//   dF/de1 = F ln2 (lG - cG lC - eG lE)    = F ln2 H2         H2 = h2 + min(cG, eG) |d2|   (no cancellation)
+//   dF/de2 = F ln2 eG (lD - aD lA - bD lB) = F ln2 eG H1      H1 = h1 + min(aD, bD) |d1|
+// The factors 2, ln2, 1/a_i are per-sample constants applied in finalize_sample().
+struct Bwd {
+    float gs[3];      // W F {eG aD/sx, eG bD/sy, cG/sz}
+    float wa[3];      // W F {eG aD, eG bD, cG}
+    float ge[2];      // W F H2,  W F eG H1
+};
+
+SQ_HD void point_backward(const Fwd& f, float W, Bwd& b) {
+    const float WF = W * f.F;
+    const float r1 = rcp(1.0f + f.t1), s1 = f.t1 * r1;
+    const float r2 = rcp(1.0f + f.t2), s2 = f.t2 * r2;
+    const bool a_big = f.d1 >= 0.0f, e_big = f.d2 >= 0.0f;
+    const float aD = a_big ? r1 : s1, bD = a_big ? s1 : r1;
+    const float eG = e_big ? r2 : s2, cG = e_big ? s2 : r2;
+    const float wz = WF * cG, wxy = WF * eG;
+    const float wx = wxy * aD, wy = wxy * bD;
+    b.ge[0] = WF * fmaf(s2, fabsf(f.d2), f.h2);
+    b.ge[1] = wxy * fmaf(s1, fabsf(f.d1), f.h1);
+    // exact zeros: the fix-up replaces s^2 by a constant, so no gradient reaches s or a through that term
+    b.wa[0] = f.zx ? 0.0f : wx;
+    b.wa[1] = f.zy ? 0.0f : wy;
+    b.wa[2] = f.zz ? 0.0f : wz;
+    b.gs[0] = f.zx ? 0.0f : wx * rcp(f.sx);
+    b.gs[1] = f.zy ? 0.0f : wy * rcp(f.sy);
+    b.gs[2] = f.zz ? 0.0f : wz * rcp(f.sz);
+}
+
+// a harmless point for lanes that carry no gradient but run the backward with their warp (weight 0)
+SQ_HD void fwd_neutral(Fwd& f) {
+    f.sx = f.sy = f.sz = 1.f;
+    f.d1 = f.d2 = 0.f; f.t1 = f.t2 = 1.f; f.h1 = f.h2 = 1.f; f.lG = 0.f; f.F = 1.f;
+    f.zx = f.zy = f.zz = false;
+}
+
+// ---------------------------------------------------------------- per-thread accumulators
+// Sums over the points a thread visits (all columns of one sample), in the units finalize_sample() expects.
+struct Acc {
+    float gs[3];      // sum gs_i
+    float gm[9];      // sum gs_i * (g_j - t_j)  for j = x, y;  sum gs_i * cf for j = z   (row-major i, j)
+    float wa[3];
+    float ge[2];
+    float loss;
+};
+constexpr int kAccN = 18;
+SQ_HD void acc_zero(Acc& a) {
+    for (int i = 0; i < 3; ++i) { a.gs[i] = 0.f; a.wa[i] = 0.f; }
+    for (int i = 0; i < 9; ++i) a.gm[i] = 0.f;
+    a.ge[0] = a.ge[1] = 0.f; a.loss = 0.f;
+}
+
+// ---------------------------------------------------------------- finalize: partial sums -> d loss / d params
+// acc: the 18 sums over all points of one sample (fp64).  scale = d loss / d (weighted sum of F) constant, i.e.
+// the product of every per-sample constant factor the point loop left out except 2, ln2, 1/a, step.
+//   grad wrt t_j  = -sum_i Ms_ij gs_i
+//   grad wrt M_ij = (1/a_i) sum gs_i (g_j - t_j)
+//   grad wrt q    = sum_ij dM_ij/dq * grad M_ij,  M = mat(conj(q))
+// z_is_index: the z moment gm[i][2] holds sum gs_i * cf (grid index units, column kernels) instead of
+// sum gs_i * (z - t_z) (point-list kernel).
+SQ_HD void finalize_sample(const Sample& S, const Grid& g, const double* acc, double scale, bool z_is_index,
+                           double* grad12) {
+    const double* gs = acc; const double* gm = acc + 3; const double* wa = acc + 12; const double* ge = acc + 15;
+    double gM[9];
+    for (int i = 0; i < 3; ++i) {
+        const double ia = 1.0 / S.a[i];
+        gM[3 * i + 0] = 2.0 * ia * gm[3 * i + 0];
+        gM[3 * i + 1] = 2.0 * ia * gm[3 * i + 1];
+        gM[3 * i + 2] = 2.0 * ia * (z_is_index ? g.step * gm[3 * i + 2] - S.t[2] * gs[i] : gm[3 * i + 2]);
+    }
+    for (int i = 0; i < 3; ++i) grad12[i] = -2.0 * wa[i] / S.a[i] * S.mask[i] * scale;
+    grad12[3] = kLn2 * ge[0] * S.mask[3] * scale;
+    grad12[4] = kLn2 * ge[1] * S.mask[4] * scale;
+    for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+        for (int i = 0; i < 3; ++i) s += S.Ms[3 * i + j] * gs[i];
+        grad12[5 + j] = -2.0 * s * S.mask[5 + j] * scale;
+    }
+    // M = mat(conj(q)):  M00=1-2(y2+z2) M01=2xy+2zw M02=2xz-2yw / M10=2xy-2zw M11=1-2(x2+z2) M12=2yz+2xw /
+    //                    M20=2xz+2yw M21=2yz-2xw M22=1-2(x2+y2)
+    const double x = S.q[0], y = S.q[1], z = S.q[2], w = S.q[3];
+    const double g00 = gM[0], g01 = gM[1], g02 = gM[2], g10 = gM[3], g11 = gM[4], g12 = gM[5],
+                 g20 = gM[6], g21 = gM[7], g22 = gM[8];
+    grad12[8]  = scale * 2.0 * (y * (g01 + g10) + z * (g02 + g20) + w * (g12 - g21) - 2.0 * x * (g11 + g22));
+    grad12[9]  = scale * 2.0 * (x * (g01 + g10) + z * (g12 + g21) + w * (g20 - g02) - 2.0 * y * (g00 + g22));
+    grad12[10] = scale * 2.0 * (x * (g02 + g20) + y * (g12 + g21) + w * (g01 - g10) - 2.0 * z * (g00 + g11));
+    grad12[11] = scale * 2.0 * (z * (g01 - g10) + y * (g20 - g02) + x * (g12 - g21));
+}
+
+// ---------------------------------------------------------------- ImplicitLoss: one column
+// classes.py:274-279.  Walk from the camera side (z index n-1) down to 0:
+//   o_c = sigmoid(k (1 - F_c)),  cs_c = running sum of o,  T_c = exp(-tau cs_c),  depth = 1 - sum_c T_c / n.
+// d depth / d o_c = (tau/n) S_c with the suffix sum S_c = sum_{c' at or behind c} T_c'.  S_c is only known at the
+// end of the walk, so gradient terms are accumulated twice -- sum x and sum P_c x with P_c the sum of T in front
+// of c -- and combined as U sum x - sum P x when the column ends.  P and U start at the first point that carries
+// gradient, which keeps the subtraction well conditioned.
+struct ImplicitParams { float kl; float tl; float tau; };     // k log2(e), tau log2(e), tau
+
+struct ColGrad {       // two-moment accumulators of one column
+    float gs0[3], gs1[3], gz0[3], gz1[3], wa0[3], wa1[3], ge0[2], ge1[2];
+};
+
+#if defined(__CUDA_ARCH__)
+#define SQ_ANY(p) __any_sync(0xffffffffu, (p))
+#else
+#define SQ_ANY(p) (p)
+#endif
+
+// Returns the rendered depth.  1 - sum T / n cannot resolve depths below ~1e-7 in fp32, but the sign of
+// (depth - target) on silhouette pixels (target exactly 0, depth 1e-16..1e-7 in the fp64 reference) decides whether
+// the column's gradient counts, and those columns carry k-amplified gradient.  So the first-order sum
+// (tau/n) sum_c cs_c is carried along and used when the depth is tiny (relative error < 0.4% there).
+template <bool BWD>
+SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams& P,
+                            const float* bh, const float* bl, float* colgrad11) {
+    float cs = 0.f, tsum = 0.f, psh = 0.f, cssum = 0.f;
+    bool seen = false;
+    ColGrad cg;
+    if (BWD) {
+        for (int i = 0; i < 3; ++i) cg.gs0[i] = cg.gs1[i] = cg.gz0[i] = cg.gz1[i] = cg.wa0[i] = cg.wa1[i] = 0.f;
+        cg.ge0[0] = cg.ge0[1] = cg.ge1[0] = cg.ge1[1] = 0.f;
+    }
+    float cfi = (float)(g.n - 1);
+    for (int c = g.n - 1; c >= 0; --c, cfi -= 1.0f) {
+        const float cf = (c == 0) ? S.cf0 : cfi;       // plane "index": exact small integers, z0/step for plane 0
+        const float sx = fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]);
+        const float sy = fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]);
+        const float sz = fmaf(cf, S.dh[2], bh[2]) + fmaf(cf, S.dl[2], bl[2]);
+        Fwd f;
+        point_forward<true>(S, sx, sy, sz, f);
+        float x, eo;
+        const float o = occupancy(f.F, P.kl, x, eo);
+        cs += o;
+        cssum += cs;
+        const float T = ex2(-P.tl * cs);
+        if (BWD) {
+            const bool active = fabsf(x) < kActive;
+            if (SQ_ANY(active)) {
+                // do/dF = -k o (1-o) = -k eo o^2 ; the -k is applied in finalize
+                const float W = active ? eo * o * o : 0.0f;
+                Fwd fa = f;
+                if (!active) fwd_neutral(fa);       // keep inactive lanes finite
+                Bwd b;
+                point_backward(fa, W, b);
+                seen = seen || active;
+                const float pp = psh;       // T in front of this point (since the first active one)
+                for (int i = 0; i < 3; ++i) {
+                    cg.gs0[i] += b.gs[i];            cg.gs1[i] = fmaf(pp, b.gs[i], cg.gs1[i]);
+                    const float gz = b.gs[i] * cf;
+                    cg.gz0[i] += gz;                 cg.gz1[i] = fmaf(pp, gz, cg.gz1[i]);
+                    cg.wa0[i] += b.wa[i];            cg.wa1[i] = fmaf(pp, b.wa[i], cg.wa1[i]);
+                }
+                for (int i = 0; i < 2; ++i) { cg.ge0[i] += b.ge[i]; cg.ge1[i] = fmaf(pp, b.ge[i], cg.ge1[i]); }
+            }
+            psh += seen ? T : 0.0f;
+        }
+        tsum += T;
+    }
+    if (BWD) {
+        const float U = psh;
+        for (int i = 0; i < 3; ++i) {
+            colgrad11[i]     = fmaf(U, cg.gs0[i], -cg.gs1[i]);
+            colgrad11[3 + i] = fmaf(U, cg.gz0[i], -cg.gz1[i]);
+            colgrad11[6 + i] = fmaf(U, cg.wa0[i], -cg.wa1[i]);
+        }
+        colgrad11[9]  = fmaf(U, cg.ge0[0], -cg.ge1[0]);
+        colgrad11[10] = fmaf(U, cg.ge0[1], -cg.ge1[1]);
+    }
+    const float inv_n = 1.0f / (float)g.n;
+    const float depth = fmaf(-tsum, inv_n, 1.0f);
+    return depth < 1e-4f ? P.tau * cssum * inv_n : depth;
+}
+
+// fold one finished column (weight w = sign(depth - target), coordinates relative to t) into the thread totals
+SQ_HD void implicit_fold(Acc& acc, const float* colgrad11, float w, float dx, float dy) {
+    for (int i = 0; i < 3; ++i) {
+        const float gsi = w * colgrad11[i];
+        acc.gs[i] += gsi;
+        acc.gm[3 * i + 0] = fmaf(gsi, dx, acc.gm[3 * i + 0]);
+        acc.gm[3 * i + 1] = fmaf(gsi, dy, acc.gm[3 * i + 1]);
+        acc.gm[3 * i + 2] = fmaf(w, colgrad11[3 + i], acc.gm[3 * i + 2]);
+        acc.wa[i] = fmaf(w, colgrad11[6 + i], acc.wa[i]);
+    }
+    acc.ge[0] = fmaf(w, colgrad11[9], acc.ge[0]);
+    acc.ge[1] = fmaf(w, colgrad11[10], acc.ge[1]);
+}
+
+// ---------------------------------------------------------------- ExplicitLoss: one column
+// classes.py:187-198: o = sigmoid(5 (1 - F)) for the true and the predicted SQ, loss = 100 mean (o_t - o_p)^2.
+// Returns sum_c (o_t - o_p)^2 over the column and accumulates d/d(pred) terms weighted by (o_t - o_p).
+template <bool BWD>
+SQ_HD float explicit_column(const Sample& St, const Sample& Sp, const Grid& g, float kl,
+                            const float* bht, const float* blt, const float* bhp, const float* blp,
+                            float dx, float dy, Acc& acc) {
+    float sq = 0.f;
+    float gs[3] = {0.f, 0.f, 0.f}, gz[3] = {0.f, 0.f, 0.f};
+    float cfi = (float)(g.n - 1);
+    for (int c = g.n - 1; c >= 0; --c, cfi -= 1.0f) {
+        const float cf = (c == 0) ? Sp.cf0 : cfi;
+        Fwd ft, fp;
+        point_forward<true>(St, fmaf(cf, St.dh[0], bht[0]) + fmaf(cf, St.dl[0], blt[0]),
+                                fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
+                                fmaf(cf, St.dh[2], bht[2]) + fmaf(cf, St.dl[2], blt[2]), ft);
+        point_forward<true>(Sp, fmaf(cf, Sp.dh[0], bhp[0]) + fmaf(cf, Sp.dl[0], blp[0]),
+                                fmaf(cf, Sp.dh[1], bhp[1]) + fmaf(cf, Sp.dl[1], blp[1]),
+                                fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]), fp);
+        float xt, et, xp, ep;
+        const float ot = occupancy(ft.F, kl, xt, et);
+        const float op = occupancy(fp.F, kl, xp, ep);
+        const float d = ot - op;
+        sq = fmaf(d, d, sq);
+        if (BWD) {
+            const bool active = fabsf(xp) < kActive;
+            if (SQ_ANY(active)) {
+                // d/dF_p of (o_t - o_p)^2 = 2 d * k o_p (1 - o_p); constants 2, k applied in finalize
+                const float W = active ? d * ep * op * op : 0.0f;
+                Fwd fa = fp;
+                if (!active) fwd_neutral(fa);
+                Bwd b;
+                point_backward(fa, W, b);
+                for (int i = 0; i < 3; ++i) {
+                    gs[i] += b.gs[i];
+                    gz[i] = fmaf(b.gs[i], cf, gz[i]);
+                    acc.wa[i] += b.wa[i];
+                }
+                acc.ge[0] += b.ge[0];
+                acc.ge[1] += b.ge[1];
+            }
+        }
+    }
+    if (BWD) {
+        for (int i = 0; i < 3; ++i) {
+            acc.gs[i] += gs[i];
+            acc.gm[3 * i + 0] = fmaf(gs[i], dx, acc.gm[3 * i + 0]);
+            acc.gm[3 * i + 1] = fmaf(gs[i], dy, acc.gm[3 * i + 1]);
+            acc.gm[3 * i + 2] += gz[i];
+        }
+    }
+    return sq;
+}
+
+// ---------------------------------------------------------------- IoU: one column
+// classes.py:398-438: no clamp, no fix-up; inside <=> F <= 1 <=> e1 * lg2(G) <= 0.  Points whose decision is
+// within `margin` of the boundary are re-evaluated in fp64 with the reference's own operation order so the
+// voxel counts match the fp64 reference exactly (DESIGN.md "IoU exactness").
+SQ_HD bool inside_exact(const Sample& S, const Grid& g, int ia, int ib, int ic) {
+    const double gx = grid_coord(g, ia), gy = grid_coord(g, ib), gz = grid_coord(g, ic);
+    double s[3];
+    for (int i = 0; i < 3; ++i) {
+        const double r = S.M[3 * i] * gx + S.M[3 * i + 1] * gy + S.M[3 * i + 2] * gz;
+        const double tr = S.M[3 * i] * S.t[0] + S.M[3 * i + 1] * S.t[1] + S.M[3 * i + 2] * S.t[2];
+        s[i] = (r - tr) / S.a[i];
+    }
+    const double A = pow(s[0] * s[0], 1.0 / S.e[1]), B = pow(s[1] * s[1], 1.0 / S.e[1]), C = pow(s[2] * s[2], 1.0 / S.e[0]);
+    const double F = pow(pow(A + B, S.e[1] / S.e[0]) + C, S.e[0]);
+    return F <= 1.0;
+}
+
+SQ_HD float log2F(const Sample& S, float sx, float sy, float sz) {
+    Fwd f;
+    point_forward<false>(S, sx, sy, sz, f);
+    return S.e1 * f.lG;
+}
+
+constexpr float kIoUMargin = 2e-4f;     // |log2 F| below which the fp32 decision is not trusted
+
+SQ_HD void iou_column(const Sample& St, const Sample& Sp, const Grid& g, int ia, int ib,
+                      const float* bht, const float* blt, const float* bhp, const float* blp,
+                      unsigned& inter, unsigned& uni) {
+    float cfi = (float)(g.n - 1);
+    for (int c = g.n - 1; c >= 0; --c, cfi -= 1.0f) {
+        const float cf = (c == 0) ? Sp.cf0 : cfi;
+        const float yt = log2F(St, fmaf(cf, St.dh[0], bht[0]) + fmaf(cf, St.dl[0], blt[0]),
+                                   fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
+                                   fmaf(cf, St.dh[2], bht[2]) + fmaf(cf, St.dl[2], blt[2]));
+        const float yp = log2F(Sp, fmaf(cf, Sp.dh[0], bhp[0]) + fmaf(cf, Sp.dl[0], blp[0]),
+                                   fmaf(cf, Sp.dh[1], bhp[1]) + fmaf(cf, Sp.dl[1], blp[1]),
+                                   fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]));
+        bool it = yt <= 0.f, ip = yp <= 0.f;
+        if (!(fabsf(yt) > kIoUMargin)) it = inside_exact(St, g, ia, ib, c);      // also catches NaN
+        if (!(fabsf(yp) > kIoUMargin)) ip = inside_exact(Sp, g, ia, ib, c);
+        inter += (it && ip) ? 1u : 0u;
+        uni += (it || ip) ? 1u : 0u;
+    }
+}
+
+// ---------------------------------------------------------------- LeastSquares: one point
+// classes.py:322-355: (sqrt(a1 a2 a3) (F - 1))^2 at a back-projected depth pixel (x, y, z).  Returns the squared
+// term without the a1 a2 a3 factor; accumulates d/dF-weighted terms.  The a-gradient of the prefactor is added in
+// finalize from the returned sum.
+template <bool BWD>
+SQ_HD float lsq_point(const Sample& S, float px, float py, float pz, Acc& acc) {
+    const double dx = (double)px - S.t[0], dy = (double)py - S.t[1], dz = (double)pz - S.t[2];
+    float s[3];
+    for (int i = 0; i < 3; ++i) s[i] = (float)(S.Ms[3 * i] * dx + S.Ms[3 * i + 1] * dy + S.Ms[3 * i + 2] * dz);
+    Fwd f;
+    point_forward<true>(S, s[0], s[1], s[2], f);
+    const float r = f.F - 1.0f;
+    if (BWD) {
+        // d/dF of (F-1)^2 = 2 (F-1); the 2 and a1 a2 a3 are applied in finalize
+        Fwd fa = f;
+        const bool ok = f.F < 1e18f;
+        if (!ok) fwd_neutral(fa);
+        Bwd b;
+        point_backward(fa, ok ? r : 0.f, b);
+        const float fdx = (float)dx, fdy = (float)dy, fdz = (float)dz;
+        for (int i = 0; i < 3; ++i) {
+            acc.gs[i] += b.gs[i];
+            acc.gm[3 * i + 0] = fmaf(b.gs[i], fdx, acc.gm[3 * i + 0]);
+            acc.gm[3 * i + 1] = fmaf(b.gs[i], fdy, acc.gm[3 * i + 1]);
+            acc.gm[3 * i + 2] = fmaf(b.gs[i], fdz, acc.gm[3 * i + 2]);
+            acc.wa[i] += b.wa[i];
+        }
+        acc.ge[0] += b.ge[0];
+        acc.ge[1] += b.ge[1];
+    }
+    return r * r;
+}
+
+}  // namespace sq

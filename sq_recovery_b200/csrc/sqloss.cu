@@ -1,0 +1,700 @@
+// libsqloss: CUDA kernels (sm_100a) and the C ABI declared in include/sqloss.h.
+//
+// Kernel plan: every loss is  prep -> column kernel -> finalize, all on the caller's stream.
+//   prep      one thread per parameter row: clamp, rotation, scaled rows, exponents, in fp64 -> Sample (scratch)
+//   column    one thread per grid column (x, y) walking z; grid points are generated from indices, nothing
+//             per-point touches HBM; per-thread sums -> warp shuffles -> shared memory -> one partial row per block
+//   finalize  one warp per sample: fixed-order fp64 sum of the partial rows, Jacobians to the 12 parameters,
+//             per-sample loss; the last block to finish averages the batch (fixed order, so results are
+//             bit-reproducible run to run)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/sqloss.h"
+#include "sq_core.cuh"
+
+using namespace sq;
+
+namespace {
+
+constexpr int kThreads = 256;            // column-kernel block size
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxCpt = 2;               // columns per thread and work item
+
+// ------------------------------------------------------------------------------------------------ layout
+// Column slots of one sample.  When n is a multiple of 8 a warp owns an 8(x) x 4(y) patch, which keeps the lanes of
+// a warp at similar depth along z (the backward is entered per warp); otherwise slots are the n*n columns in
+// x-fastest order.  Slots beyond n*n (last block only) are masked.
+struct Layout {
+    int n, patched, slots, cpt, items_per_sample;
+};
+
+__host__ __device__ inline Layout make_layout(int n) {
+    Layout L;
+    L.n = n;
+    L.patched = (n % 8 == 0);
+    L.slots = n * n;
+    L.cpt = (L.slots + kThreads - 1) / kThreads;
+    if (L.cpt > kMaxCpt) L.cpt = kMaxCpt;
+    const int per_item = L.cpt * kThreads;
+    L.items_per_sample = (L.slots + per_item - 1) / per_item;
+    return L;
+}
+
+__device__ __forceinline__ bool slot_to_xy(const Layout& L, int slot, int& ia, int& ib) {
+    if (slot >= L.slots) { ia = 0; ib = 0; return false; }
+    if (L.patched) {
+        const int patch = slot >> 5, lane = slot & 31, pw = L.n >> 3;
+        ia = ((patch % pw) << 3) + (lane & 7);
+        ib = ((patch / pw) << 2) + (lane >> 3);
+    } else {
+        ia = slot % L.n;
+        ib = slot / L.n;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ scratch
+struct Scratch {
+    Sample* pred;          // [batch]
+    Sample* tru;           // [batch]
+    float* partials;       // [batch * items_per_sample][kAccN]
+    double* per_sample;    // [batch]
+    unsigned long long* counts;   // [batch][2] (IoU)
+    unsigned int* ticket;  // [1]
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
+    const Layout L = make_layout(n > 0 ? n : 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_pred = take(sizeof(Sample) * (size_t)batch);
+    const size_t o_true = take(sizeof(Sample) * (size_t)batch);
+    // partial rows: the column kernels use items_per_sample rows per sample, the point-list kernel one row per
+    // 256 pixels; reserve the larger (cpt = 1) count
+    const size_t rows = (size_t)batch * ((L.slots + kThreads - 1) / kThreads);
+    const size_t o_part = take(sizeof(float) * kAccN * rows);
+    const size_t o_ps = take(sizeof(double) * (size_t)batch);
+    const size_t o_cnt = take(sizeof(unsigned long long) * 2 * (size_t)batch);
+    const size_t o_tick = take(sizeof(unsigned int) * 4);
+    if (s) {
+        s->pred = reinterpret_cast<Sample*>(base + o_pred);
+        s->tru = reinterpret_cast<Sample*>(base + o_true);
+        s->partials = reinterpret_cast<float*>(base + o_part);
+        s->per_sample = reinterpret_cast<double*>(base + o_ps);
+        s->counts = reinterpret_cast<unsigned long long*>(base + o_cnt);
+        s->ticket = reinterpret_cast<unsigned int*>(base + o_tick);
+    }
+    return off;
+}
+
+// ------------------------------------------------------------------------------------------------ prep
+__global__ void prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample* out,
+                            unsigned int* ticket, unsigned long long* counts) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0 && ticket) *ticket = 0u;
+    if (b < batch) {
+        double p[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+            p[i] = dtype == SQ_F64 ? static_cast<const double*>(params)[12 * (size_t)b + i]
+                                   : (double)static_cast<const float*>(params)[12 * (size_t)b + i];
+        Sample S;
+        prep_sample(p, clamp != 0, g, S);
+        out[b] = S;
+        if (counts) { counts[2 * b] = 0ull; counts[2 * b + 1] = 0ull; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ block reduce
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// per-thread Acc -> one row of kAccN floats per block
+__device__ __forceinline__ void block_reduce_store(const Acc& a, float (*red)[kAccN], float* row) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float v[kAccN];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { v[i] = a.gs[i]; v[12 + i] = a.wa[i]; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) v[3 + i] = a.gm[i];
+    v[15] = a.ge[0]; v[16] = a.ge[1]; v[17] = a.loss;
+#pragma unroll
+    for (int i = 0; i < kAccN; ++i) {
+        const float s = warp_sum(v[i]);
+        if (lane == 0) red[warp][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < kAccN) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+        row[threadIdx.x] = s;
+    }
+}
+
+__device__ __forceinline__ void load_sample(Sample* dst, const Sample* src) {
+    static_assert(sizeof(Sample) % 4 == 0, "Sample must be word-copyable");
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(Sample) / 4); i += blockDim.x) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------------ ImplicitLoss
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads, 2)
+implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitParams P,
+                const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
+                const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
+    __shared__ Sample S;
+    __shared__ float red[kWarps][kAccN];
+    const int item = blockIdx.x;
+    const int b = item / L.items_per_sample, chunk = item - b * L.items_per_sample;
+    load_sample(&S, samples + b);
+    __syncthreads();
+
+    Acc acc;
+    acc_zero(acc);
+    for (int k = 0; k < L.cpt; ++k) {
+        const int slot = (chunk * L.cpt + k) * kThreads + threadIdx.x;
+        int ia, ib;
+        const bool valid = slot_to_xy(L, slot, ia, ib);
+        float bh[3], bl[3], cg[11];
+        column_base(S, g, ia, ib, bh, bl);
+        const float depth = implicit_column<BWD>(S, g, P, bh, bl, cg);
+        const int row = g.n - 1 - ib, col = ia;            // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
+        if (valid) {
+            if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
+            if (target) {
+                const float tv = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
+                const float diff = depth - tv;
+                acc.loss += fabsf(diff);
+                if (BWD) {
+                    const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                    implicit_fold(acc, cg, w, (float)(grid_coord(g, ia) - S.t[0]), (float)(grid_coord(g, ib) - S.t[1]));
+                }
+            }
+        }
+    }
+    block_reduce_store(acc, red, partials + (size_t)item * kAccN);
+}
+
+// ------------------------------------------------------------------------------------------------ ExplicitLoss
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads, 2)
+explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, float kl,
+                float* __restrict__ partials) {
+    __shared__ Sample St, Sp;
+    __shared__ float red[kWarps][kAccN];
+    const int item = blockIdx.x;
+    const int b = item / L.items_per_sample, chunk = item - b * L.items_per_sample;
+    load_sample(&St, tru + b);
+    load_sample(&Sp, pred + b);
+    __syncthreads();
+
+    Acc acc;
+    acc_zero(acc);
+    for (int k = 0; k < L.cpt; ++k) {
+        const int slot = (chunk * L.cpt + k) * kThreads + threadIdx.x;
+        int ia, ib;
+        const bool valid = slot_to_xy(L, slot, ia, ib);
+        float bht[3], blt[3], bhp[3], blp[3];
+        column_base(St, g, ia, ib, bht, blt);
+        column_base(Sp, g, ia, ib, bhp, blp);
+        Acc col;
+        acc_zero(col);
+        const float dx = (float)(grid_coord(g, ia) - Sp.t[0]), dy = (float)(grid_coord(g, ib) - Sp.t[1]);
+        const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, dx, dy, col);
+        if (valid) {
+            acc.loss += sq;
+            if (BWD) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { acc.gs[i] += col.gs[i]; acc.wa[i] += col.wa[i]; }
+#pragma unroll
+                for (int i = 0; i < 9; ++i) acc.gm[i] += col.gm[i];
+                acc.ge[0] += col.ge[0]; acc.ge[1] += col.ge[1];
+            }
+        }
+    }
+    block_reduce_store(acc, red, partials + (size_t)item * kAccN);
+}
+
+// ------------------------------------------------------------------------------------------------ IoU
+__global__ void __launch_bounds__(kThreads, 2)
+iou_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L,
+           unsigned long long* __restrict__ counts) {
+    __shared__ Sample St, Sp;
+    __shared__ unsigned int red[kWarps][2];
+    const int item = blockIdx.x;
+    const int b = item / L.items_per_sample, chunk = item - b * L.items_per_sample;
+    load_sample(&St, tru + b);
+    load_sample(&Sp, pred + b);
+    __syncthreads();
+    unsigned inter = 0, uni = 0;
+    for (int k = 0; k < L.cpt; ++k) {
+        const int slot = (chunk * L.cpt + k) * kThreads + threadIdx.x;
+        int ia, ib;
+        const bool valid = slot_to_xy(L, slot, ia, ib);
+        float bht[3], blt[3], bhp[3], blp[3];
+        column_base(St, g, ia, ib, bht, blt);
+        column_base(Sp, g, ia, ib, bhp, blp);
+        unsigned i = 0, u = 0;
+        iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, i, u);
+        if (valid) { inter += i; uni += u; }
+    }
+    inter = __reduce_add_sync(0xffffffffu, inter);
+    uni = __reduce_add_sync(0xffffffffu, uni);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp][0] = inter; red[warp][1] = uni; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned long long s = 0;
+        for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+        atomicAdd(counts + 2 * b + threadIdx.x, s);       // integer atomics: order-independent, exact
+    }
+}
+
+__global__ void iou_export_kernel(const unsigned long long* counts, int batch, long long* inter, long long* uni) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) { inter[b] = (long long)counts[2 * b]; uni[b] = (long long)counts[2 * b + 1]; }
+}
+
+// ------------------------------------------------------------------------------------------------ LeastSquares
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads)
+lsq_kernel(const Sample* __restrict__ samples, int R, int items_per_sample,
+           const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
+           const int* __restrict__ col_off, float* __restrict__ partials) {
+    __shared__ Sample S;
+    __shared__ float red[kWarps][kAccN];
+    const int item = blockIdx.x;
+    const int b = item / items_per_sample, chunk = item - b * items_per_sample;
+    load_sample(&S, samples + b);
+    __syncthreads();
+    Acc acc;
+    acc_zero(acc);
+    const int pix = chunk * kThreads + threadIdx.x;
+    if (pix < R * R) {
+        const int row = pix / R, col = pix - row * R;
+        const float v = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
+        if (v > 0.f) {                                     // classes.py:363-368 (fp32 arithmetic, like the reference)
+            const float px = (float)col / (float)R, py = 1.0f - (float)row / (float)R;
+            acc.loss = lsq_point<BWD>(S, px, py, v, acc);
+        }
+    }
+    block_reduce_store(acc, red, partials + (size_t)item * kAccN);
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+enum { FIN_IMPLICIT = 0, FIN_EXPLICIT = 1, FIN_LSQ = 2 };
+
+// one warp per sample; the last block averages the batch
+template <int KIND>
+__global__ void __launch_bounds__(32)
+finalize_kernel(const Sample* __restrict__ samples, Grid g, int batch, int items_per_sample,
+                const float* __restrict__ partials, double loss_norm, double grad_scale,
+                int dtype, void* __restrict__ grad, double* __restrict__ per_sample,
+                double* __restrict__ per_sample_user, double* __restrict__ loss_out, unsigned int* ticket) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    __shared__ double acc[kAccN];
+    if (lane < kAccN) {
+        double s = 0.0;
+        const float* p = partials + (size_t)b * items_per_sample * kAccN + lane;
+        for (int j = 0; j < items_per_sample; ++j) s += (double)p[(size_t)j * kAccN];
+        acc[lane] = s;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const Sample& S = samples[b];
+        double ls = acc[17] * loss_norm;
+        double vol = 1.0;
+        if (KIND == FIN_LSQ) { vol = S.a[0] * S.a[1] * S.a[2]; ls *= vol; }
+        per_sample[b] = ls;
+        if (per_sample_user) per_sample_user[b] = ls;
+        if (grad) {
+            double gr[12];
+            finalize_sample(S, g, acc, grad_scale * vol, KIND != FIN_LSQ, gr);
+            if (KIND == FIN_LSQ)
+                for (int i = 0; i < 3; ++i) gr[i] += S.mask[i] * (vol / S.a[i]) * acc[17] / (double)batch;
+            for (int i = 0; i < 12; ++i) {
+                if (dtype == SQ_F64) static_cast<double*>(grad)[12 * (size_t)b + i] = gr[i];
+                else static_cast<float*>(grad)[12 * (size_t)b + i] = (float)gr[i];
+            }
+        }
+    }
+    // batch mean by the last block to arrive, in index order
+    __shared__ unsigned int last;
+    __syncwarp();
+    if (lane == 0) { __threadfence(); last = atomicAdd(ticket, 1u); }
+    __syncwarp();
+    if (last == (unsigned)batch - 1u) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = lane; i < batch; i += 32) s += *((volatile double*)(per_sample + i));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && loss_out) *loss_out = s / (double)batch;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ field
+__global__ void __launch_bounds__(256)
+field_kernel(const Sample* __restrict__ samples, Grid g, int batch, int mode, float kl, float* __restrict__ out) {
+    const size_t n = g.n, per = n * n * n;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per * batch) return;
+    const int b = (int)(idx / per);
+    size_t r = idx - (size_t)b * per;
+    const int ia = (int)(r / (n * n)); r -= (size_t)ia * n * n;
+    const int ib = (int)(r / n), ic = (int)(r - (size_t)ib * n);
+    const Sample& S = samples[b];
+    const double dx = grid_coord(g, ia) - S.t[0], dy = grid_coord(g, ib) - S.t[1], dz = grid_coord(g, ic) - S.t[2];
+    float s[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s[i] = (float)(S.Ms[3 * i] * dx + S.Ms[3 * i + 1] * dy + S.Ms[3 * i + 2] * dz);
+    Fwd f;
+    float v;
+    if (mode == 0) { point_forward<false>(S, s[0], s[1], s[2], f); v = f.F; }
+    else { point_forward<true>(S, s[0], s[1], s[2], f); float x, eo; v = occupancy(f.F, kl, x, eo); }
+    out[idx] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+#define SQ_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+// One-shot event pair around the next column kernel launched by this thread (sq_profile_events()).
+thread_local cudaEvent_t t_ev_before = nullptr, t_ev_after = nullptr;
+
+struct ColumnKernelTimer {
+    cudaStream_t st; cudaEvent_t after;
+    explicit ColumnKernelTimer(cudaStream_t s) : st(s), after(t_ev_after) {
+        if (t_ev_before) cudaEventRecord(t_ev_before, st);
+        t_ev_before = nullptr; t_ev_after = nullptr;
+    }
+    ~ColumnKernelTimer() { if (after) cudaEventRecord(after, st); }
+};
+
+int check_scratch(int batch, int n, void* scratch, size_t bytes, Scratch* s) {
+    if (batch <= 0 || n <= 0) return (int)cudaErrorInvalidValue;
+    const size_t need = scratch_layout(batch, n, nullptr, nullptr);
+    if (!scratch || bytes < need) return (int)cudaErrorInvalidValue;
+    scratch_layout(batch, n, static_cast<char*>(scratch), s);
+    return 0;
+}
+
+int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid& g, Sample* out,
+                unsigned int* ticket, unsigned long long* counts, cudaStream_t st) {
+    if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
+    prep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* sq_version(void) { return "sqloss-b200 0.1 (sm_100a)"; }
+
+const char* sq_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
+
+int sq_device_sm_count(int device, int* sm_count) {
+    return (int)cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device);
+}
+
+void sq_profile_events(void* ev_before, void* ev_after) {
+    t_ev_before = static_cast<cudaEvent_t>(ev_before);
+    t_ev_after = static_cast<cudaEvent_t>(ev_after);
+}
+
+size_t sq_scratch_bytes(int batch, int n) {
+    if (batch <= 0 || n <= 0) return 0;
+    return scratch_layout(batch, n, nullptr, nullptr);
+}
+
+int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double step, double z0,
+                     const float* target, long long target_stride_b, const int* row_off, const int* col_off,
+                     float tau, float sharpness, double* loss_out, double* per_sample, void* grad_pred,
+                     float* depth_out, void* scratch, size_t scratch_bytes, sq_stream_t stream) {
+    Scratch s;
+    int rc = check_scratch(batch, n, scratch, scratch_bytes, &s);
+    if (rc) return rc;
+    if (target && (!row_off || !col_off)) return (int)cudaErrorInvalidValue;
+    if (grad_pred && !target) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Grid g{n, step, z0};
+    const Layout L = make_layout(n);
+    const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, tau};
+    rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
+    if (rc) return rc;
+    const int items = batch * L.items_per_sample;
+    {
+        ColumnKernelTimer timer(st);
+        if (grad_pred)
+            implicit_kernel<true><<<items, kThreads, 0, st>>>(s.pred, g, L, P, target, target_stride_b, row_off,
+                                                              col_off, s.partials, depth_out);
+        else
+            implicit_kernel<false><<<items, kThreads, 0, st>>>(s.pred, g, L, P, target, target_stride_b, row_off,
+                                                               col_off, s.partials, depth_out);
+    }
+    SQ_TRY(cudaGetLastError());
+    if (target) {
+        const double nn = (double)n * n;
+        finalize_kernel<FIN_IMPLICIT><<<batch, 32, 0, st>>>(
+            s.pred, g, batch, L.items_per_sample, s.partials, 1.0 / nn,
+            -(double)sharpness * (double)tau / (nn * n * (double)batch), pred_dtype, grad_pred, s.per_sample,
+            per_sample, loss_out, s.ticket);
+        SQ_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype, int batch, int n, double step,
+                     double z0, float sharpness, float mult, double* loss_out, double* per_sample, void* grad_pred,
+                     void* scratch, size_t scratch_bytes, sq_stream_t stream) {
+    Scratch s;
+    int rc = check_scratch(batch, n, scratch, scratch_bytes, &s);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Grid g{n, step, z0};
+    const Layout L = make_layout(n);
+    rc = launch_prep(true_params, params_dtype, batch, true, g, s.tru, nullptr, nullptr, st);
+    if (rc) return rc;
+    rc = launch_prep(pred, params_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
+    if (rc) return rc;
+    const int items = batch * L.items_per_sample;
+    {
+        ColumnKernelTimer timer(st);
+        if (grad_pred) explicit_kernel<true><<<items, kThreads, 0, st>>>(s.tru, s.pred, g, L, sharpness * kLog2e, s.partials);
+        else explicit_kernel<false><<<items, kThreads, 0, st>>>(s.tru, s.pred, g, L, sharpness * kLog2e, s.partials);
+    }
+    SQ_TRY(cudaGetLastError());
+    const double n3 = (double)n * n * n;
+    finalize_kernel<FIN_EXPLICIT><<<batch, 32, 0, st>>>(
+        s.pred, g, batch, L.items_per_sample, s.partials, (double)mult / n3,
+        2.0 * (double)sharpness * (double)mult / (n3 * (double)batch), params_dtype, grad_pred, s.per_sample,
+        per_sample, loss_out, s.ticket);
+    SQ_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sq_iou_counts(const void* true_params, const void* pred, int params_dtype, int batch, int n, double step,
+                  double z0, long long* inter, long long* uni, void* scratch, size_t scratch_bytes,
+                  sq_stream_t stream) {
+    Scratch s;
+    int rc = check_scratch(batch, n, scratch, scratch_bytes, &s);
+    if (rc) return rc;
+    if (!inter || !uni) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Grid g{n, step, z0};
+    const Layout L = make_layout(n);
+    rc = launch_prep(true_params, params_dtype, batch, false, g, s.tru, nullptr, nullptr, st);
+    if (rc) return rc;
+    rc = launch_prep(pred, params_dtype, batch, false, g, s.pred, nullptr, s.counts, st);
+    if (rc) return rc;
+    {
+        ColumnKernelTimer timer(st);
+        iou_kernel<<<batch * L.items_per_sample, kThreads, 0, st>>>(s.tru, s.pred, g, L, s.counts);
+    }
+    SQ_TRY(cudaGetLastError());
+    iou_export_kernel<<<(batch + 127) / 128, 128, 0, st>>>(s.counts, batch, inter, uni);
+    SQ_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_size, const float* target,
+                     long long target_stride_b, const int* row_off, const int* col_off, double* loss_out,
+                     double* per_sample, void* grad_pred, void* scratch, size_t scratch_bytes, sq_stream_t stream) {
+    Scratch s;
+    int rc = check_scratch(batch, render_size, scratch, scratch_bytes, &s);
+    if (rc) return rc;
+    if (!target || !row_off || !col_off) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Grid g{2, 1.0, 0.0};     // the point list carries its own coordinates; the grid is unused
+    rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
+    if (rc) return rc;
+    const int R = render_size;
+    const int ips = (R * R + kThreads - 1) / kThreads;
+    if (grad_pred) lsq_kernel<true><<<batch * ips, kThreads, 0, st>>>(s.pred, R, ips, target, target_stride_b, row_off, col_off, s.partials);
+    else lsq_kernel<false><<<batch * ips, kThreads, 0, st>>>(s.pred, R, ips, target, target_stride_b, row_off, col_off, s.partials);
+    SQ_TRY(cudaGetLastError());
+    finalize_kernel<FIN_LSQ><<<batch, 32, 0, st>>>(s.pred, g, batch, ips, s.partials, 1.0, 2.0 / (double)batch,
+                                                   pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, s.ticket);
+    SQ_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sq_field(const void* params, int params_dtype, int batch, int n, double step, double z0, int mode,
+             float sharpness, float* out, void* scratch, size_t scratch_bytes, sq_stream_t stream) {
+    Scratch s;
+    int rc = check_scratch(batch, n, scratch, scratch_bytes, &s);
+    if (rc) return rc;
+    if (!out || (mode != 0 && mode != 1)) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Grid g{n, step, z0};
+    rc = launch_prep(params, params_dtype, batch, mode == 1, g, s.pred, nullptr, nullptr, st);
+    if (rc) return rc;
+    const size_t total = (size_t)batch * n * n * n;
+    field_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s.pred, g, batch, mode, sharpness * kLog2e, out);
+    SQ_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer API
+struct sq_ctx {
+    int device;
+    cudaStream_t stream;
+    char* dev; size_t dev_bytes;          // one device arena, carved per call
+    char* pin; size_t pin_bytes;          // pinned staging for results
+};
+
+static int ctx_reserve(sq_ctx* c, size_t dev_bytes, size_t pin_bytes) {
+    if (dev_bytes > c->dev_bytes) {
+        if (c->dev) SQ_TRY(cudaFree(c->dev));
+        c->dev = nullptr; c->dev_bytes = 0;
+        SQ_TRY(cudaMalloc(&c->dev, dev_bytes));
+        c->dev_bytes = dev_bytes;
+    }
+    if (pin_bytes > c->pin_bytes) {
+        if (c->pin) SQ_TRY(cudaFreeHost(c->pin));
+        c->pin = nullptr; c->pin_bytes = 0;
+        SQ_TRY(cudaMallocHost(&c->pin, pin_bytes));
+        c->pin_bytes = pin_bytes;
+    }
+    return 0;
+}
+
+int sq_ctx_create(int device, sq_ctx** out) {
+    if (!out) return (int)cudaErrorInvalidValue;
+    SQ_TRY(cudaSetDevice(device));
+    sq_ctx* c = new (std::nothrow) sq_ctx();
+    if (!c) return (int)cudaErrorMemoryAllocation;
+    c->device = device; c->dev = nullptr; c->dev_bytes = 0; c->pin = nullptr; c->pin_bytes = 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return (int)e; }
+    *out = c;
+    return 0;
+}
+
+void sq_ctx_destroy(sq_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->dev) cudaFree(c->dev);
+    if (c->pin) cudaFreeHost(c->pin);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// F.interpolate(mode="nearest") source index: min(floor(dst * (float)in / out), in - 1)
+static void nearest_offsets(int in, int out, int stride, int* off) {
+    const float scale = (float)in / (float)out;
+    for (int i = 0; i < out; ++i) {
+        int s = (int)floorf((float)i * scale);
+        if (s > in - 1) s = in - 1;
+        off[i] = s * stride;
+    }
+}
+
+int sq_implicit_loss_host(sq_ctx* c, const float* pred_host, int batch, int render_size, const float* images_host,
+                          int height, int width, float tau, float sharpness, double* loss_host, float* grad_host) {
+    if (!c || !pred_host || !images_host || batch <= 0 || render_size <= 0) return (int)cudaErrorInvalidValue;
+    SQ_TRY(cudaSetDevice(c->device));
+    const int R = render_size;
+    const size_t b_pred = align_up(sizeof(float) * 12 * (size_t)batch, 256);
+    const size_t b_img = align_up(sizeof(float) * (size_t)batch * height * width, 256);
+    const size_t b_off = align_up(sizeof(int) * 2 * (size_t)R, 256);
+    const size_t b_out = align_up(sizeof(double) + sizeof(float) * 12 * (size_t)batch, 256);
+    const size_t b_scr = sq_scratch_bytes(batch, R);
+    int rc = ctx_reserve(c, b_pred + b_img + b_off + b_out + b_scr, b_off + b_out);
+    if (rc) return rc;
+    char* d = c->dev;
+    float* d_pred = reinterpret_cast<float*>(d); d += b_pred;
+    float* d_img = reinterpret_cast<float*>(d); d += b_img;
+    int* d_off = reinterpret_cast<int*>(d); d += b_off;
+    double* d_loss = reinterpret_cast<double*>(d);
+    float* d_grad = reinterpret_cast<float*>(d + sizeof(double)); d += b_out;
+    void* d_scr = d;
+    int* h_off = reinterpret_cast<int*>(c->pin);
+    char* h_out = c->pin + b_off;
+    nearest_offsets(height, R, width, h_off);
+    nearest_offsets(width, R, 1, h_off + R);
+    SQ_TRY(cudaMemcpyAsync(d_pred, pred_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
+    SQ_TRY(cudaMemcpyAsync(d_img, images_host, sizeof(float) * (size_t)batch * height * width, cudaMemcpyHostToDevice, c->stream));
+    SQ_TRY(cudaMemcpyAsync(d_off, h_off, sizeof(int) * 2 * (size_t)R, cudaMemcpyHostToDevice, c->stream));
+    rc = sq_implicit_loss(d_pred, SQ_F32, batch, R, 1.0 / (double)(R - 1), 1e-4, d_img, (long long)height * width,
+                          d_off, d_off + R, tau, sharpness, d_loss, nullptr, grad_host ? d_grad : nullptr, nullptr,
+                          d_scr, b_scr, c->stream);
+    if (rc) return rc;
+    const size_t out_bytes = sizeof(double) + (grad_host ? sizeof(float) * 12 * (size_t)batch : 0);
+    SQ_TRY(cudaMemcpyAsync(h_out, d_loss, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    SQ_TRY(cudaStreamSynchronize(c->stream));
+    if (loss_host) memcpy(loss_host, h_out, sizeof(double));
+    if (grad_host) memcpy(grad_host, h_out + sizeof(double), sizeof(float) * 12 * (size_t)batch);
+    return 0;
+}
+
+int sq_explicit_loss_host(sq_ctx* c, const float* true_host, const float* pred_host, int batch, int render_size,
+                          double* loss_host, float* grad_host) {
+    if (!c || !true_host || !pred_host || batch <= 0 || render_size <= 0) return (int)cudaErrorInvalidValue;
+    SQ_TRY(cudaSetDevice(c->device));
+    // arange(0, 1 + step, step) of the reference: count the entries the way numpy does (ceil((stop-start)/step))
+    const double step = 1.0 / (double)render_size;
+    const int n = (int)ceil((1.0 + step) / step);
+    const size_t b_par = align_up(sizeof(float) * 12 * (size_t)batch, 256);
+    const size_t b_out = align_up(sizeof(double) + sizeof(float) * 12 * (size_t)batch, 256);
+    const size_t b_scr = sq_scratch_bytes(batch, n);
+    int rc = ctx_reserve(c, 2 * b_par + b_out + b_scr, b_out);
+    if (rc) return rc;
+    char* d = c->dev;
+    float* d_true = reinterpret_cast<float*>(d); d += b_par;
+    float* d_pred = reinterpret_cast<float*>(d); d += b_par;
+    double* d_loss = reinterpret_cast<double*>(d);
+    float* d_grad = reinterpret_cast<float*>(d + sizeof(double)); d += b_out;
+    SQ_TRY(cudaMemcpyAsync(d_true, true_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
+    SQ_TRY(cudaMemcpyAsync(d_pred, pred_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
+    rc = sq_explicit_loss(d_true, d_pred, SQ_F32, batch, n, step, 1e-4, 5.0f, 100.0f, d_loss, nullptr,
+                          grad_host ? d_grad : nullptr, d, b_scr, c->stream);
+    if (rc) return rc;
+    const size_t out_bytes = sizeof(double) + (grad_host ? sizeof(float) * 12 * (size_t)batch : 0);
+    SQ_TRY(cudaMemcpyAsync(c->pin, d_loss, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    SQ_TRY(cudaStreamSynchronize(c->stream));
+    if (loss_host) memcpy(loss_host, c->pin, sizeof(double));
+    if (grad_host) memcpy(grad_host, c->pin + sizeof(double), sizeof(float) * 12 * (size_t)batch);
+    return 0;
+}
+
+int sq_iou_counts_host(sq_ctx* c, const float* true_host, const float* pred_host, int batch, int render_size,
+                       long long* inter_host, long long* uni_host) {
+    if (!c || !true_host || !pred_host || !inter_host || !uni_host || batch <= 0 || render_size <= 1)
+        return (int)cudaErrorInvalidValue;
+    SQ_TRY(cudaSetDevice(c->device));
+    const int n = render_size;
+    const size_t b_par = align_up(sizeof(float) * 12 * (size_t)batch, 256);
+    const size_t b_out = align_up(sizeof(long long) * 2 * (size_t)batch, 256);
+    const size_t b_scr = sq_scratch_bytes(batch, n);
+    int rc = ctx_reserve(c, 2 * b_par + b_out + b_scr, b_out);
+    if (rc) return rc;
+    char* d = c->dev;
+    float* d_true = reinterpret_cast<float*>(d); d += b_par;
+    float* d_pred = reinterpret_cast<float*>(d); d += b_par;
+    long long* d_cnt = reinterpret_cast<long long*>(d); d += b_out;
+    SQ_TRY(cudaMemcpyAsync(d_true, true_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
+    SQ_TRY(cudaMemcpyAsync(d_pred, pred_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
+    rc = sq_iou_counts(d_true, d_pred, SQ_F32, batch, n, 1.0 / (double)(n - 1), 0.0, d_cnt, d_cnt + batch, d, b_scr, c->stream);
+    if (rc) return rc;
+    SQ_TRY(cudaMemcpyAsync(c->pin, d_cnt, sizeof(long long) * 2 * (size_t)batch, cudaMemcpyDeviceToHost, c->stream));
+    SQ_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(inter_host, c->pin, sizeof(long long) * (size_t)batch);
+    memcpy(uni_host, c->pin + sizeof(long long) * (size_t)batch, sizeof(long long) * (size_t)batch);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,301 @@
+"""torch.autograd.Function wrappers over the C ABI (include/sqloss.h).
+
+Each Function runs the fused forward+backward kernel once in ``forward`` and keeps d loss / d params for
+``backward``; under ``torch.no_grad()`` or when no input needs a gradient the forward-only kernel
+runs.  Everything is launched on torch's current stream; nothing here synchronises the host.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_scratch: Dict[Tuple[int, int], torch.Tensor] = {}
+_offsets: Dict[Tuple[int, int, int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"sq_recovery_b200: {what} must live on a CUDA device (got {t.device}); "
+                           "there is no CPU path in this package")
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _get_scratch(device: torch.device, batch: int, n: int) -> torch.Tensor:
+    """Per (device, stream) workspace, grown on demand and reused (stream-ordered, so reuse is safe)."""
+    need = _lib.lib().sq_scratch_bytes(batch, n)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(device))
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def _params(p: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Contiguous fp32 or fp64 copy of a (B,12) parameter tensor and its dtype tag."""
+    if p.dim() != 2 or p.shape[1] != 12:
+        raise ValueError(f"expected parameters of shape (B, 12), got {tuple(p.shape)}")
+    if p.dtype == torch.float64:
+        return p.detach().contiguous(), _lib.SQ_F64
+    return p.detach().float().contiguous(), _lib.SQ_F32
+
+
+def nearest_offsets(height: int, width: int, size: int, device: torch.device):
+    """Element offsets of the rows / columns F.interpolate(mode='nearest') samples (torch/classes.py:286, :359).
+
+    Derived from F.interpolate itself so the index rule is PyTorch's by construction.
+    """
+    key = (height, width, size, device.index if device.index is not None else -1)
+    hit = _offsets.get(key)
+    if hit is None:
+        rows = F.interpolate(torch.arange(height, dtype=torch.float32).view(1, 1, height, 1), size=(size, 1), mode="nearest")
+        cols = F.interpolate(torch.arange(width, dtype=torch.float32).view(1, 1, 1, width), size=(1, size), mode="nearest")
+        row_off = (rows.view(-1).to(torch.int32) * width).to(device)
+        col_off = cols.view(-1).to(torch.int32).to(device)
+        hit = (row_off, col_off)
+        _offsets[key] = hit
+    return hit
+
+
+def _image(true: torch.Tensor) -> torch.Tensor:
+    if true.dim() != 4 or true.shape[1] != 1:
+        raise ValueError(f"expected depth images of shape (B, 1, H, W), got {tuple(true.shape)}")
+    return true.detach().float().contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class ImplicitLossFn(torch.autograd.Function):
+    """ImplicitLoss.__call__ (torch/classes.py:284-295) -> 0-dim fp64 loss; gradient reaches ``pred`` only."""
+
+    @staticmethod
+    def forward(ctx, true, pred, n, step, z0, tau, sharpness):
+        _require_cuda(pred, "pred"); _require_cuda(true, "true")
+        dev = pred.device
+        img = _image(true)
+        p, tag = _params(pred)
+        B = p.shape[0]
+        if img.shape[0] != B:
+            raise ValueError("true and pred disagree on the batch size")
+        row_off, col_off = nearest_offsets(img.shape[2], img.shape[3], n, dev)
+        want_grad = ctx.needs_input_grad[1]
+        loss = torch.empty((), dtype=torch.float64, device=dev)
+        grad = torch.empty_like(p) if want_grad else None
+        scratch = _get_scratch(dev, B, n)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().sq_implicit_loss(
+                _ptr(p), tag, B, n, step, z0, _ptr(img), img.shape[2] * img.shape[3], _ptr(row_off), _ptr(col_off),
+                tau, sharpness, _ptr(loss), None, _ptr(grad), None, _ptr(scratch), scratch.numel(), _stream(dev))
+        _lib.check(rc, "sq_implicit_loss")
+        ctx.grad = grad
+        ctx.pred_dtype = pred.dtype
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        g = None
+        if ctx.grad is not None:
+            g = (ctx.grad * go.to(ctx.grad.dtype)).to(ctx.pred_dtype)
+        return None, g, None, None, None, None, None
+
+
+class ExplicitLossFn(torch.autograd.Function):
+    """ExplicitLoss.__call__ (torch/classes.py:191-201).  The loss is symmetric in (true, pred), so a gradient for
+    ``true`` (no reference caller asks for one) is the same kernel with the roles swapped."""
+
+    @staticmethod
+    def forward(ctx, true, pred, n, step, z0, sharpness, mult):
+        _require_cuda(pred, "pred"); _require_cuda(true, "true")
+        dev = pred.device
+        if true.dtype == torch.float64 or pred.dtype == torch.float64:
+            true_c, pred_c = true.double(), pred.double()
+        else:
+            true_c, pred_c = true, pred
+        t, tag = _params(true_c)
+        p, _ = _params(pred_c)
+        B = p.shape[0]
+        if t.shape[0] != B:
+            raise ValueError("true and pred disagree on the batch size")
+        loss = torch.empty((), dtype=torch.float64, device=dev)
+        scratch = _get_scratch(dev, B, n)
+        L = _lib.lib()
+
+        def run(a, b, grad):
+            with torch.cuda.device(dev):
+                rc = L.sq_explicit_loss(_ptr(a), _ptr(b), tag, B, n, step, z0, sharpness, mult, _ptr(loss), None,
+                                        _ptr(grad), _ptr(scratch), scratch.numel(), _stream(dev))
+            _lib.check(rc, "sq_explicit_loss")
+
+        ctx.grad_true = ctx.grad_pred = None
+        if ctx.needs_input_grad[0]:
+            ctx.grad_true = torch.empty_like(t)
+            run(p, t, ctx.grad_true)
+        ctx.grad_pred = torch.empty_like(p) if ctx.needs_input_grad[1] else None
+        run(t, p, ctx.grad_pred)
+        ctx.dtypes = (true.dtype, pred.dtype)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        gt = gp = None
+        if ctx.grad_true is not None:
+            gt = (ctx.grad_true * go.to(ctx.grad_true.dtype)).to(ctx.dtypes[0])
+        if ctx.grad_pred is not None:
+            gp = (ctx.grad_pred * go.to(ctx.grad_pred.dtype)).to(ctx.dtypes[1])
+        return gt, gp, None, None, None, None, None
+
+
+class LeastSquaresFn(torch.autograd.Function):
+    """LeastSquares.__call__ (torch/classes.py:358-371) -> 0-dim loss in fp32 like the reference (``:319``)."""
+
+    @staticmethod
+    def forward(ctx, true, pred, render_size):
+        _require_cuda(pred, "pred"); _require_cuda(true, "true")
+        dev = pred.device
+        img = _image(true)
+        p, tag = _params(pred)
+        B = p.shape[0]
+        row_off, col_off = nearest_offsets(img.shape[2], img.shape[3], render_size, dev)
+        want_grad = ctx.needs_input_grad[1]
+        loss = torch.empty((), dtype=torch.float64, device=dev)
+        grad = torch.empty_like(p) if want_grad else None
+        scratch = _get_scratch(dev, B, render_size)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().sq_least_squares(
+                _ptr(p), tag, B, render_size, _ptr(img), img.shape[2] * img.shape[3], _ptr(row_off), _ptr(col_off),
+                _ptr(loss), None, _ptr(grad), _ptr(scratch), scratch.numel(), _stream(dev))
+        _lib.check(rc, "sq_least_squares")
+        ctx.grad = grad
+        ctx.pred_dtype = pred.dtype
+        return loss.to(pred.dtype if pred.dtype.is_floating_point else torch.float32)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        g = None
+        if ctx.grad is not None:
+            g = (ctx.grad * go.to(ctx.grad.dtype)).to(ctx.pred_dtype)
+        return None, g, None
+
+
+def iou_counts(true: torch.Tensor, pred: torch.Tensor, n: int, step: float, z0: float = 0.0):
+    """(intersection[B], union[B]) int64 voxel counts of F<=1 (torch/classes.py:433-438).  Forward only."""
+    _require_cuda(pred, "pred"); _require_cuda(true, "true")
+    dev = pred.device
+    if true.dtype == torch.float64 or pred.dtype == torch.float64:
+        true, pred = true.double(), pred.double()
+    t, tag = _params(true)
+    p, _ = _params(pred)
+    B = p.shape[0]
+    if t.shape[0] != B:
+        raise ValueError("true and pred disagree on the batch size")
+    out = torch.empty((2, B), dtype=torch.int64, device=dev)
+    scratch = _get_scratch(dev, B, n)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().sq_iou_counts(_ptr(t), _ptr(p), tag, B, n, step, z0, _ptr(out[0]), _ptr(out[1]),
+                                      _ptr(scratch), scratch.numel(), _stream(dev))
+    _lib.check(rc, "sq_iou_counts")
+    return out[0], out[1]
+
+
+def depth_projection(pred: torch.Tensor, n: int, step: float, z0: float, tau: float, sharpness: float) -> torch.Tensor:
+    """ImplicitLoss.depth_projection (torch/classes.py:232-282): (B, n, n) fp32 render, image orientation."""
+    _require_cuda(pred, "pred")
+    dev = pred.device
+    p, tag = _params(pred)
+    B = p.shape[0]
+    out = torch.empty((B, n, n), dtype=torch.float32, device=dev)
+    scratch = _get_scratch(dev, B, n)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().sq_implicit_loss(_ptr(p), tag, B, n, step, z0, None, 0, None, None, tau, sharpness, None, None,
+                                         None, _ptr(out), _ptr(scratch), scratch.numel(), _stream(dev))
+    _lib.check(rc, "sq_implicit_loss(depth)")
+    return out
+
+
+def field(params: torch.Tensor, n: int, step: float, z0: float, mode: int, sharpness: float = 0.0) -> torch.Tensor:
+    """Full (B, n, n, n) fp32 grid: mode 0 = F (ins_outs), mode 1 = occupancy sigmoid(sharpness (1 - F))."""
+    _require_cuda(params, "params")
+    dev = params.device
+    p, tag = _params(params)
+    B = p.shape[0]
+    out = torch.empty((B, n, n, n), dtype=torch.float32, device=dev)
+    scratch = _get_scratch(dev, B, n)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().sq_field(_ptr(p), tag, B, n, step, z0, mode, sharpness, _ptr(out), _ptr(scratch),
+                                 scratch.numel(), _stream(dev))
+    _lib.check(rc, "sq_field")
+    return out
+
+
+class HostContext:
+    """sq_ctx wrapper: the host-buffer entry points of the C ABI (what a non-torch caller binds)."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().sq_ctx_create(device, ctypes.byref(self._h)), "sq_ctx_create")
+
+    def close(self):
+        if self._h:
+            _lib.lib().sq_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _np(a, dtype):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        return a, a.ctypes.data_as(ctypes.c_void_p)
+
+    def implicit_loss(self, pred, images, render_size, tau, sharpness, want_grad=True):
+        pred, p_pred = self._np(pred, np.float32)
+        images, p_img = self._np(images, np.float32)
+        B = pred.shape[0]
+        H, W = images.shape[-2], images.shape[-1]
+        loss = ctypes.c_double()
+        grad = np.empty((B, 12), dtype=np.float32) if want_grad else None
+        rc = _lib.lib().sq_implicit_loss_host(self._h, p_pred, B, render_size, p_img, H, W, tau, sharpness,
+                                              ctypes.cast(ctypes.byref(loss), ctypes.c_void_p),
+                                              grad.ctypes.data_as(ctypes.c_void_p) if want_grad else None)
+        _lib.check(rc, "sq_implicit_loss_host")
+        return loss.value, grad
+
+    def explicit_loss(self, true, pred, render_size, want_grad=True):
+        true, p_true = self._np(true, np.float32)
+        pred, p_pred = self._np(pred, np.float32)
+        B = pred.shape[0]
+        loss = ctypes.c_double()
+        grad = np.empty((B, 12), dtype=np.float32) if want_grad else None
+        rc = _lib.lib().sq_explicit_loss_host(self._h, p_true, p_pred, B, render_size,
+                                              ctypes.cast(ctypes.byref(loss), ctypes.c_void_p),
+                                              grad.ctypes.data_as(ctypes.c_void_p) if want_grad else None)
+        _lib.check(rc, "sq_explicit_loss_host")
+        return loss.value, grad
+
+    def iou_counts(self, true, pred, render_size):
+        true, p_true = self._np(true, np.float32)
+        pred, p_pred = self._np(pred, np.float32)
+        B = pred.shape[0]
+        inter, uni = np.empty(B, dtype=np.int64), np.empty(B, dtype=np.int64)
+        rc = _lib.lib().sq_iou_counts_host(self._h, p_true, p_pred, B, render_size,
+                                           inter.ctypes.data_as(ctypes.c_void_p), uni.ctypes.data_as(ctypes.c_void_p))
+        _lib.check(rc, "sq_iou_counts_host")
+        return inter, uni

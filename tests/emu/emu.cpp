@@ -1,0 +1,130 @@
+// Host build of sq_recovery_b200/csrc/sq_core.cuh -- TEST TOOL, never part of the product.
+//
+// The per-point core is written as host+device functions so that the forward/backward algebra and the
+// finalize Jacobians can be checked against the oracle on a machine without a GPU.  This file replays the
+// kernels' loop structure (one "thread" per column, fp32 per-column sums, fp64 across columns) serially.
+// MUFU approximations are replaced by libm (ex2f/log2f/1/x), so this checks the maths, not the MUFU error.
+#include "sq_core.cuh"
+#include <vector>
+#include <cstring>
+
+using namespace sq;
+
+static void acc_to_double(const Acc& a, double* d) {
+    for (int i = 0; i < 3; ++i) d[i] += a.gs[i];
+    for (int i = 0; i < 9; ++i) d[3 + i] += a.gm[i];
+    for (int i = 0; i < 3; ++i) d[12 + i] += a.wa[i];
+    d[15] += a.ge[0]; d[16] += a.ge[1]; d[17] += a.loss;
+}
+
+extern "C" {
+
+// target: [B, n, n] in image orientation (row, col); depth_out optional [B, n, n] image orientation
+int emu_implicit(const double* pred, int B, int n, double step, double z0, const float* target, float tau, float k,
+                 double* loss_out, double* grad /*[B,12] or null*/, float* depth_out /*or null*/) {
+    Grid g{n, step, z0};
+    ImplicitParams P{k * kLog2e, tau * kLog2e, tau};
+    double total = 0.0;
+    for (int b = 0; b < B; ++b) {
+        double p[12]; for (int i = 0; i < 12; ++i) p[i] = pred[12 * b + i];
+        Sample S; prep_sample(p, true, g, S);
+        double accd[kAccN] = {0};
+        for (int ib = 0; ib < n; ++ib) for (int ia = 0; ia < n; ++ia) {
+            float bh[3], bl[3], cg[11];
+            column_base(S, g, ia, ib, bh, bl);
+            const float depth = grad ? implicit_column<true>(S, g, P, bh, bl, cg) : implicit_column<false>(S, g, P, bh, bl, cg);
+            const int row = n - 1 - ib, col = ia;
+            if (depth_out) depth_out[(size_t)b * n * n + row * n + col] = depth;
+            const float tgt = target ? target[(size_t)b * n * n + row * n + col] : 0.f;
+            const float diff = depth - tgt;
+            Acc a; acc_zero(a);
+            a.loss = fabsf(diff);
+            if (grad) {
+                const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                implicit_fold(a, cg, w, (float)(grid_coord(g, ia) - S.t[0]), (float)(grid_coord(g, ib) - S.t[1]));
+            }
+            acc_to_double(a, accd);
+        }
+        total += accd[17] / ((double)n * n);
+        if (grad) {
+            const double scale = -(double)k * tau / ((double)n * n * n * B);
+            finalize_sample(S, g, accd, scale, true, grad + 12 * b);
+        }
+    }
+    *loss_out = total / B;
+    return 0;
+}
+
+int emu_explicit(const double* tru, const double* pred, int B, int n, double step, double z0, float k, float mult,
+                 double* loss_out, double* grad) {
+    Grid g{n, step, z0};
+    double total = 0.0;
+    for (int b = 0; b < B; ++b) {
+        double pt[12], pp[12];
+        for (int i = 0; i < 12; ++i) { pt[i] = tru[12 * b + i]; pp[i] = pred[12 * b + i]; }
+        Sample St, Sp; prep_sample(pt, true, g, St); prep_sample(pp, true, g, Sp);
+        double accd[kAccN] = {0};
+        for (int ib = 0; ib < n; ++ib) for (int ia = 0; ia < n; ++ia) {
+            float bht[3], blt[3], bhp[3], blp[3];
+            column_base(St, g, ia, ib, bht, blt);
+            column_base(Sp, g, ia, ib, bhp, blp);
+            Acc a; acc_zero(a);
+            const float dx = (float)(grid_coord(g, ia) - Sp.t[0]), dy = (float)(grid_coord(g, ib) - Sp.t[1]);
+            a.loss = grad ? explicit_column<true>(St, Sp, g, k * kLog2e, bht, blt, bhp, blp, dx, dy, a)
+                          : explicit_column<false>(St, Sp, g, k * kLog2e, bht, blt, bhp, blp, dx, dy, a);
+            acc_to_double(a, accd);
+        }
+        const double n3 = (double)n * n * n;
+        total += mult * accd[17] / n3;
+        if (grad) finalize_sample(Sp, g, accd, 2.0 * k * mult / (n3 * B), true, grad + 12 * b);
+    }
+    *loss_out = total / B;
+    return 0;
+}
+
+int emu_iou(const double* tru, const double* pred, int B, int n, double step, long long* inter, long long* uni) {
+    Grid g{n, step, 0.0};
+    for (int b = 0; b < B; ++b) {
+        double pt[12], pp[12];
+        for (int i = 0; i < 12; ++i) { pt[i] = tru[12 * b + i]; pp[i] = pred[12 * b + i]; }
+        Sample St, Sp; prep_sample(pt, false, g, St); prep_sample(pp, false, g, Sp);
+        long long I = 0, U = 0;
+        for (int ib = 0; ib < n; ++ib) for (int ia = 0; ia < n; ++ia) {
+            float bht[3], blt[3], bhp[3], blp[3];
+            column_base(St, g, ia, ib, bht, blt);
+            column_base(Sp, g, ia, ib, bhp, blp);
+            unsigned i = 0, u = 0;
+            iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, i, u);
+            I += i; U += u;
+        }
+        inter[b] = I; uni[b] = U;
+    }
+    return 0;
+}
+
+// points: [sum m, 3] (x, y, z) with offsets[B+1]
+int emu_lsq(const double* pred, int B, const float* points, const int* offsets, double* loss_out, double* grad) {
+    Grid g{2, 1.0, 0.0};
+    double total = 0.0;
+    for (int b = 0; b < B; ++b) {
+        double p[12]; for (int i = 0; i < 12; ++i) p[i] = pred[12 * b + i];
+        Sample S; prep_sample(p, true, g, S);
+        double accd[kAccN] = {0};
+        for (int j = offsets[b]; j < offsets[b + 1]; ++j) {
+            Acc a; acc_zero(a);
+            a.loss = grad ? lsq_point<true>(S, points[3 * j], points[3 * j + 1], points[3 * j + 2], a)
+                          : lsq_point<false>(S, points[3 * j], points[3 * j + 1], points[3 * j + 2], a);
+            acc_to_double(a, accd);
+        }
+        const double vol = S.a[0] * S.a[1] * S.a[2];
+        total += vol * accd[17];
+        if (grad) {
+            finalize_sample(S, g, accd, 2.0 * vol / B, false, grad + 12 * b);
+            for (int i = 0; i < 3; ++i) grad[12 * b + i] += S.mask[i] * (vol / S.a[i]) * accd[17] / B;
+        }
+    }
+    *loss_out = total / B;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+"""Parity of the CUDA product (through the reference-facing classes and the C ABI) against the oracle.
+
+All tests here need a B200 (``-m gpu``).  Tolerances are the north-star ones: loss rtol 1e-5, parameter
+gradients rtol 1e-4 / atol 1e-6 (fp32 kernels vs the fp64 reference); IoU voxel counts are exact.
+Nothing here reads /root/reference: the reference's outputs come from tests/golden/*.npz (frozen by
+oracle/make_goldens.py) and from the oracle restatement evaluated on the CPU.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, random_golden_files
+from oracle import sq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL, GRAD_ATOL = 1e-4, 1e-6
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def S():
+    import sq_recovery_b200 as pkg
+    return pkg
+
+
+def run(crit, true, pred, dev):
+    """loss (float) and d loss / d pred (np.float64) through the public call + autograd."""
+    true = torch.as_tensor(true).to(dev)
+    pred = torch.as_tensor(pred).to(dev).clone().requires_grad_(True)
+    loss = crit(true, pred)
+    loss.backward()
+    assert pred.grad is not None and pred.grad.dtype == pred.dtype and pred.grad.shape == pred.shape
+    return loss.item(), pred.grad.double().cpu().numpy()
+
+
+def check(loss, grad, ref_loss, ref_grad, loss_rtol=LOSS_RTOL, rtol=GRAD_RTOL, atol=GRAD_ATOL, what="", keep=None):
+    ref_loss = float(ref_loss)
+    assert abs(loss - ref_loss) <= loss_rtol * abs(ref_loss) + 1e-12, f"{what}: loss {loss} vs {ref_loss}"
+    err = np.abs(grad - ref_grad) / (atol + rtol * np.abs(ref_grad))
+    if keep is not None:
+        err = err[np.asarray(keep)]
+    assert err.max() <= 1.0, f"{what}: worst gradient error {err.max():.2f}x tolerance at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def unambiguous(oracle_crit, img, pred):
+    """Per-sample mask: False where the MAE derivative sign(depth - target) (classes.py:292) is decided by less than
+    fp32 can resolve.  |.| is not differentiable at a tie; a pixel whose fp64 render differs from its fp32 target by
+    < 1e-6 flips that pixel's whole contribution, so such samples are excluded from the GRADIENT comparison (same
+    spirit as the north-star's exclusion of points within 1e-6 of a clamp boundary).  The loss is still compared."""
+    with torch.no_grad():
+        d = oracle_crit.depth_projection(torch.as_tensor(pred))
+        t = oracle_crit.resize(torch.as_tensor(img))[:, 0].double()
+    tie = ((d - t).abs() < 1e-6) & (d > 1e-5)
+    return ~tie.flatten(1).any(dim=1).numpy()
+
+
+# ------------------------------------------------------------------ the reference's own fixtures
+def test_fixture_implicit(fixtures_golden, dev, S):
+    g = fixtures_golden
+    imgs = torch.tensor(g["imgs_u8"].astype(np.float32) / 255.0)
+    lab = g["labels"]
+    crit = S.ImplicitLoss(64, dev, 1.5, 260)
+    l, gr = run(crit, imgs, lab, dev)
+    check(l, gr, g["implicit64_loss"], g["implicit64_grad"], what="implicit64")
+    assert abs(l - 0.007077226864072453) < 1e-5 * 0.0071
+    l, gr = run(crit, imgs, np.roll(lab, 1, 0), dev)
+    check(l, gr, g["implicit64_roll_loss"], g["implicit64_roll_grad"], what="implicit64 rolled labels")
+    depth = crit.depth_projection(torch.tensor(lab).to(dev)).cpu().numpy()
+    np.testing.assert_allclose(depth, g["implicit64_depth"], atol=2e-5)
+    l, gr = run(S.ImplicitLoss(32, dev), imgs, np.roll(lab, 1, 0), dev)      # default tau / sharpness
+    check(l, gr, g["implicit32_default_loss"], g["implicit32_default_grad"], what="implicit32 defaults")
+    # per-sample: image i with its own label is small, with the next label >= 10x larger
+    own = [crit(imgs[i:i + 1].to(dev), torch.tensor(lab[i:i + 1]).to(dev)).item() for i in range(10)]
+    np.testing.assert_allclose(own, g["implicit64_per_sample"], rtol=1e-5)
+
+
+def test_fixture_explicit_iou_lsq(fixtures_golden, dev, S):
+    g = fixtures_golden
+    imgs = torch.tensor(g["imgs_u8"].astype(np.float32) / 255.0)
+    lab = g["labels"]
+    roll = np.roll(lab, 1, 0)
+    ex = S.ExplicitLoss(32, dev)
+    assert ex(torch.tensor(lab).to(dev), torch.tensor(lab).to(dev)).item() == 0.0
+    l, gr = run(ex, lab, roll, dev)
+    check(l, gr, g["explicit32_roll_loss"], g["explicit32_roll_grad"], what="explicit32")
+    acc = S.IoUAccuracy(64, dev)
+    t, p = torch.tensor(lab).to(dev), torch.tensor(roll).to(dev)
+    assert acc(t, t).item() == 1.0
+    i, u = acc.counts(t, p)
+    assert (i.cpu().numpy() == g["iou64_roll_inter"]).all() and (u.cpu().numpy() == g["iou64_roll_union"]).all()
+    assert abs(acc(t, p).item() - float(g["iou64_roll"])) < 1e-7
+    per = S.IoUAccuracy(64, dev, reduce=False)(t, p)
+    assert per.shape == (10,) and per.dtype == torch.float64
+    np.testing.assert_allclose(per.cpu().numpy(), g["iou64_roll_per_sample"], rtol=1e-12)
+    ls = S.LeastSquares(64, dev)            # fp32 internals in the reference itself (classes.py:319)
+    l, gr = run(ls, imgs, lab, dev)
+    check(l, gr, g["lsq64_loss"], g["lsq64_grad"], loss_rtol=1e-4, rtol=1e-3, atol=1e-5, what="lsq64")
+    l, gr = run(ls, imgs, roll, dev)
+    check(l, gr, g["lsq64_roll_loss"], g["lsq64_roll_grad"], loss_rtol=1e-4, rtol=1e-3, atol=1e-3, what="lsq64 rolled")
+
+
+def test_fixture_main_and_visu(fixtures_golden, dev, S):
+    g = fixtures_golden
+    main = torch.tensor(g["main_params"]).to(dev)                      # classes.py:453-473: IoU of identical params
+    assert S.IoUAccuracy(render_size=64, device=dev)(main, main).item() == 1.0
+    # visu.py:142-165: fp64 leaf tensors, .backward(), read pred.grad
+    l, gr = run(S.ExplicitLoss(render_size=32, device=dev), g["visu_true"], g["visu_pred"], dev)
+    check(l, gr, g["visu_explicit32_loss"], g["visu_explicit32_grad"], what="visu explicit32 fp64")
+    a = S.IoUAccuracy(render_size=128, device=dev, full=True)(torch.tensor(g["visu_true"]).to(dev),
+                                                               torch.tensor(g["visu_pred"]).to(dev))
+    assert abs(a.detach().cpu().item() - float(g["visu_iou128"])) < 1e-7
+
+
+# ------------------------------------------------------------------ seeded random inputs frozen from the reference
+@pytest.mark.parametrize("fname", random_golden_files())
+def test_random_goldens(fname, dev, S):
+    g = load_golden(fname)
+    R = int(g["R"])
+    for tag in ("far", "near"):
+        pred = g[f"pred_{tag}"]
+        for name, crit in (("implicit_t15_k260", S.ImplicitLoss(R, dev, 1.5, 260)), ("implicit_default", S.ImplicitLoss(R, dev))):
+            l, gr = run(crit, g["img"], pred, dev)
+            check(l, gr, g[f"{name}_{tag}_loss"], g[f"{name}_{tag}_grad"], what=f"{fname} {name} {tag}")
+        l, gr = run(S.ExplicitLoss(R, dev), g["true"], pred, dev)
+        check(l, gr, g[f"explicit_{tag}_loss"], g[f"explicit_{tag}_grad"], what=f"{fname} explicit {tag}")
+        i, u = S.IoUAccuracy(R, dev).counts(torch.tensor(g["true"]).to(dev), torch.tensor(pred).to(dev))
+        assert (i.cpu().numpy() == g[f"iou_{tag}_inter"]).all() and (u.cpu().numpy() == g[f"iou_{tag}_union"]).all()
+        l, gr = run(S.LeastSquares(R, dev), g["img"], pred, dev)
+        check(l, gr, g[f"lsq_{tag}_loss"], g[f"lsq_{tag}_grad"], loss_rtol=1e-4, rtol=2e-3, atol=1e-4, what=f"{fname} lsq {tag}")
+    d = S.ImplicitLoss(R, dev, 1.5, 260).depth_projection(torch.tensor(g["true"]).to(dev))
+    np.testing.assert_allclose(d.cpu().numpy(), g["depth_true"], atol=2e-5)
+    if g["occupancy_true"].size:
+        occ = S.ExplicitLoss(R, dev).occupancy(torch.tensor(g["true"][:2]).to(dev))
+        np.testing.assert_allclose(occ.cpu().numpy(), g["occupancy_true"], atol=2e-5)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases(edge_golden, dev, S):
+    g = edge_golden
+    R = int(g["R"])
+    img = torch.tensor(g["img"]).float()
+    l, gr = run(S.ImplicitLoss(R, dev, 1.5, 260), img, g["pred"], dev)          # fp64 parameters
+    check(l, gr, g["implicit_loss"], g["implicit_grad"], what="edge implicit")
+    l, gr = run(S.ImplicitLoss(R, dev, 1.0, 20), img, g["pred"], dev)
+    check(l, gr, g["implicit_soft_loss"], g["implicit_soft_grad"], what="edge implicit soft")
+    l, gr = run(S.ExplicitLoss(R, dev), g["true"], g["pred"], dev)
+    check(l, gr, g["explicit_loss"], g["explicit_grad"], what="edge explicit")
+    # clamp sub-gradient: exactly 0 outside the range, live on the inclusive boundary
+    assert gr[0, 0] == 0 and gr[0, 1] == 0 and gr[0, 2] != 0
+    assert gr[1, 3] == 0 and gr[1, 4] != 0
+    assert gr[2, 5] == 0 and gr[2, 6] == 0 and gr[2, 7] != 0
+    l, gr = run(S.ExplicitLoss(R, dev), g["pred"], g["true"], dev)
+    check(l, gr, g["explicit_swapped_loss"], g["explicit_swapped_grad"], what="edge explicit swapped")
+    i, u = S.IoUAccuracy(R, dev).counts(torch.tensor(g["true"]).to(dev), torch.tensor(g["pred"]).to(dev))
+    assert (i.cpu().numpy() == g["iou_inter"]).all() and (u.cpu().numpy() == g["iou_union"]).all()
+    ex24 = S.ExplicitLoss(24, dev)                                      # arange(0, 1+1/24, 1/24) has R+2 entries
+    assert ex24.xyz.shape == (3, 26, 26, 26) and int(g["explicit24_n"]) == 26
+    l, gr = run(ex24, g["true24"], g["pred24"], dev)
+    check(l, gr, g["explicit24_loss"], g["explicit24_grad"], what="explicit R=24")
+
+
+# ------------------------------------------------------------------ live oracle on fresh seeded inputs
+@pytest.mark.parametrize("seed,B,R", [(21, 8, 32), (22, 3, 64), (23, 16, 16)])
+def test_against_oracle(seed, B, R, dev, S):
+    true = O.random_params(B, seed)
+    pred_far, pred_near = O.random_params(B, seed + 500), O.perturbed_params(true, seed)
+    with torch.no_grad():
+        img = O.ImplicitLoss(4 * R, "cpu", 1.5, 260).depth_projection(true).float().unsqueeze(1)
+    for pred in (pred_far, pred_near):
+        for args in ((1.5, 260), (1, 100)):
+            p = pred.clone().requires_grad_(True)
+            oc = O.ImplicitLoss(R, "cpu", *args)
+            ref = oc(img, p); ref.backward()
+            l, gr = run(S.ImplicitLoss(R, dev, *args), img, pred, dev)
+            keep = unambiguous(oc, img, pred)
+            assert keep.sum() >= B - 2
+            check(l, gr, ref.item(), p.grad.double().numpy(), what=f"implicit{args} B={B} R={R}", keep=keep)
+        p = pred.clone().requires_grad_(True)
+        ref = O.ExplicitLoss(R, "cpu")(true, p); ref.backward()
+        l, gr = run(S.ExplicitLoss(R, dev), true, pred, dev)
+        check(l, gr, ref.item(), p.grad.double().numpy(), what=f"explicit B={B} R={R}")
+        i, u = O.IoUAccuracy(R, "cpu").counts(true, pred)
+        i2, u2 = S.IoUAccuracy(R, dev).counts(true.to(dev), pred.to(dev))
+        assert torch.equal(i, i2.cpu()) and torch.equal(u, u2.cpu())
+
+
+# ------------------------------------------------------------------ full BASELINE sizes through size-independent properties
+def test_full_size_properties(dev, S):
+    B, R = 256, 64                                                      # BASELINE config 2
+    true = O.random_params(B, 0).to(dev)
+    pred = O.perturbed_params(O.random_params(B, 0), 5).to(dev)
+    crit = S.ImplicitLoss(R, dev, 1.5, 260)
+    target = crit.depth_projection(true).unsqueeze(1)                   # synthetic depth maps
+    p1 = pred.clone().requires_grad_(True)
+    l1 = crit(target, p1); l1.backward()
+    p2 = pred.clone().requires_grad_(True)
+    l2 = crit(target, p2); l2.backward()
+    assert l1.item() == l2.item() and torch.equal(p1.grad, p2.grad)    # run-to-run bit reproducible
+    assert torch.isfinite(p1.grad).all()
+    # rendering the true params and comparing them with themselves gives (numerically) zero loss
+    assert crit(target, true).item() < 1e-6
+    # batch split invariance: the loss is the mean of per-sample losses, gradients scale with 1/B
+    halves = []
+    for sl in (slice(0, 128), slice(128, 256)):
+        ph = pred[sl].clone().requires_grad_(True)
+        lh = crit(target[sl], ph); lh.backward()
+        halves.append((lh.item(), ph.grad))
+    assert abs(0.5 * (halves[0][0] + halves[1][0]) - l1.item()) < 1e-12
+    torch.testing.assert_close(torch.cat([halves[0][1], halves[1][1]]) * 0.5, p1.grad, rtol=1e-6, atol=1e-12)
+    # a slice of the full batch against the oracle
+    idx = [0, 77, 255]
+    po = pred[idx].cpu().clone().requires_grad_(True)
+    oc = O.ImplicitLoss(R, "cpu", 1.5, 260)
+    ref = oc(target[idx].cpu(), po); ref.backward()
+    ps = pred[idx].clone().requires_grad_(True)
+    ls = crit(target[idx], ps); ls.backward()
+    check(ls.item(), ps.grad.double().cpu().numpy(), ref.item(), po.grad.double().numpy(), what="slice of config 2",
+          keep=unambiguous(oc, target[idx].cpu(), pred[idx].cpu()))
+    # ExplicitLoss / IoU identities at full size
+    ex = S.ExplicitLoss(R, dev)
+    assert ex(true, true).item() == 0.0
+    assert S.IoUAccuracy(R, dev)(true, true).item() == 1.0
+    i, u = S.IoUAccuracy(R, dev).counts(true, pred)
+    assert (i <= u).all() and (u > 0).all()
+    pe = pred.clone().requires_grad_(True)
+    le = ex(true, pe); le.backward()
+    assert torch.isfinite(pe.grad).all() and le.item() > 0
+
+
+# ------------------------------------------------------------------ API / autograd behaviour
+def test_autograd_contract(dev, S):
+    B, R = 4, 32
+    true = O.random_params(B, 3).to(dev)
+    img = S.ImplicitLoss(128, dev, 1.5, 260).depth_projection(true).unsqueeze(1)
+    crit = S.ImplicitLoss(R, dev, 1.5, 260)
+    # non-leaf pred built with torch.cat like train.py:89; gradient must reach the heads
+    heads = [O.random_params(B, 4).to(dev)[:, s].clone().requires_grad_(True) for s in (slice(0, 3), slice(3, 5), slice(5, 8), slice(8, 12))]
+    pred = torch.cat(heads, dim=1)
+    loss = crit(img, pred)
+    assert loss.dim() == 0 and loss.dtype == torch.float64 and loss.device.type == "cuda"
+    (3.0 * loss).backward()
+    g3 = torch.cat([h.grad for h in heads], dim=1)
+    p = pred.detach().clone().requires_grad_(True)
+    crit(img, p).backward()
+    torch.testing.assert_close(g3, 3.0 * p.grad, rtol=1e-6, atol=0)
+    with torch.no_grad():                                               # train.py:135-146 validation path
+        lv = crit(img, pred)
+        assert not lv.requires_grad and abs(lv.item() - loss.item()) < 1e-7
+    assert not crit(img, pred.detach()).requires_grad
+    # fp64 leaf (visu.py:142-153): grad comes back in fp64
+    p64 = pred.detach().double().requires_grad_(True)
+    S.ExplicitLoss(R, dev)(true.double(), p64).backward()
+    assert p64.grad.dtype == torch.float64
+    # public attributes the reference sets (classes.py:114-127, 208-222, 381-392)
+    assert crit.render_size == R and crit.tau == 1.5 and crit.sigmoid_sharpness == 260 and crit.reduce is True
+    assert crit.xyz.shape == (3, R, R, R) and crit.xyz.dtype == torch.float64 and crit.xyz.min().item() == 1e-4
+    assert S.ExplicitLoss(R, dev).xyz.shape == (3, R + 1, R + 1, R + 1)
+    assert S.IoUAccuracy(R, dev).xyz.min().item() == 0.0
+    pp = S.ExplicitLoss.preprocess_sq(torch.tensor([[2., .01, .5, 0., 2., -1., .5, 2., 1., 2., 3., 4.]]))
+    assert pp.tolist() == [[1., .05, .5, .1, 1., 0., .5, 1., 1., 2., 3., 4.]]
+    with pytest.raises(RuntimeError):
+        S.ImplicitLoss(R, torch.device("cpu"))
+    with pytest.raises(RuntimeError):
+        crit(img.cpu(), pred.detach().cpu())
+
+
+def test_quaternion_helpers(dev, S):
+    q = torch.tensor(O.randquat(np.random.RandomState(0)), device=dev)
+    np.testing.assert_allclose(S.quaternion.mat_from_quaternion(q)[0].cpu().numpy(), O.mat_from_quaternion(q.cpu()).numpy(), atol=1e-15)
+    assert torch.equal(S.quaternion.conjugate(q).cpu(), O.conjugate(q.cpu()))
+
+
+# ------------------------------------------------------------------ host-buffer C ABI (include/sqloss.h)
+def test_host_entry_points(dev, S):
+    from sq_recovery_b200.functional import HostContext
+    B, R = 8, 32
+    true, pred = O.random_params(B, 31), O.random_params(B, 32)
+    img = S.ImplicitLoss(128, dev, 1.5, 260).depth_projection(true.to(dev)).unsqueeze(1).cpu()
+    ctx = HostContext(0)
+    l, g = ctx.implicit_loss(pred.numpy(), img.numpy(), R, 1.5, 260.0)
+    l2, g2 = run(S.ImplicitLoss(R, dev, 1.5, 260), img, pred, dev)
+    assert l == l2 and np.array_equal(g.astype(np.float64), g2)
+    l, g = ctx.explicit_loss(true.numpy(), pred.numpy(), R)
+    l2, g2 = run(S.ExplicitLoss(R, dev), true, pred, dev)
+    assert l == l2 and np.array_equal(g.astype(np.float64), g2)
+    i, u = ctx.iou_counts(true.numpy(), pred.numpy(), R)
+    i2, u2 = S.IoUAccuracy(R, dev).counts(true.to(dev), pred.to(dev))
+    assert np.array_equal(i, i2.cpu().numpy()) and np.array_equal(u, u2.cpu().numpy())
+    ctx.close()
