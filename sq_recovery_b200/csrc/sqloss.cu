@@ -20,9 +20,22 @@ using namespace sq;
 
 namespace {
 
-constexpr int kThreads = 256;            // column-kernel block size
+// Tunables (tools/tune.py builds variants with -D to measure them on the GPU; the defaults are the measured best).
+#ifndef SQ_THREADS
+#define SQ_THREADS 256                   // column-kernel block size
+#endif
+#ifndef SQ_MAX_CPT
+#define SQ_MAX_CPT 2                     // columns per thread and work item
+#endif
+#ifndef SQ_IMP_MINB
+#define SQ_IMP_MINB 2                    // min resident blocks/SM of the implicit fwd+bwd kernel (register cap)
+#endif
+#ifndef SQ_EXP_MINB
+#define SQ_EXP_MINB 2
+#endif
+constexpr int kThreads = SQ_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxCpt = 2;               // columns per thread and work item
+constexpr int kMaxCpt = SQ_MAX_CPT;
 
 // ------------------------------------------------------------------------------------------------ layout
 // Column slots of one sample.  When n is a multiple of 8 a warp owns an 8(x) x 4(y) patch, which keeps the lanes of
@@ -150,7 +163,7 @@ __device__ __forceinline__ void load_sample(Sample* dst, const Sample* src) {
 
 // ------------------------------------------------------------------------------------------------ ImplicitLoss
 template <bool BWD>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, BWD ? SQ_IMP_MINB : 4)
 implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitParams P,
                 const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
@@ -189,7 +202,7 @@ implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitPa
 
 // ------------------------------------------------------------------------------------------------ ExplicitLoss
 template <bool BWD>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SQ_EXP_MINB)
 explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, float kl,
                 float* __restrict__ partials) {
     __shared__ Sample St, Sp;
