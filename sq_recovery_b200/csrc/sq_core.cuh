@@ -29,7 +29,7 @@ namespace sq {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr double kLn2 = 0.6931471805599453;
 constexpr float kAbsFix = 1e-2f;          // |s| used when s == 0  (s^2 := 1e-4, classes.py:171-173)
-constexpr float kActive = 40.0f;          // |log2 of the sigmoid odds| beyond which o(1-o) < 2^-40 is dropped
+constexpr float kActive = 32.0f;          // |log2 of the sigmoid odds| beyond which o(1-o) < 2^-32 is dropped
 
 // ---------------------------------------------------------------- MUFU primitives
 SQ_HD float ex2(float x) {
@@ -89,6 +89,7 @@ struct Sample {
     double t[3];
     // fp32 constants of the point loop
     float dh[3], dl[3];       // Ms[i][2] * step, split hi/lo: s_i(c) = base_i + d_i * cf(c)
+    float idh[3];             // 1 / dh (+-inf when the column runs parallel to a face of the SQ's box)
     float cf0;                // z0 / step: the (non-integer) "index" of plane 0
     float pxy, pz;            // 2/e2, 2/e1
     float e21, e1;            // e2/e1, e1
@@ -130,6 +131,7 @@ SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, Sample& S) {
         const double ia = 1.0 / S.a[i];
         for (int j = 0; j < 3; ++j) S.Ms[3 * i + j] = S.M[3 * i + j] * ia;
         split2(S.Ms[3 * i + 2] * g.step, S.dh[i], S.dl[i]);
+        S.idh[i] = 1.0f / S.dh[i];
     }
     S.cf0 = (float)(g.z0 / g.step);
     S.pxy = (float)(2.0 / S.e[1]);
@@ -295,34 +297,84 @@ SQ_HD void finalize_sample(const Sample& S, const Grid& g, const double* acc, do
 // end of the walk, so gradient terms are accumulated twice -- sum x and sum P_c x with P_c the sum of T in front
 // of c -- and combined as U sum x - sum P x when the column ends.  P and U start at the first point that carries
 // gradient, which keeps the subtraction well conditioned.
-struct ImplicitParams { float kl; float tl; float tau; };     // k log2(e), tau log2(e), tau
+// ---------------------------------------------------------------- culling
+// F >= max(sx^2, sy^2, sz^2) for every shape (G >= C and G >= E >= A^(e2/e1), ...), so a point with
+// max |s_i| >= bound has kl (F - 1) >= 128, 2^that overflows and o = 1/(1 + inf) = 0 EXACTLY in this kernel's own
+// fp32 arithmetic (in the fp64 reference o < 2^-128 there, and exp(-tau * that) is exactly 1).  Such points change
+// nothing: cs, T and every gradient weight are what they were.  A column therefore only has to be walked over
+// the z range where it can be inside the box |s_i| < bound; the rest is accounted for in closed form.
+SQ_HD float cull_bound(float kl) { return sqrtf((1.0f + 128.0f / kl) * 1.002f); }
+
+// inclusive z-index range [c_lo, c_hi] outside which max|s_i| >= bound; empty when c_hi < c_lo
+SQ_HD void column_range(const Sample& S, const Grid& g, float bound, const float* bh, int& c_lo, int& c_hi) {
+    float lo = -1e30f, hi = 1e30f;
+    for (int i = 0; i < 3; ++i) {
+        const float u = (bound - bh[i]) * S.idh[i], v = (-bound - bh[i]) * S.idh[i];
+        lo = fmaxf(lo, fminf(u, v));       // fminf/fmaxf drop the NaN of 0 * inf
+        hi = fminf(hi, fmaxf(u, v));
+    }
+    // one plane of slack per side: rounding of the bounds, the lo parts of s, and plane 0 sitting at z0 not 0
+    const float nf = (float)g.n;
+    lo = fminf(fmaxf(lo - 1.0f, 0.0f), nf);
+    hi = fmaxf(fminf(hi + 1.0f, nf - 1.0f), -1.0f);
+    c_lo = (int)ceilf(lo);
+    c_hi = (int)floorf(hi);
+}
+
+#if defined(__CUDA_ARCH__)
+#define SQ_ANY(p) __any_sync(0xffffffffu, (p))
+#define SQ_WARP_MAX(v) __reduce_max_sync(0xffffffffu, (v))
+#define SQ_WARP_MIN(v) __reduce_min_sync(0xffffffffu, (v))
+#else
+#define SQ_ANY(p) (p)
+#define SQ_WARP_MAX(v) (v)
+#define SQ_WARP_MIN(v) (v)
+#endif
+
+// union over the warp of the lanes' ranges; (0, -1) when every lane's range is empty
+SQ_HD void warp_range(int n, int& c_lo, int& c_hi) {
+    const bool empty = c_hi < c_lo;
+    c_hi = SQ_WARP_MAX(empty ? -1 : c_hi);
+    c_lo = SQ_WARP_MIN(empty ? n : c_lo);
+    if (c_hi < c_lo) { c_lo = 0; c_hi = -1; }
+}
+
+// ---------------------------------------------------------------- ImplicitLoss: one column
+// classes.py:274-279.  Walk from the camera side (z index n-1) down to 0:
+//   o_c = sigmoid(k (1 - F_c)),  cs_c = running sum of o,  T_c = exp(-tau cs_c),  depth = 1 - sum_c T_c / n.
+// d depth / d o_c = (tau/n) S_c with the suffix sum S_c = sum_{c' at or behind c} T_c'.  S_c is only known at the
+// end of the walk, so gradient terms are accumulated twice -- sum x and sum P_c x with P_c the sum of T in front
+// of c -- and combined as U sum x - sum P x when the column ends.  P and U start at the first point that carries
+// gradient, which keeps the subtraction well conditioned.
+struct ImplicitParams { float kl; float tl; float bound; };     // k log2(e), tau log2(e), cull_bound(kl)
+
+constexpr float kDeep = 40.0f;       // points behind 2^-kDeep of transmittance carry no gradient (S_c < n 2^-kDeep)
 
 struct ColGrad {       // two-moment accumulators of one column
     float gs0[3], gs1[3], gz0[3], gz1[3], wa0[3], wa1[3], ge0[2], ge1[2];
 };
 
-#if defined(__CUDA_ARCH__)
-#define SQ_ANY(p) __any_sync(0xffffffffu, (p))
-#else
-#define SQ_ANY(p) (p)
-#endif
-
 // Returns the rendered depth.  1 - sum T / n cannot resolve depths below ~1e-7 in fp32, but the sign of
 // (depth - target) on silhouette pixels (target exactly 0, depth 1e-16..1e-7 in the fp64 reference) decides whether
 // the column's gradient counts, and those columns carry k-amplified gradient.  So the first-order sum
 // (tau/n) sum_c cs_c is carried along and used when the depth is tiny (relative error < 0.4% there).
+// [c_lo, c_hi]: the (warp-uniform) z range to walk, from column_range() / warp_range().
 template <bool BWD>
 SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams& P,
-                            const float* bh, const float* bl, float* colgrad11) {
-    float cs = 0.f, tsum = 0.f, psh = 0.f, cssum = 0.f;
-    bool seen = false;
+                            const float* bh, const float* bl, int c_lo, int c_hi, float* colgrad11) {
+    // planes in front of the range: o = 0, cs = 0, T = 1 each
+    float csl = 0.f;                                  // -tau log2(e) cs
+    float T = 1.0f;                                   // 2^csl
+    float tsum = (float)(g.n - 1 - c_hi);
+    float cssum = 0.f;                                // sum_c csl_c
+    float psh = 0.f, seen = 0.f;
     ColGrad cg;
     if (BWD) {
         for (int i = 0; i < 3; ++i) cg.gs0[i] = cg.gs1[i] = cg.gz0[i] = cg.gz1[i] = cg.wa0[i] = cg.wa1[i] = 0.f;
         cg.ge0[0] = cg.ge0[1] = cg.ge1[0] = cg.ge1[1] = 0.f;
     }
-    float cfi = (float)(g.n - 1);
-    for (int c = g.n - 1; c >= 0; --c, cfi -= 1.0f) {
+    float cfi = (float)c_hi;
+    for (int c = c_hi; c >= c_lo; --c, cfi -= 1.0f) {
         const float cf = (c == 0) ? S.cf0 : cfi;       // plane "index": exact small integers, z0/step for plane 0
         const float sx = fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]);
         const float sy = fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]);
@@ -331,11 +383,11 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
         point_forward<true>(S, sx, sy, sz, f);
         float x, eo;
         const float o = occupancy(f.F, P.kl, x, eo);
-        cs += o;
-        cssum += cs;
-        const float T = ex2(-P.tl * cs);
+        csl = fmaf(o, -P.tl, csl);
+        cssum += csl;
+        T = ex2(csl);
         if (BWD) {
-            const bool active = fabsf(x) < kActive;
+            const bool active = (fabsf(x) < kActive) && (csl > -kDeep);
             if (SQ_ANY(active)) {
                 // do/dF = -k o (1-o) = -k eo o^2 ; the -k is applied in finalize
                 const float W = active ? eo * o * o : 0.0f;
@@ -343,7 +395,7 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
                 if (!active) fwd_neutral(fa);       // keep inactive lanes finite
                 Bwd b;
                 point_backward(fa, W, b);
-                seen = seen || active;
+                seen = active ? 1.0f : seen;
                 const float pp = psh;       // T in front of this point (since the first active one)
                 for (int i = 0; i < 3; ++i) {
                     cg.gs0[i] += b.gs[i];            cg.gs1[i] = fmaf(pp, b.gs[i], cg.gs1[i]);
@@ -353,12 +405,16 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
                 }
                 for (int i = 0; i < 2; ++i) { cg.ge0[i] += b.ge[i]; cg.ge1[i] = fmaf(pp, b.ge[i], cg.ge1[i]); }
             }
-            psh += seen ? T : 0.0f;
+            psh = fmaf(seen, T, psh);
         }
         tsum += T;
     }
+    // planes behind the range: o = 0, cs and T stay what they are
+    const float nb = (float)c_lo;
+    tsum = fmaf(nb, T, tsum);
+    cssum = fmaf(nb, csl, cssum);
     if (BWD) {
-        const float U = psh;
+        const float U = fmaf(nb * seen, T, psh);
         for (int i = 0; i < 3; ++i) {
             colgrad11[i]     = fmaf(U, cg.gs0[i], -cg.gs1[i]);
             colgrad11[3 + i] = fmaf(U, cg.gz0[i], -cg.gz1[i]);
@@ -369,7 +425,7 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
     }
     const float inv_n = 1.0f / (float)g.n;
     const float depth = fmaf(-tsum, inv_n, 1.0f);
-    return depth < 1e-4f ? P.tau * cssum * inv_n : depth;
+    return depth < 1e-4f ? -(float)kLn2 * cssum * inv_n : depth;     // tau sum cs = -ln2 sum csl
 }
 
 // fold one finished column (weight w = sign(depth - target), coordinates relative to t) into the thread totals
@@ -389,45 +445,65 @@ SQ_HD void implicit_fold(Acc& acc, const float* colgrad11, float w, float dx, fl
 // ---------------------------------------------------------------- ExplicitLoss: one column
 // classes.py:187-198: o = sigmoid(5 (1 - F)) for the true and the predicted SQ, loss = 100 mean (o_t - o_p)^2.
 // Returns sum_c (o_t - o_p)^2 over the column and accumulates d/d(pred) terms weighted by (o_t - o_p).
-template <bool BWD>
-SQ_HD float explicit_column(const Sample& St, const Sample& Sp, const Grid& g, float kl,
-                            const float* bht, const float* blt, const float* bhp, const float* blp,
-                            float dx, float dy, Acc& acc) {
-    float sq = 0.f;
-    float gs[3] = {0.f, 0.f, 0.f}, gz[3] = {0.f, 0.f, 0.f};
-    float cfi = (float)(g.n - 1);
-    for (int c = g.n - 1; c >= 0; --c, cfi -= 1.0f) {
-        const float cf = (c == 0) ? Sp.cf0 : cfi;
-        Fwd ft, fp;
+// rt / rp: warp-uniform z ranges {lo, hi} of the true / predicted SQ (column_range + warp_range); outside its
+// range an SQ's occupancy is exactly 0 and its chain is not evaluated.
+struct Range { int lo, hi; };
+
+// one z plane of explicit_column; HAS_T / HAS_P: whether the true / predicted SQ can be occupied on this plane
+template <bool BWD, bool HAS_T, bool HAS_P>
+SQ_HD void explicit_step(const Sample& St, const Sample& Sp, float kl, float cf,
+                         const float* bht, const float* blt, const float* bhp, const float* blp,
+                         float& sq, float* gs, float* gz, Acc& acc) {
+    float ot = 0.f, op = 0.f, xp = 1e30f, ep = 0.f;
+    Fwd ft, fp;
+    if (HAS_T)
         point_forward<true>(St, fmaf(cf, St.dh[0], bht[0]) + fmaf(cf, St.dl[0], blt[0]),
                                 fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
                                 fmaf(cf, St.dh[2], bht[2]) + fmaf(cf, St.dl[2], blt[2]), ft);
+    if (HAS_P)
         point_forward<true>(Sp, fmaf(cf, Sp.dh[0], bhp[0]) + fmaf(cf, Sp.dl[0], blp[0]),
                                 fmaf(cf, Sp.dh[1], bhp[1]) + fmaf(cf, Sp.dl[1], blp[1]),
                                 fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]), fp);
-        float xt, et, xp, ep;
-        const float ot = occupancy(ft.F, kl, xt, et);
-        const float op = occupancy(fp.F, kl, xp, ep);
-        const float d = ot - op;
-        sq = fmaf(d, d, sq);
-        if (BWD) {
-            const bool active = fabsf(xp) < kActive;
-            if (SQ_ANY(active)) {
-                // d/dF_p of (o_t - o_p)^2 = 2 d * k o_p (1 - o_p); constants 2, k applied in finalize
-                const float W = active ? d * ep * op * op : 0.0f;
-                Fwd fa = fp;
-                if (!active) fwd_neutral(fa);
-                Bwd b;
-                point_backward(fa, W, b);
-                for (int i = 0; i < 3; ++i) {
-                    gs[i] += b.gs[i];
-                    gz[i] = fmaf(b.gs[i], cf, gz[i]);
-                    acc.wa[i] += b.wa[i];
-                }
-                acc.ge[0] += b.ge[0];
-                acc.ge[1] += b.ge[1];
+    if (HAS_T) { float xt, et; ot = occupancy(ft.F, kl, xt, et); }
+    if (HAS_P) op = occupancy(fp.F, kl, xp, ep);
+    const float d = ot - op;
+    sq = fmaf(d, d, sq);
+    if (BWD && HAS_P) {
+        const bool active = fabsf(xp) < kActive;
+        if (SQ_ANY(active)) {
+            // d/dF_p of (o_t - o_p)^2 = 2 d * k o_p (1 - o_p); constants 2, k applied in finalize
+            const float W = active ? d * ep * op * op : 0.0f;
+            Fwd fa = fp;
+            if (!active) fwd_neutral(fa);
+            Bwd b;
+            point_backward(fa, W, b);
+            for (int i = 0; i < 3; ++i) {
+                gs[i] += b.gs[i];
+                gz[i] = fmaf(b.gs[i], cf, gz[i]);
+                acc.wa[i] += b.wa[i];
             }
+            acc.ge[0] += b.ge[0];
+            acc.ge[1] += b.ge[1];
         }
+    }
+}
+
+template <bool BWD>
+SQ_HD float explicit_column(const Sample& St, const Sample& Sp, const Grid& g, float kl,
+                            const float* bht, const float* blt, const float* bhp, const float* blp,
+                            Range rt, Range rp, float dx, float dy, Acc& acc) {
+    float sq = 0.f;
+    float gs[3] = {0.f, 0.f, 0.f}, gz[3] = {0.f, 0.f, 0.f};
+    const bool et = rt.hi < rt.lo, ep = rp.hi < rp.lo;
+    const int c_hi = rt.hi > rp.hi ? rt.hi : rp.hi;
+    const int c_lo = et ? rp.lo : ep ? rt.lo : (rt.lo < rp.lo ? rt.lo : rp.lo);
+    float cfi = (float)c_hi;
+    for (int c = c_hi; c >= c_lo; --c, cfi -= 1.0f) {
+        const float cf = (c == 0) ? Sp.cf0 : cfi;
+        const bool in_t = (c >= rt.lo && c <= rt.hi), in_p = (c >= rp.lo && c <= rp.hi);    // warp-uniform
+        if (in_t && in_p) explicit_step<BWD, true, true>(St, Sp, kl, cf, bht, blt, bhp, blp, sq, gs, gz, acc);
+        else if (in_p)    explicit_step<BWD, false, true>(St, Sp, kl, cf, bht, blt, bhp, blp, sq, gs, gz, acc);
+        else if (in_t)    explicit_step<BWD, true, false>(St, Sp, kl, cf, bht, blt, bhp, blp, sq, gs, gz, acc);
     }
     if (BWD) {
         for (int i = 0; i < 3; ++i) {
@@ -444,7 +520,12 @@ SQ_HD float explicit_column(const Sample& St, const Sample& Sp, const Grid& g, f
 // classes.py:398-438: no clamp, no fix-up; inside <=> F <= 1 <=> e1 * lg2(G) <= 0.  Points whose decision is
 // within `margin` of the boundary are re-evaluated in fp64 with the reference's own operation order so the
 // voxel counts match the fp64 reference exactly (DESIGN.md "IoU exactness").
-SQ_HD bool inside_exact(const Sample& S, const Grid& g, int ia, int ib, int ic) {
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+bool inside_exact(const Sample& S, const Grid& g, int ia, int ib, int ic) {
     const double gx = grid_coord(g, ia), gy = grid_coord(g, ib), gz = grid_coord(g, ic);
     double s[3];
     for (int i = 0; i < 3; ++i) {
@@ -465,21 +546,33 @@ SQ_HD float log2F(const Sample& S, float sx, float sy, float sz) {
 
 constexpr float kIoUMargin = 2e-4f;     // |log2 F| below which the fp32 decision is not trusted
 
+// The z ranges come from column_range() with kIoUBound: a point with max|s_i| >= kIoUBound has F >= 1.002, far
+// beyond the margin, so it is outside without evaluating anything.
+constexpr float kIoUBound = 1.001f;
+
 SQ_HD void iou_column(const Sample& St, const Sample& Sp, const Grid& g, int ia, int ib,
                       const float* bht, const float* blt, const float* bhp, const float* blp,
-                      unsigned& inter, unsigned& uni) {
-    float cfi = (float)(g.n - 1);
-    for (int c = g.n - 1; c >= 0; --c, cfi -= 1.0f) {
+                      Range rt, Range rp, unsigned& inter, unsigned& uni) {
+    const int c_hi = rt.hi > rp.hi ? rt.hi : rp.hi;
+    const int c_lo = (rt.hi < rt.lo) ? rp.lo : (rp.hi < rp.lo) ? rt.lo : (rt.lo < rp.lo ? rt.lo : rp.lo);
+    float cfi = (float)c_hi;
+    for (int c = c_hi; c >= c_lo; --c, cfi -= 1.0f) {
         const float cf = (c == 0) ? Sp.cf0 : cfi;
-        const float yt = log2F(St, fmaf(cf, St.dh[0], bht[0]) + fmaf(cf, St.dl[0], blt[0]),
-                                   fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
-                                   fmaf(cf, St.dh[2], bht[2]) + fmaf(cf, St.dl[2], blt[2]));
-        const float yp = log2F(Sp, fmaf(cf, Sp.dh[0], bhp[0]) + fmaf(cf, Sp.dl[0], blp[0]),
-                                   fmaf(cf, Sp.dh[1], bhp[1]) + fmaf(cf, Sp.dl[1], blp[1]),
-                                   fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]));
-        bool it = yt <= 0.f, ip = yp <= 0.f;
-        if (!(fabsf(yt) > kIoUMargin)) it = inside_exact(St, g, ia, ib, c);      // also catches NaN
-        if (!(fabsf(yp) > kIoUMargin)) ip = inside_exact(Sp, g, ia, ib, c);
+        bool it = false, ip = false;
+        if (c >= rt.lo && c <= rt.hi) {
+            const float yt = log2F(St, fmaf(cf, St.dh[0], bht[0]) + fmaf(cf, St.dl[0], blt[0]),
+                                       fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
+                                       fmaf(cf, St.dh[2], bht[2]) + fmaf(cf, St.dl[2], blt[2]));
+            it = yt <= 0.f;
+            if (!(fabsf(yt) > kIoUMargin)) it = inside_exact(St, g, ia, ib, c);      // also catches NaN
+        }
+        if (c >= rp.lo && c <= rp.hi) {
+            const float yp = log2F(Sp, fmaf(cf, Sp.dh[0], bhp[0]) + fmaf(cf, Sp.dl[0], blp[0]),
+                                       fmaf(cf, Sp.dh[1], bhp[1]) + fmaf(cf, Sp.dl[1], blp[1]),
+                                       fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]));
+            ip = yp <= 0.f;
+            if (!(fabsf(yp) > kIoUMargin)) ip = inside_exact(Sp, g, ia, ib, c);
+        }
         inter += (it && ip) ? 1u : 0u;
         uni += (it || ip) ? 1u : 0u;
     }

@@ -2,8 +2,10 @@
 //
 // Kernel plan: every loss is  prep -> column kernel -> finalize, all on the caller's stream.
 //   prep      one thread per parameter row: clamp, rotation, scaled rows, exponents, in fp64 -> Sample (scratch)
-//   column    one thread per grid column (x, y) walking z; grid points are generated from indices, nothing
-//             per-point touches HBM; per-thread sums -> warp shuffles -> shared memory -> one partial row per block
+//   column    one thread per grid column (x, y) walking the part of z that can hold occupancy (the rest is culled
+//             in closed form); grid points are generated from indices, nothing per-point touches HBM; warps are
+//             autonomous: private Sample copy in shared memory, per-thread sums -> warp shuffles -> one partial
+//             row per warp, no block barrier
 //   finalize  one warp per sample: fixed-order fp64 sum of the partial rows, Jacobians to the 12 parameters,
 //             per-sample loss; the last block to finish averages the batch (fixed order, so results are
 //             bit-reproducible run to run)
@@ -20,40 +22,67 @@ using namespace sq;
 
 namespace {
 
-// Tunables (tools/tune.py builds variants with -D to measure them on the GPU; the defaults are the measured best).
-#ifndef SQ_THREADS
-#define SQ_THREADS 256                   // column-kernel block size
+// Tunables (tools/tune.py builds variants with -D to measure them on the GPU; the defaults are the measured best,
+// profiles/tune_r01.txt).  Per column kernel: block size, min resident blocks per SM (register cap), columns per
+// thread and warp work item.
+#ifndef SQ_IMPB_THREADS
+#define SQ_IMPB_THREADS 128              // implicit fwd+bwd
 #endif
-#ifndef SQ_MAX_CPT
-#define SQ_MAX_CPT 2                     // columns per thread and work item
+#ifndef SQ_IMPB_MINB
+#define SQ_IMPB_MINB 6
 #endif
-#ifndef SQ_IMP_MINB
-#define SQ_IMP_MINB 2                    // min resident blocks/SM of the implicit fwd+bwd kernel (register cap)
+#ifndef SQ_IMPB_CPT
+#define SQ_IMPB_CPT 2
+#endif
+#ifndef SQ_IMPF_THREADS
+#define SQ_IMPF_THREADS 256              // implicit fwd only (validation, depth rendering)
+#endif
+#ifndef SQ_IMPF_MINB
+#define SQ_IMPF_MINB 4
+#endif
+#ifndef SQ_IMPF_CPT
+#define SQ_IMPF_CPT 1
+#endif
+#ifndef SQ_EXP_THREADS
+#define SQ_EXP_THREADS 256               // explicit fwd and fwd+bwd
 #endif
 #ifndef SQ_EXP_MINB
 #define SQ_EXP_MINB 2
 #endif
-constexpr int kThreads = SQ_THREADS;
+#ifndef SQ_EXP_CPT
+#define SQ_EXP_CPT 1
+#endif
+#ifndef SQ_IOU_THREADS
+#define SQ_IOU_THREADS 128
+#endif
+#ifndef SQ_IOU_MINB
+#define SQ_IOU_MINB 4
+#endif
+#ifndef SQ_IOU_CPT
+#define SQ_IOU_CPT 1
+#endif
+constexpr int kThreads = 256;            // block size of the small kernels (point list, field)
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxCpt = SQ_MAX_CPT;
 
 // ------------------------------------------------------------------------------------------------ layout
 // Column slots of one sample.  When n is a multiple of 8 a warp owns an 8(x) x 4(y) patch, which keeps the lanes of
-// a warp at similar depth along z (the backward is entered per warp); otherwise slots are the n*n columns in
-// x-fastest order.  Slots beyond n*n (last block only) are masked.
+// a warp at similar depth along z (the culled z range and the backward are entered per warp); otherwise slots are
+// the n*n columns in x-fastest order.  Slots beyond n*n (last warp only) are masked.
+// Work is handed out per WARP: warp item w of a sample covers slots [w*32*cpt, (w+1)*32*cpt).  Warps never
+// synchronise with each other (no __syncthreads in the column kernels), each writes its own partial row.
 struct Layout {
-    int n, patched, slots, cpt, items_per_sample;
+    int n, patched, slots, cpt, rows_per_sample;
 };
 
-__host__ __device__ inline Layout make_layout(int n) {
+__host__ __device__ inline Layout make_layout(int n, int max_cpt) {
     Layout L;
     L.n = n;
     L.patched = (n % 8 == 0);
     L.slots = n * n;
-    L.cpt = (L.slots + kThreads - 1) / kThreads;
-    if (L.cpt > kMaxCpt) L.cpt = kMaxCpt;
-    const int per_item = L.cpt * kThreads;
-    L.items_per_sample = (L.slots + per_item - 1) / per_item;
+    L.cpt = (L.slots + 31) / 32;
+    if (L.cpt > max_cpt) L.cpt = max_cpt;
+    const int per_item = L.cpt * 32;
+    L.rows_per_sample = (L.slots + per_item - 1) / per_item;
     return L;
 }
 
@@ -74,7 +103,7 @@ __device__ __forceinline__ bool slot_to_xy(const Layout& L, int slot, int& ia, i
 struct Scratch {
     Sample* pred;          // [batch]
     Sample* tru;           // [batch]
-    float* partials;       // [batch * items_per_sample][kAccN]
+    float* partials;       // [batch * rows_per_sample][kAccN]
     double* per_sample;    // [batch]
     unsigned long long* counts;   // [batch][2] (IoU)
     unsigned int* ticket;  // [1]
@@ -83,15 +112,16 @@ struct Scratch {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
-    const Layout L = make_layout(n > 0 ? n : 1);
+    const Layout L = make_layout(n > 0 ? n : 1, 1);      // cpt = 1: the most rows any kernel configuration writes
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_pred = take(sizeof(Sample) * (size_t)batch);
     const size_t o_true = take(sizeof(Sample) * (size_t)batch);
-    // partial rows: the column kernels use items_per_sample rows per sample, the point-list kernel one row per
-    // 256 pixels; reserve the larger (cpt = 1) count
-    const size_t rows = (size_t)batch * ((L.slots + kThreads - 1) / kThreads);
-    const size_t o_part = take(sizeof(float) * kAccN * rows);
+    // partial rows: one per warp item for the column kernels, one per 256 pixels for the point-list kernel
+    size_t rows_ps = (size_t)L.rows_per_sample;
+    const size_t lsq_rows = (size_t)(L.slots + kThreads - 1) / kThreads;
+    if (lsq_rows > rows_ps) rows_ps = lsq_rows;
+    const size_t o_part = take(sizeof(float) * kAccN * rows_ps * (size_t)batch);
     const size_t o_ps = take(sizeof(double) * (size_t)batch);
     const size_t o_cnt = take(sizeof(unsigned long long) * 2 * (size_t)batch);
     const size_t o_tick = take(sizeof(unsigned int) * 4);
@@ -124,22 +154,40 @@ __global__ void prep_kernel(const void* params, int dtype, int batch, int clamp,
     }
 }
 
-// ------------------------------------------------------------------------------------------------ block reduce
+// ------------------------------------------------------------------------------------------------ reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-// per-thread Acc -> one row of kAccN floats per block
-__device__ __forceinline__ void block_reduce_store(const Acc& a, float (*red)[kAccN], float* row) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float v[kAccN];
+__device__ __forceinline__ void acc_to_array(const Acc& a, float* v) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) { v[i] = a.gs[i]; v[12 + i] = a.wa[i]; }
 #pragma unroll
     for (int i = 0; i < 9; ++i) v[3 + i] = a.gm[i];
     v[15] = a.ge[0]; v[16] = a.ge[1]; v[17] = a.loss;
+}
+
+// per-thread Acc -> one row of kAccN floats per WARP (lane i ends up holding and storing sum i)
+__device__ __forceinline__ void warp_reduce_store(const Acc& a, float* row) {
+    const int lane = threadIdx.x & 31;
+    float v[kAccN];
+    acc_to_array(a, v);
+    float mine = 0.f;
+#pragma unroll
+    for (int i = 0; i < kAccN; ++i) {
+        const float s = warp_sum(v[i]);
+        if (lane == i) mine = s;
+    }
+    if (lane < kAccN) row[lane] = mine;
+}
+
+// per-thread Acc -> one row of kAccN floats per BLOCK (point-list kernel)
+__device__ __forceinline__ void block_reduce_store(const Acc& a, float (*red)[kAccN], float* row) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float v[kAccN];
+    acc_to_array(a, v);
 #pragma unroll
     for (int i = 0; i < kAccN; ++i) {
         const float s = warp_sum(v[i]);
@@ -154,35 +202,47 @@ __device__ __forceinline__ void block_reduce_store(const Acc& a, float (*red)[kA
     }
 }
 
-__device__ __forceinline__ void load_sample(Sample* dst, const Sample* src) {
+__device__ __forceinline__ void load_sample(Sample* dst, const Sample* src) {       // whole block
     static_assert(sizeof(Sample) % 4 == 0, "Sample must be word-copyable");
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
     for (int i = threadIdx.x; i < (int)(sizeof(Sample) / 4); i += blockDim.x) d[i] = s[i];
 }
 
+__device__ __forceinline__ void warp_load_sample(Sample* dst, const Sample* src) {  // one warp, private copy
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    for (int i = threadIdx.x & 31; i < (int)(sizeof(Sample) / 4); i += 32) d[i] = s[i];
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ ImplicitLoss
-template <bool BWD>
-__global__ void __launch_bounds__(kThreads, BWD ? SQ_IMP_MINB : 4)
-implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitParams P,
+template <bool BWD, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitParams P, int total_items,
                 const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
-    __shared__ Sample S;
-    __shared__ float red[kWarps][kAccN];
-    const int item = blockIdx.x;
-    const int b = item / L.items_per_sample, chunk = item - b * L.items_per_sample;
-    load_sample(&S, samples + b);
-    __syncthreads();
+    __shared__ Sample Ssh[THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (THREADS / 32) + warp;
+    if (item >= total_items) return;                      // warp-uniform; no block-level barrier anywhere below
+    const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
+    Sample& S = Ssh[warp];
+    warp_load_sample(&S, samples + b);
 
     Acc acc;
     acc_zero(acc);
     for (int k = 0; k < L.cpt; ++k) {
-        const int slot = (chunk * L.cpt + k) * kThreads + threadIdx.x;
+        const int slot = (chunk * L.cpt + k) * 32 + lane;
         int ia, ib;
         const bool valid = slot_to_xy(L, slot, ia, ib);
         float bh[3], bl[3], cg[11];
         column_base(S, g, ia, ib, bh, bl);
-        const float depth = implicit_column<BWD>(S, g, P, bh, bl, cg);
+        int c_lo, c_hi;
+        column_range(S, g, P.bound, bh, c_lo, c_hi);
+        if (!valid) { c_lo = 0; c_hi = -1; }               // masked lanes do not widen the warp's range
+        warp_range(g.n, c_lo, c_hi);
+        const float depth = implicit_column<BWD>(S, g, P, bh, bl, c_lo, c_hi, cg);
         const int row = g.n - 1 - ib, col = ia;            // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
         if (valid) {
             if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
@@ -197,35 +257,43 @@ implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitPa
             }
         }
     }
-    block_reduce_store(acc, red, partials + (size_t)item * kAccN);
+    if (target) warp_reduce_store(acc, partials + (size_t)item * kAccN);
 }
 
 // ------------------------------------------------------------------------------------------------ ExplicitLoss
 template <bool BWD>
-__global__ void __launch_bounds__(kThreads, SQ_EXP_MINB)
+__global__ void __launch_bounds__(SQ_EXP_THREADS, SQ_EXP_MINB)
 explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, float kl,
-                float* __restrict__ partials) {
-    __shared__ Sample St, Sp;
-    __shared__ float red[kWarps][kAccN];
-    const int item = blockIdx.x;
-    const int b = item / L.items_per_sample, chunk = item - b * L.items_per_sample;
-    load_sample(&St, tru + b);
-    load_sample(&Sp, pred + b);
-    __syncthreads();
+                float bound, int total_items, float* __restrict__ partials) {
+    __shared__ Sample Tsh[SQ_EXP_THREADS / 32], Psh[SQ_EXP_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (SQ_EXP_THREADS / 32) + warp;
+    if (item >= total_items) return;
+    const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
+    Sample& St = Tsh[warp];
+    Sample& Sp = Psh[warp];
+    warp_load_sample(&St, tru + b);
+    warp_load_sample(&Sp, pred + b);
 
     Acc acc;
     acc_zero(acc);
     for (int k = 0; k < L.cpt; ++k) {
-        const int slot = (chunk * L.cpt + k) * kThreads + threadIdx.x;
+        const int slot = (chunk * L.cpt + k) * 32 + lane;
         int ia, ib;
         const bool valid = slot_to_xy(L, slot, ia, ib);
         float bht[3], blt[3], bhp[3], blp[3];
         column_base(St, g, ia, ib, bht, blt);
         column_base(Sp, g, ia, ib, bhp, blp);
+        Range rt, rp;
+        column_range(St, g, bound, bht, rt.lo, rt.hi);
+        column_range(Sp, g, bound, bhp, rp.lo, rp.hi);
+        if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }      // masked lanes do not widen the warp's range
+        warp_range(g.n, rt.lo, rt.hi);
+        warp_range(g.n, rp.lo, rp.hi);
         Acc col;
         acc_zero(col);
         const float dx = (float)(grid_coord(g, ia) - Sp.t[0]), dy = (float)(grid_coord(g, ib) - Sp.t[1]);
-        const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, dx, dy, col);
+        const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, rt, rp, dx, dy, col);
         if (valid) {
             acc.loss += sq;
             if (BWD) {
@@ -237,41 +305,45 @@ explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred,
             }
         }
     }
-    block_reduce_store(acc, red, partials + (size_t)item * kAccN);
+    warp_reduce_store(acc, partials + (size_t)item * kAccN);
 }
 
 // ------------------------------------------------------------------------------------------------ IoU
-__global__ void __launch_bounds__(kThreads, 2)
-iou_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L,
+__global__ void __launch_bounds__(SQ_IOU_THREADS, SQ_IOU_MINB)
+iou_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, int total_items,
            unsigned long long* __restrict__ counts) {
-    __shared__ Sample St, Sp;
-    __shared__ unsigned int red[kWarps][2];
-    const int item = blockIdx.x;
-    const int b = item / L.items_per_sample, chunk = item - b * L.items_per_sample;
-    load_sample(&St, tru + b);
-    load_sample(&Sp, pred + b);
-    __syncthreads();
+    __shared__ Sample Tsh[SQ_IOU_THREADS / 32], Psh[SQ_IOU_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * (SQ_IOU_THREADS / 32) + warp;
+    if (item >= total_items) return;
+    const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
+    Sample& St = Tsh[warp];
+    Sample& Sp = Psh[warp];
+    warp_load_sample(&St, tru + b);
+    warp_load_sample(&Sp, pred + b);
     unsigned inter = 0, uni = 0;
     for (int k = 0; k < L.cpt; ++k) {
-        const int slot = (chunk * L.cpt + k) * kThreads + threadIdx.x;
+        const int slot = (chunk * L.cpt + k) * 32 + lane;
         int ia, ib;
         const bool valid = slot_to_xy(L, slot, ia, ib);
         float bht[3], blt[3], bhp[3], blp[3];
         column_base(St, g, ia, ib, bht, blt);
         column_base(Sp, g, ia, ib, bhp, blp);
+        Range rt, rp;
+        column_range(St, g, kIoUBound, bht, rt.lo, rt.hi);
+        column_range(Sp, g, kIoUBound, bhp, rp.lo, rp.hi);
+        if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }
+        warp_range(g.n, rt.lo, rt.hi);
+        warp_range(g.n, rp.lo, rp.hi);
         unsigned i = 0, u = 0;
-        iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, i, u);
+        iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
         if (valid) { inter += i; uni += u; }
     }
     inter = __reduce_add_sync(0xffffffffu, inter);
     uni = __reduce_add_sync(0xffffffffu, uni);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { red[warp][0] = inter; red[warp][1] = uni; }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        unsigned long long s = 0;
-        for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
-        atomicAdd(counts + 2 * b + threadIdx.x, s);       // integer atomics: order-independent, exact
+    if (lane == 0) {                                      // integer atomics: order-independent, exact
+        atomicAdd(counts + 2 * b, (unsigned long long)inter);
+        atomicAdd(counts + 2 * b + 1, (unsigned long long)uni);
     }
 }
 
@@ -444,25 +516,28 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
     if (grad_pred && !target) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g{n, step, z0};
-    const Layout L = make_layout(n);
-    const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, tau};
+    const Layout L = make_layout(n, grad_pred ? SQ_IMPB_CPT : SQ_IMPF_CPT);
+    const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, cull_bound(sharpness * kLog2e)};
     rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
     if (rc) return rc;
-    const int items = batch * L.items_per_sample;
+    const int items = batch * L.rows_per_sample;
     {
         ColumnKernelTimer timer(st);
-        if (grad_pred)
-            implicit_kernel<true><<<items, kThreads, 0, st>>>(s.pred, g, L, P, target, target_stride_b, row_off,
-                                                              col_off, s.partials, depth_out);
-        else
-            implicit_kernel<false><<<items, kThreads, 0, st>>>(s.pred, g, L, P, target, target_stride_b, row_off,
-                                                               col_off, s.partials, depth_out);
+        if (grad_pred) {
+            constexpr int W = SQ_IMPB_THREADS / 32;
+            implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB><<<(items + W - 1) / W, SQ_IMPB_THREADS, 0, st>>>(
+                s.pred, g, L, P, items, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+        } else {
+            constexpr int W = SQ_IMPF_THREADS / 32;
+            implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB><<<(items + W - 1) / W, SQ_IMPF_THREADS, 0, st>>>(
+                s.pred, g, L, P, items, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+        }
     }
     SQ_TRY(cudaGetLastError());
     if (target) {
         const double nn = (double)n * n;
         finalize_kernel<FIN_IMPLICIT><<<batch, 32, 0, st>>>(
-            s.pred, g, batch, L.items_per_sample, s.partials, 1.0 / nn,
+            s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn,
             -(double)sharpness * (double)tau / (nn * n * (double)batch), pred_dtype, grad_pred, s.per_sample,
             per_sample, loss_out, s.ticket);
         SQ_TRY(cudaGetLastError());
@@ -478,21 +553,23 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g{n, step, z0};
-    const Layout L = make_layout(n);
+    const Layout L = make_layout(n, SQ_EXP_CPT);
     rc = launch_prep(true_params, params_dtype, batch, true, g, s.tru, nullptr, nullptr, st);
     if (rc) return rc;
     rc = launch_prep(pred, params_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
     if (rc) return rc;
-    const int items = batch * L.items_per_sample;
+    constexpr int WE = SQ_EXP_THREADS / 32;
+    const int items = batch * L.rows_per_sample, blocks = (items + WE - 1) / WE;
+    const float kl = sharpness * kLog2e, bound = cull_bound(kl);
     {
         ColumnKernelTimer timer(st);
-        if (grad_pred) explicit_kernel<true><<<items, kThreads, 0, st>>>(s.tru, s.pred, g, L, sharpness * kLog2e, s.partials);
-        else explicit_kernel<false><<<items, kThreads, 0, st>>>(s.tru, s.pred, g, L, sharpness * kLog2e, s.partials);
+        if (grad_pred) explicit_kernel<true><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.partials);
+        else explicit_kernel<false><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.partials);
     }
     SQ_TRY(cudaGetLastError());
     const double n3 = (double)n * n * n;
     finalize_kernel<FIN_EXPLICIT><<<batch, 32, 0, st>>>(
-        s.pred, g, batch, L.items_per_sample, s.partials, (double)mult / n3,
+        s.pred, g, batch, L.rows_per_sample, s.partials, (double)mult / n3,
         2.0 * (double)sharpness * (double)mult / (n3 * (double)batch), params_dtype, grad_pred, s.per_sample,
         per_sample, loss_out, s.ticket);
     SQ_TRY(cudaGetLastError());
@@ -508,14 +585,16 @@ int sq_iou_counts(const void* true_params, const void* pred, int params_dtype, i
     if (!inter || !uni) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g{n, step, z0};
-    const Layout L = make_layout(n);
+    const Layout L = make_layout(n, SQ_IOU_CPT);
     rc = launch_prep(true_params, params_dtype, batch, false, g, s.tru, nullptr, nullptr, st);
     if (rc) return rc;
     rc = launch_prep(pred, params_dtype, batch, false, g, s.pred, nullptr, s.counts, st);
     if (rc) return rc;
+    constexpr int WI = SQ_IOU_THREADS / 32;
+    const int items = batch * L.rows_per_sample, blocks = (items + WI - 1) / WI;
     {
         ColumnKernelTimer timer(st);
-        iou_kernel<<<batch * L.items_per_sample, kThreads, 0, st>>>(s.tru, s.pred, g, L, s.counts);
+        iou_kernel<<<blocks, SQ_IOU_THREADS, 0, st>>>(s.tru, s.pred, g, L, items, s.counts);
     }
     SQ_TRY(cudaGetLastError());
     iou_export_kernel<<<(batch + 127) / 128, 128, 0, st>>>(s.counts, batch, inter, uni);

@@ -23,7 +23,7 @@ extern "C" {
 int emu_implicit(const double* pred, int B, int n, double step, double z0, const float* target, float tau, float k,
                  double* loss_out, double* grad /*[B,12] or null*/, float* depth_out /*or null*/) {
     Grid g{n, step, z0};
-    ImplicitParams P{k * kLog2e, tau * kLog2e, tau};
+    ImplicitParams P{k * kLog2e, tau * kLog2e, cull_bound(k * kLog2e)};
     double total = 0.0;
     for (int b = 0; b < B; ++b) {
         double p[12]; for (int i = 0; i < 12; ++i) p[i] = pred[12 * b + i];
@@ -32,7 +32,11 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
         for (int ib = 0; ib < n; ++ib) for (int ia = 0; ia < n; ++ia) {
             float bh[3], bl[3], cg[11];
             column_base(S, g, ia, ib, bh, bl);
-            const float depth = grad ? implicit_column<true>(S, g, P, bh, bl, cg) : implicit_column<false>(S, g, P, bh, bl, cg);
+            int c_lo, c_hi;
+            column_range(S, g, P.bound, bh, c_lo, c_hi);
+            warp_range(n, c_lo, c_hi);
+            const float depth = grad ? implicit_column<true>(S, g, P, bh, bl, c_lo, c_hi, cg)
+                                     : implicit_column<false>(S, g, P, bh, bl, c_lo, c_hi, cg);
             const int row = n - 1 - ib, col = ia;
             if (depth_out) depth_out[(size_t)b * n * n + row * n + col] = depth;
             const float tgt = target ? target[(size_t)b * n * n + row * n + col] : 0.f;
@@ -70,8 +74,12 @@ int emu_explicit(const double* tru, const double* pred, int B, int n, double ste
             column_base(Sp, g, ia, ib, bhp, blp);
             Acc a; acc_zero(a);
             const float dx = (float)(grid_coord(g, ia) - Sp.t[0]), dy = (float)(grid_coord(g, ib) - Sp.t[1]);
-            a.loss = grad ? explicit_column<true>(St, Sp, g, k * kLog2e, bht, blt, bhp, blp, dx, dy, a)
-                          : explicit_column<false>(St, Sp, g, k * kLog2e, bht, blt, bhp, blp, dx, dy, a);
+            const float bound = cull_bound(k * kLog2e);
+            Range rt, rp;
+            column_range(St, g, bound, bht, rt.lo, rt.hi); warp_range(n, rt.lo, rt.hi);
+            column_range(Sp, g, bound, bhp, rp.lo, rp.hi); warp_range(n, rp.lo, rp.hi);
+            a.loss = grad ? explicit_column<true>(St, Sp, g, k * kLog2e, bht, blt, bhp, blp, rt, rp, dx, dy, a)
+                          : explicit_column<false>(St, Sp, g, k * kLog2e, bht, blt, bhp, blp, rt, rp, dx, dy, a);
             acc_to_double(a, accd);
         }
         const double n3 = (double)n * n * n;
@@ -94,7 +102,10 @@ int emu_iou(const double* tru, const double* pred, int B, int n, double step, lo
             column_base(St, g, ia, ib, bht, blt);
             column_base(Sp, g, ia, ib, bhp, blp);
             unsigned i = 0, u = 0;
-            iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, i, u);
+            Range rt, rp;
+            column_range(St, g, kIoUBound, bht, rt.lo, rt.hi); warp_range(n, rt.lo, rt.hi);
+            column_range(Sp, g, kIoUBound, bhp, rp.lo, rp.hi); warp_range(n, rp.lo, rp.hi);
+            iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
             I += i; U += u;
         }
         inter[b] = I; uni[b] = U;
