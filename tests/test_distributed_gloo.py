@@ -71,4 +71,4 @@ def test_two_ranks_match_single_process():
     for rank, g_mean, grad, g_iou in out:
         assert abs(g_mean - ref.item()) < 1e-12
         assert abs(g_iou - iou) < 1e-7
-    np.testing.assert_allclose(np.concatenate([o[2] for o in out]), p.grad.double().numpy(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(np.concatenate([o[2] for o in out]), p.grad.double().numpy(), rtol=1e-6, atol=1e-9)   # fp32 leaves
