@@ -29,10 +29,10 @@ namespace {
 #define SQ_IMPB_THREADS 128              // implicit fwd+bwd
 #endif
 #ifndef SQ_IMPB_MINB
-#define SQ_IMPB_MINB 6
+#define SQ_IMPB_MINB 5
 #endif
 #ifndef SQ_IMPB_CPT
-#define SQ_IMPB_CPT 2
+#define SQ_IMPB_CPT 1
 #endif
 #ifndef SQ_IMPF_THREADS
 #define SQ_IMPF_THREADS 256              // implicit fwd only (validation, depth rendering)
@@ -86,18 +86,42 @@ __host__ __device__ inline Layout make_layout(int n, int max_cpt) {
     return L;
 }
 
-__device__ __forceinline__ bool slot_to_xy(const Layout& L, int slot, int& ia, int& ib) {
-    if (slot >= L.slots) { ia = 0; ib = 0; return false; }
-    if (L.patched) {
-        const int patch = slot >> 5, lane = slot & 31, pw = L.n >> 3;
-        ia = ((patch % pw) << 3) + (lane & 7);
-        ib = ((patch / pw) << 2) + (lane >> 3);
-    } else {
-        ia = slot % L.n;
-        ib = slot / L.n;
+// Column (x, y) of lane `lane` for the k-th 32-slot group of a warp item.  Item j of a sample owns groups
+// j, j + J, j + 2J, ... (J = rows_per_sample): its columns are spread over the whole image, so the items of one
+// sample cost about the same (objects sit near the image centre; a contiguous tile would be all-empty or all-full).
+struct ColIter {
+    int ia, ib, slot;
+    int pa, pb, jq, jr;       // patched layout: patch coordinates and the per-step patch advance (J / pw, J % pw)
+    __device__ __forceinline__ void init(const Layout& L, int first_group, int lane) {
+        slot = first_group * 32 + lane;
+        if (L.patched) {
+            const int pw = L.n >> 3, J = L.rows_per_sample;
+            pb = first_group / pw;                     // once per work item
+            pa = first_group - pb * pw;
+            jq = J / pw;
+            jr = J - jq * pw;
+            ia = (pa << 3) + (lane & 7);
+            ib = (pb << 2) + (lane >> 3);
+        } else {
+            ib = slot / L.n;
+            ia = slot - ib * L.n;
+            pa = pb = jq = jr = 0;
+        }
     }
-    return true;
-}
+    __device__ __forceinline__ void next(const Layout& L) {
+        slot += 32 * L.rows_per_sample;
+        if (L.patched) {
+            pa += jr; pb += jq;
+            if (pa >= (L.n >> 3)) { pa -= (L.n >> 3); ++pb; }
+            ia = (pa << 3) + (slot & 7);
+            ib = (pb << 2) + ((slot & 31) >> 3);
+        } else {
+            ib = slot / L.n;
+            ia = slot - ib * L.n;
+        }
+    }
+    __device__ __forceinline__ bool valid(const Layout& L) const { return slot < L.slots; }
+};
 
 // ------------------------------------------------------------------------------------------------ scratch
 struct Scratch {
@@ -106,7 +130,7 @@ struct Scratch {
     float* partials;       // [batch * rows_per_sample][kAccN]
     double* per_sample;    // [batch]
     unsigned long long* counts;   // [batch][2] (IoU)
-    unsigned int* ticket;  // [1]
+    unsigned int* ticket;  // [0] finalize ticket, [1] work-stealing cursor of the column kernel
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -140,7 +164,7 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
 __global__ void prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample* out,
                             unsigned int* ticket, unsigned long long* counts) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0 && ticket) *ticket = 0u;
+    if (b == 0 && ticket) { ticket[0] = 0u; ticket[1] = 0u; }
     if (b < batch) {
         double p[12];
 #pragma unroll
@@ -209,141 +233,196 @@ __device__ __forceinline__ void load_sample(Sample* dst, const Sample* src) {   
     for (int i = threadIdx.x; i < (int)(sizeof(Sample) / 4); i += blockDim.x) d[i] = s[i];
 }
 
-__device__ __forceinline__ void warp_load_sample(Sample* dst, const Sample* src) {  // one warp, private copy
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-    for (int i = threadIdx.x & 31; i < (int)(sizeof(Sample) / 4); i += 32) d[i] = s[i];
-    __syncwarp();
+// Register-staged copy of one Sample by one warp: fetch() issues the global loads (their latency overlaps whatever
+// the warp does next), commit() writes them to the warp's private shared-memory copy.
+constexpr int kSampleWords = (int)(sizeof(Sample) / 4);
+constexpr int kSampleRegs = (kSampleWords + 31) / 32;
+struct SampleFetch {
+    uint32_t w[kSampleRegs];
+    __device__ __forceinline__ void fetch(const Sample* src, int lane) {
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+        for (int j = 0; j < kSampleRegs; ++j) {
+            const int i = lane + 32 * j;
+            w[j] = i < kSampleWords ? __ldg(s + i) : 0u;
+        }
+    }
+    __device__ __forceinline__ void commit(Sample* dst, int lane) const {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        __syncwarp();                                      // everyone is done with the previous contents
+#pragma unroll
+        for (int j = 0; j < kSampleRegs; ++j) {
+            const int i = lane + 32 * j;
+            if (i < kSampleWords) d[i] = w[j];
+        }
+        __syncwarp();
+    }
+};
+
+__device__ __forceinline__ int next_item(unsigned int* cursor, int lane) {
+    int item = 0;
+    if (lane == 0) item = (int)atomicAdd(cursor, 1u);
+    return __shfl_sync(0xffffffffu, item, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ ImplicitLoss
 template <bool BWD, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitParams P, int total_items,
-                const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
+                unsigned int* __restrict__ cursor, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
     __shared__ Sample Ssh[THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.x * (THREADS / 32) + warp;
-    if (item >= total_items) return;                      // warp-uniform; no block-level barrier anywhere below
-    const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
     Sample& S = Ssh[warp];
-    warp_load_sample(&S, samples + b);
+    // Persistent warps pull work items from a global cursor: item cost varies a lot with the culled z range, and a
+    // static assignment left the SMs idle at the tail.  The next item and its Sample are fetched while the current
+    // item is processed.  No block-level barrier anywhere.
+    int item = next_item(cursor, lane);
+    SampleFetch pre;
+    if (item < total_items) pre.fetch(samples + item / L.rows_per_sample, lane);
+    while (item < total_items) {
+        const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
+        pre.commit(&S, lane);
+        const int upcoming = next_item(cursor, lane);
+        if (upcoming < total_items) pre.fetch(samples + upcoming / L.rows_per_sample, lane);
 
-    Acc acc;
-    acc_zero(acc);
-    for (int k = 0; k < L.cpt; ++k) {
-        const int slot = (chunk * L.cpt + k) * 32 + lane;
-        int ia, ib;
-        const bool valid = slot_to_xy(L, slot, ia, ib);
-        float bh[3], bl[3], cg[11];
-        column_base(S, g, ia, ib, bh, bl);
-        int c_lo, c_hi;
-        column_range(S, g, P.bound, bh, c_lo, c_hi);
-        if (!valid) { c_lo = 0; c_hi = -1; }               // masked lanes do not widen the warp's range
-        warp_range(g.n, c_lo, c_hi);
-        const float depth = implicit_column<BWD>(S, g, P, bh, bl, c_lo, c_hi, cg);
-        const int row = g.n - 1 - ib, col = ia;            // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
-        if (valid) {
-            if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
-            if (target) {
-                const float tv = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
-                const float diff = depth - tv;
-                acc.loss += fabsf(diff);
-                if (BWD) {
-                    const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                    implicit_fold(acc, cg, w, (float)(grid_coord(g, ia) - S.t[0]), (float)(grid_coord(g, ib) - S.t[1]));
+        Acc acc;
+        acc_zero(acc);
+        ColIter it;
+        it.init(L, chunk, lane);
+        for (int k = 0; k < L.cpt; ++k, it.next(L)) {
+            const int ia = it.ia, ib = it.ib;
+            const bool valid = it.valid(L);
+            const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
+            float tv = 0.f;                                // issued now, needed after the z walk
+            if (valid && target) tv = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
+            float bh[3], bl[3], cg[11];
+            column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl);
+            int c_lo, c_hi;
+            column_range(S, g, P.bound, bh, c_lo, c_hi);
+            if (!valid) { c_lo = 0; c_hi = -1; }           // masked lanes do not widen the warp's range
+            warp_range(g.n, c_lo, c_hi);
+            const float depth = implicit_column<BWD>(S, g, P, bh, bl, c_lo, c_hi, cg);
+            if (valid) {
+                if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
+                if (target) {
+                    const float diff = depth - tv;
+                    acc.loss += fabsf(diff);
+                    if (BWD) {
+                        const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                        implicit_fold(acc, cg, w, (float)(grid_coord(g, ia) - S.t[0]), (float)(grid_coord(g, ib) - S.t[1]));
+                    }
                 }
             }
         }
+        if (target) warp_reduce_store(acc, partials + (size_t)item * kAccN);
+        item = upcoming;
     }
-    if (target) warp_reduce_store(acc, partials + (size_t)item * kAccN);
 }
 
 // ------------------------------------------------------------------------------------------------ ExplicitLoss
 template <bool BWD>
 __global__ void __launch_bounds__(SQ_EXP_THREADS, SQ_EXP_MINB)
 explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, float kl,
-                float bound, int total_items, float* __restrict__ partials) {
+                float bound, int total_items, unsigned int* __restrict__ cursor, float* __restrict__ partials) {
     __shared__ Sample Tsh[SQ_EXP_THREADS / 32], Psh[SQ_EXP_THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.x * (SQ_EXP_THREADS / 32) + warp;
-    if (item >= total_items) return;
-    const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
     Sample& St = Tsh[warp];
     Sample& Sp = Psh[warp];
-    warp_load_sample(&St, tru + b);
-    warp_load_sample(&Sp, pred + b);
-
-    Acc acc;
-    acc_zero(acc);
-    for (int k = 0; k < L.cpt; ++k) {
-        const int slot = (chunk * L.cpt + k) * 32 + lane;
-        int ia, ib;
-        const bool valid = slot_to_xy(L, slot, ia, ib);
-        float bht[3], blt[3], bhp[3], blp[3];
-        column_base(St, g, ia, ib, bht, blt);
-        column_base(Sp, g, ia, ib, bhp, blp);
-        Range rt, rp;
-        column_range(St, g, bound, bht, rt.lo, rt.hi);
-        column_range(Sp, g, bound, bhp, rp.lo, rp.hi);
-        if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }      // masked lanes do not widen the warp's range
-        warp_range(g.n, rt.lo, rt.hi);
-        warp_range(g.n, rp.lo, rp.hi);
-        Acc col;
-        acc_zero(col);
-        const float dx = (float)(grid_coord(g, ia) - Sp.t[0]), dy = (float)(grid_coord(g, ib) - Sp.t[1]);
-        const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, rt, rp, dx, dy, col);
-        if (valid) {
-            acc.loss += sq;
-            if (BWD) {
+    int item = next_item(cursor, lane);
+    SampleFetch pre_t, pre_p;
+    if (item < total_items) { pre_t.fetch(tru + item / L.rows_per_sample, lane); pre_p.fetch(pred + item / L.rows_per_sample, lane); }
+    while (item < total_items) {
+        const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
+        pre_t.commit(&St, lane);
+        pre_p.commit(&Sp, lane);
+        const int upcoming = next_item(cursor, lane);
+        if (upcoming < total_items) {
+            pre_t.fetch(tru + upcoming / L.rows_per_sample, lane);
+            pre_p.fetch(pred + upcoming / L.rows_per_sample, lane);
+        }
+        Acc acc;
+        acc_zero(acc);
+        ColIter it;
+        it.init(L, chunk, lane);
+        for (int k = 0; k < L.cpt; ++k, it.next(L)) {
+            const bool valid = it.valid(L);
+            const int ia = valid ? it.ia : 0, ib = valid ? it.ib : 0;
+            float bht[3], blt[3], bhp[3], blp[3];
+            column_base(St, g, ia, ib, bht, blt);
+            column_base(Sp, g, ia, ib, bhp, blp);
+            Range rt, rp;
+            column_range(St, g, bound, bht, rt.lo, rt.hi);
+            column_range(Sp, g, bound, bhp, rp.lo, rp.hi);
+            if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }      // masked lanes do not widen the warp's range
+            warp_range(g.n, rt.lo, rt.hi);
+            warp_range(g.n, rp.lo, rp.hi);
+            Acc col;
+            acc_zero(col);
+            const float dx = (float)(grid_coord(g, ia) - Sp.t[0]), dy = (float)(grid_coord(g, ib) - Sp.t[1]);
+            const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, rt, rp, dx, dy, col);
+            if (valid) {
+                acc.loss += sq;
+                if (BWD) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) { acc.gs[i] += col.gs[i]; acc.wa[i] += col.wa[i]; }
+                    for (int i = 0; i < 3; ++i) { acc.gs[i] += col.gs[i]; acc.wa[i] += col.wa[i]; }
 #pragma unroll
-                for (int i = 0; i < 9; ++i) acc.gm[i] += col.gm[i];
-                acc.ge[0] += col.ge[0]; acc.ge[1] += col.ge[1];
+                    for (int i = 0; i < 9; ++i) acc.gm[i] += col.gm[i];
+                    acc.ge[0] += col.ge[0]; acc.ge[1] += col.ge[1];
+                }
             }
         }
+        warp_reduce_store(acc, partials + (size_t)item * kAccN);
+        item = upcoming;
     }
-    warp_reduce_store(acc, partials + (size_t)item * kAccN);
 }
 
 // ------------------------------------------------------------------------------------------------ IoU
 __global__ void __launch_bounds__(SQ_IOU_THREADS, SQ_IOU_MINB)
 iou_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, int total_items,
-           unsigned long long* __restrict__ counts) {
+           unsigned int* __restrict__ cursor, unsigned long long* __restrict__ counts) {
     __shared__ Sample Tsh[SQ_IOU_THREADS / 32], Psh[SQ_IOU_THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.x * (SQ_IOU_THREADS / 32) + warp;
-    if (item >= total_items) return;
-    const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
     Sample& St = Tsh[warp];
     Sample& Sp = Psh[warp];
-    warp_load_sample(&St, tru + b);
-    warp_load_sample(&Sp, pred + b);
-    unsigned inter = 0, uni = 0;
-    for (int k = 0; k < L.cpt; ++k) {
-        const int slot = (chunk * L.cpt + k) * 32 + lane;
-        int ia, ib;
-        const bool valid = slot_to_xy(L, slot, ia, ib);
-        float bht[3], blt[3], bhp[3], blp[3];
-        column_base(St, g, ia, ib, bht, blt);
-        column_base(Sp, g, ia, ib, bhp, blp);
-        Range rt, rp;
-        column_range(St, g, kIoUBound, bht, rt.lo, rt.hi);
-        column_range(Sp, g, kIoUBound, bhp, rp.lo, rp.hi);
-        if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }
-        warp_range(g.n, rt.lo, rt.hi);
-        warp_range(g.n, rp.lo, rp.hi);
-        unsigned i = 0, u = 0;
-        iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
-        if (valid) { inter += i; uni += u; }
-    }
-    inter = __reduce_add_sync(0xffffffffu, inter);
-    uni = __reduce_add_sync(0xffffffffu, uni);
-    if (lane == 0) {                                      // integer atomics: order-independent, exact
-        atomicAdd(counts + 2 * b, (unsigned long long)inter);
-        atomicAdd(counts + 2 * b + 1, (unsigned long long)uni);
+    int item = next_item(cursor, lane);
+    SampleFetch pre_t, pre_p;
+    if (item < total_items) { pre_t.fetch(tru + item / L.rows_per_sample, lane); pre_p.fetch(pred + item / L.rows_per_sample, lane); }
+    while (item < total_items) {
+        const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
+        pre_t.commit(&St, lane);
+        pre_p.commit(&Sp, lane);
+        const int upcoming = next_item(cursor, lane);
+        if (upcoming < total_items) {
+            pre_t.fetch(tru + upcoming / L.rows_per_sample, lane);
+            pre_p.fetch(pred + upcoming / L.rows_per_sample, lane);
+        }
+        unsigned inter = 0, uni = 0;
+        ColIter it;
+        it.init(L, chunk, lane);
+        for (int k = 0; k < L.cpt; ++k, it.next(L)) {
+            const bool valid = it.valid(L);
+            const int ia = valid ? it.ia : 0, ib = valid ? it.ib : 0;
+            float bht[3], blt[3], bhp[3], blp[3];
+            column_base(St, g, ia, ib, bht, blt);
+            column_base(Sp, g, ia, ib, bhp, blp);
+            Range rt, rp;
+            column_range(St, g, kIoUBound, bht, rt.lo, rt.hi);
+            column_range(Sp, g, kIoUBound, bhp, rp.lo, rp.hi);
+            if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }
+            warp_range(g.n, rt.lo, rt.hi);
+            warp_range(g.n, rp.lo, rp.hi);
+            unsigned i = 0, u = 0;
+            iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
+            if (valid) { inter += i; uni += u; }
+        }
+        inter = __reduce_add_sync(0xffffffffu, inter);
+        uni = __reduce_add_sync(0xffffffffu, uni);
+        if (lane == 0) {                                  // integer atomics: order-independent, exact
+            atomicAdd(counts + 2 * b, (unsigned long long)inter);
+            atomicAdd(counts + 2 * b + 1, (unsigned long long)uni);
+        }
+        item = upcoming;
     }
 }
 
@@ -475,6 +554,22 @@ int check_scratch(int batch, int n, void* scratch, size_t bytes, Scratch* s) {
     return 0;
 }
 
+// blocks of a persistent column kernel: enough to fill every SM at the kernel's occupancy, no more than the work
+int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        sms[dev] = n;
+    }
+    const int need = (items + warps_per_block - 1) / warps_per_block;
+    const int fill = sms[dev] * min_blocks_per_sm;
+    return need < fill ? need : fill;
+}
+
 int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid& g, Sample* out,
                 unsigned int* ticket, unsigned long long* counts, cudaStream_t st) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
@@ -524,13 +619,13 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
     {
         ColumnKernelTimer timer(st);
         if (grad_pred) {
-            constexpr int W = SQ_IMPB_THREADS / 32;
-            implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB><<<(items + W - 1) / W, SQ_IMPB_THREADS, 0, st>>>(
-                s.pred, g, L, P, items, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+            const int blocks = persistent_blocks(items, SQ_IMPB_THREADS / 32, SQ_IMPB_MINB);
+            implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB><<<blocks, SQ_IMPB_THREADS, 0, st>>>(
+                s.pred, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
         } else {
-            constexpr int W = SQ_IMPF_THREADS / 32;
-            implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB><<<(items + W - 1) / W, SQ_IMPF_THREADS, 0, st>>>(
-                s.pred, g, L, P, items, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+            const int blocks = persistent_blocks(items, SQ_IMPF_THREADS / 32, SQ_IMPF_MINB);
+            implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB><<<blocks, SQ_IMPF_THREADS, 0, st>>>(
+                s.pred, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
         }
     }
     SQ_TRY(cudaGetLastError());
@@ -558,13 +653,13 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     if (rc) return rc;
     rc = launch_prep(pred, params_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
     if (rc) return rc;
-    constexpr int WE = SQ_EXP_THREADS / 32;
-    const int items = batch * L.rows_per_sample, blocks = (items + WE - 1) / WE;
+    const int items = batch * L.rows_per_sample;
+    const int blocks = persistent_blocks(items, SQ_EXP_THREADS / 32, SQ_EXP_MINB);
     const float kl = sharpness * kLog2e, bound = cull_bound(kl);
     {
         ColumnKernelTimer timer(st);
-        if (grad_pred) explicit_kernel<true><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.partials);
-        else explicit_kernel<false><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.partials);
+        if (grad_pred) explicit_kernel<true><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.ticket + 1, s.partials);
+        else explicit_kernel<false><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.ticket + 1, s.partials);
     }
     SQ_TRY(cudaGetLastError());
     const double n3 = (double)n * n * n;
@@ -588,13 +683,13 @@ int sq_iou_counts(const void* true_params, const void* pred, int params_dtype, i
     const Layout L = make_layout(n, SQ_IOU_CPT);
     rc = launch_prep(true_params, params_dtype, batch, false, g, s.tru, nullptr, nullptr, st);
     if (rc) return rc;
-    rc = launch_prep(pred, params_dtype, batch, false, g, s.pred, nullptr, s.counts, st);
+    rc = launch_prep(pred, params_dtype, batch, false, g, s.pred, s.ticket, s.counts, st);
     if (rc) return rc;
-    constexpr int WI = SQ_IOU_THREADS / 32;
-    const int items = batch * L.rows_per_sample, blocks = (items + WI - 1) / WI;
+    const int items = batch * L.rows_per_sample;
+    const int blocks = persistent_blocks(items, SQ_IOU_THREADS / 32, SQ_IOU_MINB);
     {
         ColumnKernelTimer timer(st);
-        iou_kernel<<<blocks, SQ_IOU_THREADS, 0, st>>>(s.tru, s.pred, g, L, items, s.counts);
+        iou_kernel<<<blocks, SQ_IOU_THREADS, 0, st>>>(s.tru, s.pred, g, L, items, s.ticket + 1, s.counts);
     }
     SQ_TRY(cudaGetLastError());
     iou_export_kernel<<<(batch + 127) / 128, 128, 0, st>>>(s.counts, batch, inter, uni);

@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 from oracle import sq_oracle as O          # input distributions only
 from sq_recovery_b200 import _lib as L0     # prototypes
 
-B, R = 256, 64
+B, R = int(os.environ.get("SQ_B", 256)), 64
 dev = torch.device("cuda:0")
 
 
@@ -65,8 +65,13 @@ def timed(h, launch, iters=20):
 def main():
     import sq_recovery_b200 as S
     from sq_recovery_b200.functional import nearest_offsets
-    true = O.random_params(B, 0).to(dev)
-    pred = O.perturbed_params(O.random_params(B, 0), 7).to(dev)
+    true = O.random_params(B, 0)
+    pred = O.perturbed_params(true, 7)
+    if os.environ.get("SQ_SORT"):            # experiment: heaviest samples (largest clamped volume) first / last
+        vol = pred[:, 0].clamp(0.05, 1) * pred[:, 1].clamp(0.05, 1) * pred[:, 2].clamp(0.05, 1)
+        order = torch.argsort(vol, descending=os.environ["SQ_SORT"] == "desc")
+        true, pred = true[order].contiguous(), pred[order].contiguous()
+    true, pred = true.to(dev), pred.to(dev)
     img = S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(true).unsqueeze(1).contiguous()
     row_off, col_off = nearest_offsets(256, 256, R, dev)
     loss = torch.empty((), dtype=torch.float64, device=dev)
