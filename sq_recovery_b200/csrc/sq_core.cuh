@@ -79,7 +79,9 @@ struct Grid {
     int n;          // points per axis
     double step;    // spacing
     double z0;      // coordinate of index 0 (1e-4 with the zero fix-up, else 0)
+    float inv_n;    // 1 / n
 };
+SQ_HD Grid make_grid(int n, double step, double z0) { Grid g; g.n = n; g.step = step; g.z0 = z0; g.inv_n = 1.0f / (float)n; return g; }
 SQ_HD double grid_coord(const Grid& g, int i) { return i == 0 ? g.z0 : (double)i * g.step; }
 
 // ---------------------------------------------------------------- per-sample constants
@@ -141,10 +143,11 @@ SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, Sample& S) {
 }
 
 // s at plane "index" 0 for the column through grid point (ia, ib): base_i = Ms_i . ((gx,gy,0) - t), as hi/lo floats
-SQ_HD void column_base(const Sample& S, const Grid& g, int ia, int ib, float* bh, float* bl) {
+SQ_HD void column_base(const Sample& S, const Grid& g, int ia, int ib, float* bh, float* bl, float* dxy = nullptr) {
     const double dx = grid_coord(g, ia) - S.t[0], dy = grid_coord(g, ib) - S.t[1], dz = -S.t[2];
     for (int i = 0; i < 3; ++i)
         split2(S.Ms[3 * i] * dx + S.Ms[3 * i + 1] * dy + S.Ms[3 * i + 2] * dz, bh[i], bl[i]);
+    if (dxy) { dxy[0] = (float)dx; dxy[1] = (float)dy; }      // column position relative to t (for the M gradient)
 }
 
 // ---------------------------------------------------------------- forward at one point
@@ -359,62 +362,97 @@ struct ColGrad {       // two-moment accumulators of one column
 // the column's gradient counts, and those columns carry k-amplified gradient.  So the first-order sum
 // (tau/n) sum_c cs_c is carried along and used when the depth is tiny (relative error < 0.4% there).
 // [c_lo, c_hi]: the (warp-uniform) z range to walk, from column_range() / warp_range().
+// running state of one column walk
+struct ColState {
+    float csl, cssum, tsum, psh, seen, T;
+};
+
+// geometry + forward chain + occupancy of one plane (independent of the scan state: two planes can be in flight)
+struct Plane { Fwd f; float x, eo, o, cf; };
+
+SQ_HD void plane_forward(const Sample& S, const ImplicitParams& P, const float* bh, const float* bl, float cf, Plane& p) {
+    p.cf = cf;
+    const float sx = fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]);
+    const float sy = fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]);
+    const float sz = fmaf(cf, S.dh[2], bh[2]) + fmaf(cf, S.dl[2], bl[2]);
+    point_forward<true>(S, sx, sy, sz, p.f);
+    p.o = occupancy(p.f.F, P.kl, p.x, p.eo);
+}
+
+// scan step of one plane: transmittance, suffix-sum bookkeeping and (for gradient-carrying warps) the backward
+template <bool BWD>
+SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, ColGrad& cg) {
+    st.csl = fmaf(p.o, -P.tl, st.csl);
+    st.cssum += st.csl;
+    st.T = ex2(st.csl);
+    if (BWD) {
+        const bool active = (fabsf(p.x) < kActive) && (st.csl > -kDeep);
+        if (SQ_ANY(active)) {
+            // do/dF = -k o (1-o) = -k eo o^2 ; the -k is applied in finalize
+            const float W = active ? p.eo * p.o * p.o : 0.0f;
+            Fwd fa = p.f;
+            if (!active) fwd_neutral(fa);       // keep inactive lanes finite
+            Bwd b;
+            point_backward(fa, W, b);
+            st.seen = active ? 1.0f : st.seen;
+            const float pp = st.psh;       // T in front of this point (since the first active one)
+            for (int i = 0; i < 3; ++i) {
+                cg.gs0[i] += b.gs[i];            cg.gs1[i] = fmaf(pp, b.gs[i], cg.gs1[i]);
+                const float gz = b.gs[i] * p.cf;
+                cg.gz0[i] += gz;                 cg.gz1[i] = fmaf(pp, gz, cg.gz1[i]);
+                cg.wa0[i] += b.wa[i];            cg.wa1[i] = fmaf(pp, b.wa[i], cg.wa1[i]);
+            }
+            for (int i = 0; i < 2; ++i) { cg.ge0[i] += b.ge[i]; cg.ge1[i] = fmaf(pp, b.ge[i], cg.ge1[i]); }
+        }
+        st.psh = fmaf(st.seen, st.T, st.psh);
+    }
+    st.tsum += st.T;
+}
+
+// ILP: number of z planes whose (independent) forward chains are in flight per thread.  A column walk is a serial
+// chain of ~8 dependent MUFU ops per plane; two planes in flight halve the latency of the longest work item, which
+// is what bounds the kernel at small batch.
+#ifndef SQ_IMP_ILP
+#define SQ_IMP_ILP 2
+#endif
+
 template <bool BWD>
 SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams& P,
                             const float* bh, const float* bl, int c_lo, int c_hi, float* colgrad11) {
     // planes in front of the range: o = 0, cs = 0, T = 1 each
-    float csl = 0.f;                                  // -tau log2(e) cs
-    float T = 1.0f;                                   // 2^csl
-    float tsum = (float)(g.n - 1 - c_hi);
-    float cssum = 0.f;                                // sum_c csl_c
-    float psh = 0.f, seen = 0.f;
+    ColState st;
+    st.csl = 0.f;                                     // -tau log2(e) cs
+    st.T = 1.0f;                                      // 2^csl
+    st.tsum = (float)(g.n - 1 - c_hi);
+    st.cssum = 0.f;                                   // sum_c csl_c
+    st.psh = 0.f; st.seen = 0.f;
     ColGrad cg;
     if (BWD) {
         for (int i = 0; i < 3; ++i) cg.gs0[i] = cg.gs1[i] = cg.gz0[i] = cg.gz1[i] = cg.wa0[i] = cg.wa1[i] = 0.f;
         cg.ge0[0] = cg.ge0[1] = cg.ge1[0] = cg.ge1[1] = 0.f;
     }
-    float cfi = (float)c_hi;
-    for (int c = c_hi; c >= c_lo; --c, cfi -= 1.0f) {
-        const float cf = (c == 0) ? S.cf0 : cfi;       // plane "index": exact small integers, z0/step for plane 0
-        const float sx = fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]);
-        const float sy = fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]);
-        const float sz = fmaf(cf, S.dh[2], bh[2]) + fmaf(cf, S.dl[2], bl[2]);
-        Fwd f;
-        point_forward<true>(S, sx, sy, sz, f);
-        float x, eo;
-        const float o = occupancy(f.F, P.kl, x, eo);
-        csl = fmaf(o, -P.tl, csl);
-        cssum += csl;
-        T = ex2(csl);
-        if (BWD) {
-            const bool active = (fabsf(x) < kActive) && (csl > -kDeep);
-            if (SQ_ANY(active)) {
-                // do/dF = -k o (1-o) = -k eo o^2 ; the -k is applied in finalize
-                const float W = active ? eo * o * o : 0.0f;
-                Fwd fa = f;
-                if (!active) fwd_neutral(fa);       // keep inactive lanes finite
-                Bwd b;
-                point_backward(fa, W, b);
-                seen = active ? 1.0f : seen;
-                const float pp = psh;       // T in front of this point (since the first active one)
-                for (int i = 0; i < 3; ++i) {
-                    cg.gs0[i] += b.gs[i];            cg.gs1[i] = fmaf(pp, b.gs[i], cg.gs1[i]);
-                    const float gz = b.gs[i] * cf;
-                    cg.gz0[i] += gz;                 cg.gz1[i] = fmaf(pp, gz, cg.gz1[i]);
-                    cg.wa0[i] += b.wa[i];            cg.wa1[i] = fmaf(pp, b.wa[i], cg.wa1[i]);
-                }
-                for (int i = 0; i < 2; ++i) { cg.ge0[i] += b.ge[i]; cg.ge1[i] = fmaf(pp, b.ge[i], cg.ge1[i]); }
-            }
-            psh = fmaf(seen, T, psh);
-        }
-        tsum += T;
+    int c = c_hi;
+    float cfi = (float)c_hi;                          // plane "index": exact small integers, z0/step for plane 0
+#if SQ_IMP_ILP >= 2
+    for (; c - 1 >= c_lo; c -= 2, cfi -= 2.0f) {
+        Plane p0, p1;
+        plane_forward(S, P, bh, bl, cfi, p0);
+        plane_forward(S, P, bh, bl, (c - 1 == 0) ? S.cf0 : cfi - 1.0f, p1);
+        plane_scan<BWD>(P, p0, st, cg);
+        plane_scan<BWD>(P, p1, st, cg);
+    }
+#endif
+    for (; c >= c_lo; --c, cfi -= 1.0f) {
+        Plane p0;
+        plane_forward(S, P, bh, bl, (c == 0) ? S.cf0 : cfi, p0);
+        plane_scan<BWD>(P, p0, st, cg);
     }
     // planes behind the range: o = 0, cs and T stay what they are
     const float nb = (float)c_lo;
-    tsum = fmaf(nb, T, tsum);
-    cssum = fmaf(nb, csl, cssum);
+    st.tsum = fmaf(nb, st.T, st.tsum);
+    st.cssum = fmaf(nb, st.csl, st.cssum);
     if (BWD) {
-        const float U = fmaf(nb * seen, T, psh);
+        const float U = fmaf(nb * st.seen, st.T, st.psh);
         for (int i = 0; i < 3; ++i) {
             colgrad11[i]     = fmaf(U, cg.gs0[i], -cg.gs1[i]);
             colgrad11[3 + i] = fmaf(U, cg.gz0[i], -cg.gz1[i]);
@@ -423,9 +461,8 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
         colgrad11[9]  = fmaf(U, cg.ge0[0], -cg.ge1[0]);
         colgrad11[10] = fmaf(U, cg.ge0[1], -cg.ge1[1]);
     }
-    const float inv_n = 1.0f / (float)g.n;
-    const float depth = fmaf(-tsum, inv_n, 1.0f);
-    return depth < 1e-4f ? -(float)kLn2 * cssum * inv_n : depth;     // tau sum cs = -ln2 sum csl
+    const float depth = fmaf(-st.tsum, g.inv_n, 1.0f);
+    return depth < 1e-4f ? -(float)kLn2 * st.cssum * g.inv_n : depth;     // tau sum cs = -ln2 sum csl
 }
 
 // fold one finished column (weight w = sign(depth - target), coordinates relative to t) into the thread totals

@@ -29,10 +29,10 @@ namespace {
 #define SQ_IMPB_THREADS 128              // implicit fwd+bwd
 #endif
 #ifndef SQ_IMPB_MINB
-#define SQ_IMPB_MINB 5
+#define SQ_IMPB_MINB 4
 #endif
 #ifndef SQ_IMPB_CPT
-#define SQ_IMPB_CPT 1
+#define SQ_IMPB_CPT 2
 #endif
 #ifndef SQ_IMPF_THREADS
 #define SQ_IMPF_THREADS 256              // implicit fwd only (validation, depth rendering)
@@ -72,6 +72,11 @@ constexpr int kWarps = kThreads / 32;
 // synchronise with each other (no __syncthreads in the column kernels), each writes its own partial row.
 struct Layout {
     int n, patched, slots, cpt, rows_per_sample;
+    int rows_shift;      // log2(rows_per_sample) when it is a power of two, else -1
+    __host__ __device__ __forceinline__ void split(int item, int& b, int& chunk) const {
+        if (rows_shift >= 0) { b = item >> rows_shift; chunk = item & (rows_per_sample - 1); }
+        else { b = item / rows_per_sample; chunk = item - b * rows_per_sample; }
+    }
 };
 
 __host__ __device__ inline Layout make_layout(int n, int max_cpt) {
@@ -83,6 +88,8 @@ __host__ __device__ inline Layout make_layout(int n, int max_cpt) {
     if (L.cpt > max_cpt) L.cpt = max_cpt;
     const int per_item = L.cpt * 32;
     L.rows_per_sample = (L.slots + per_item - 1) / per_item;
+    L.rows_shift = -1;
+    for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == L.rows_per_sample) L.rows_shift = sh;
     return L;
 }
 
@@ -194,8 +201,12 @@ __device__ __forceinline__ void acc_to_array(const Acc& a, float* v) {
 }
 
 // per-thread Acc -> one row of kAccN floats per WARP (lane i ends up holding and storing sum i)
-__device__ __forceinline__ void warp_reduce_store(const Acc& a, float* row) {
+__device__ __forceinline__ void warp_reduce_store(const Acc& a, float* row, bool nonzero) {
     const int lane = threadIdx.x & 31;
+    if (!__any_sync(0xffffffffu, nonzero)) {          // e.g. image-border patches: no object, no loss, no gradient
+        if (lane < kAccN) row[lane] = 0.f;
+        return;
+    }
     float v[kAccN];
     acc_to_array(a, v);
     float mine = 0.f;
@@ -259,9 +270,14 @@ struct SampleFetch {
     }
 };
 
+// Work distribution: the first item of a warp is its global warp index (no atomic burst when 3000 warps start at
+// once), later items come from a cursor that counts on from there.
+__device__ __forceinline__ int first_item() {
+    return (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+}
 __device__ __forceinline__ int next_item(unsigned int* cursor, int lane) {
     int item = 0;
-    if (lane == 0) item = (int)atomicAdd(cursor, 1u);
+    if (lane == 0) item = (int)(atomicAdd(cursor, 1u) + gridDim.x * (blockDim.x >> 5));
     return __shfl_sync(0xffffffffu, item, 0);
 }
 
@@ -277,14 +293,15 @@ implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitPa
     // Persistent warps pull work items from a global cursor: item cost varies a lot with the culled z range, and a
     // static assignment left the SMs idle at the tail.  The next item and its Sample are fetched while the current
     // item is processed.  No block-level barrier anywhere.
-    int item = next_item(cursor, lane);
+    int item = first_item();
     SampleFetch pre;
-    if (item < total_items) pre.fetch(samples + item / L.rows_per_sample, lane);
+    if (item < total_items) pre.fetch(samples + (L.rows_shift >= 0 ? item >> L.rows_shift : item / L.rows_per_sample), lane);
     while (item < total_items) {
-        const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
+        int b, chunk;
+        L.split(item, b, chunk);
         pre.commit(&S, lane);
         const int upcoming = next_item(cursor, lane);
-        if (upcoming < total_items) pre.fetch(samples + upcoming / L.rows_per_sample, lane);
+        if (upcoming < total_items) pre.fetch(samples + (L.rows_shift >= 0 ? upcoming >> L.rows_shift : upcoming / L.rows_per_sample), lane);
 
         Acc acc;
         acc_zero(acc);
@@ -296,8 +313,8 @@ implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitPa
             const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
             float tv = 0.f;                                // issued now, needed after the z walk
             if (valid && target) tv = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
-            float bh[3], bl[3], cg[11];
-            column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl);
+            float bh[3], bl[3], cg[11], dxy[2];
+            column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
             int c_lo, c_hi;
             column_range(S, g, P.bound, bh, c_lo, c_hi);
             if (!valid) { c_lo = 0; c_hi = -1; }           // masked lanes do not widen the warp's range
@@ -310,12 +327,12 @@ implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitPa
                     acc.loss += fabsf(diff);
                     if (BWD) {
                         const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                        implicit_fold(acc, cg, w, (float)(grid_coord(g, ia) - S.t[0]), (float)(grid_coord(g, ib) - S.t[1]));
+                        implicit_fold(acc, cg, w, dxy[0], dxy[1]);
                     }
                 }
             }
         }
-        if (target) warp_reduce_store(acc, partials + (size_t)item * kAccN);
+        if (target) warp_reduce_store(acc, partials + (size_t)item * kAccN, acc.loss != 0.f);   // zero loss => zero gradient
         item = upcoming;
     }
 }
@@ -329,17 +346,19 @@ explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& St = Tsh[warp];
     Sample& Sp = Psh[warp];
-    int item = next_item(cursor, lane);
+    int item = first_item();
     SampleFetch pre_t, pre_p;
-    if (item < total_items) { pre_t.fetch(tru + item / L.rows_per_sample, lane); pre_p.fetch(pred + item / L.rows_per_sample, lane); }
+    if (item < total_items) { const int b0 = L.rows_shift >= 0 ? item >> L.rows_shift : item / L.rows_per_sample; pre_t.fetch(tru + b0, lane); pre_p.fetch(pred + b0, lane); }
     while (item < total_items) {
-        const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
+        int b, chunk;
+        L.split(item, b, chunk);
         pre_t.commit(&St, lane);
         pre_p.commit(&Sp, lane);
         const int upcoming = next_item(cursor, lane);
         if (upcoming < total_items) {
-            pre_t.fetch(tru + upcoming / L.rows_per_sample, lane);
-            pre_p.fetch(pred + upcoming / L.rows_per_sample, lane);
+            const int b1 = L.rows_shift >= 0 ? upcoming >> L.rows_shift : upcoming / L.rows_per_sample;
+            pre_t.fetch(tru + b1, lane);
+            pre_p.fetch(pred + b1, lane);
         }
         Acc acc;
         acc_zero(acc);
@@ -349,8 +368,9 @@ explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred,
             const bool valid = it.valid(L);
             const int ia = valid ? it.ia : 0, ib = valid ? it.ib : 0;
             float bht[3], blt[3], bhp[3], blp[3];
+            float dxy[2];
             column_base(St, g, ia, ib, bht, blt);
-            column_base(Sp, g, ia, ib, bhp, blp);
+            column_base(Sp, g, ia, ib, bhp, blp, dxy);
             Range rt, rp;
             column_range(St, g, bound, bht, rt.lo, rt.hi);
             column_range(Sp, g, bound, bhp, rp.lo, rp.hi);
@@ -359,8 +379,7 @@ explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred,
             warp_range(g.n, rp.lo, rp.hi);
             Acc col;
             acc_zero(col);
-            const float dx = (float)(grid_coord(g, ia) - Sp.t[0]), dy = (float)(grid_coord(g, ib) - Sp.t[1]);
-            const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, rt, rp, dx, dy, col);
+            const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, rt, rp, dxy[0], dxy[1], col);
             if (valid) {
                 acc.loss += sq;
                 if (BWD) {
@@ -372,7 +391,7 @@ explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred,
                 }
             }
         }
-        warp_reduce_store(acc, partials + (size_t)item * kAccN);
+        warp_reduce_store(acc, partials + (size_t)item * kAccN, acc.loss != 0.f);
         item = upcoming;
     }
 }
@@ -385,17 +404,19 @@ iou_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& St = Tsh[warp];
     Sample& Sp = Psh[warp];
-    int item = next_item(cursor, lane);
+    int item = first_item();
     SampleFetch pre_t, pre_p;
-    if (item < total_items) { pre_t.fetch(tru + item / L.rows_per_sample, lane); pre_p.fetch(pred + item / L.rows_per_sample, lane); }
+    if (item < total_items) { const int b0 = L.rows_shift >= 0 ? item >> L.rows_shift : item / L.rows_per_sample; pre_t.fetch(tru + b0, lane); pre_p.fetch(pred + b0, lane); }
     while (item < total_items) {
-        const int b = item / L.rows_per_sample, chunk = item - b * L.rows_per_sample;
+        int b, chunk;
+        L.split(item, b, chunk);
         pre_t.commit(&St, lane);
         pre_p.commit(&Sp, lane);
         const int upcoming = next_item(cursor, lane);
         if (upcoming < total_items) {
-            pre_t.fetch(tru + upcoming / L.rows_per_sample, lane);
-            pre_p.fetch(pred + upcoming / L.rows_per_sample, lane);
+            const int b1 = L.rows_shift >= 0 ? upcoming >> L.rows_shift : upcoming / L.rows_per_sample;
+            pre_t.fetch(tru + b1, lane);
+            pre_p.fetch(pred + b1, lane);
         }
         unsigned inter = 0, uni = 0;
         ColIter it;
@@ -469,11 +490,25 @@ finalize_kernel(const Sample* __restrict__ samples, Grid g, int batch, int items
                 double* __restrict__ per_sample_user, double* __restrict__ loss_out, unsigned int* ticket) {
     const int b = blockIdx.x, lane = threadIdx.x;
     __shared__ double acc[kAccN];
-    if (lane < kAccN) {
-        double s = 0.0;
-        const float* p = partials + (size_t)b * items_per_sample * kAccN + lane;
-        for (int j = 0; j < items_per_sample; ++j) s += (double)p[(size_t)j * kAccN];
-        acc[lane] = s;
+    __shared__ double part[32][kAccN + 1];
+    {   // lane l sums rows l, l+32, ... (independent loads in flight), then a fixed-order sum over the 32 lanes
+        double s[kAccN];
+#pragma unroll
+        for (int i = 0; i < kAccN; ++i) s[i] = 0.0;
+        const float* base = partials + (size_t)b * items_per_sample * kAccN;
+        for (int j = lane; j < items_per_sample; j += 32) {
+            const float* p = base + (size_t)j * kAccN;
+#pragma unroll
+            for (int i = 0; i < kAccN; ++i) s[i] += (double)p[i];
+        }
+#pragma unroll
+        for (int i = 0; i < kAccN; ++i) part[lane][i] = s[i];
+        __syncwarp();
+        if (lane < kAccN) {
+            double t = 0.0;
+            for (int l = 0; l < 32; ++l) t += part[l][lane];
+            acc[lane] = t;
+        }
     }
     __syncwarp();
     if (lane == 0) {
@@ -610,7 +645,7 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
     if (target && (!row_off || !col_off)) return (int)cudaErrorInvalidValue;
     if (grad_pred && !target) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const Grid g{n, step, z0};
+    const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, grad_pred ? SQ_IMPB_CPT : SQ_IMPF_CPT);
     const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, cull_bound(sharpness * kLog2e)};
     rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
@@ -647,7 +682,7 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     int rc = check_scratch(batch, n, scratch, scratch_bytes, &s);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const Grid g{n, step, z0};
+    const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, SQ_EXP_CPT);
     rc = launch_prep(true_params, params_dtype, batch, true, g, s.tru, nullptr, nullptr, st);
     if (rc) return rc;
@@ -679,7 +714,7 @@ int sq_iou_counts(const void* true_params, const void* pred, int params_dtype, i
     if (rc) return rc;
     if (!inter || !uni) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const Grid g{n, step, z0};
+    const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, SQ_IOU_CPT);
     rc = launch_prep(true_params, params_dtype, batch, false, g, s.tru, nullptr, nullptr, st);
     if (rc) return rc;
@@ -705,7 +740,7 @@ int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_siz
     if (rc) return rc;
     if (!target || !row_off || !col_off) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const Grid g{2, 1.0, 0.0};     // the point list carries its own coordinates; the grid is unused
+    const Grid g = make_grid(2, 1.0, 0.0);     // the point list carries its own coordinates; the grid is unused
     rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
     if (rc) return rc;
     const int R = render_size;
@@ -726,7 +761,7 @@ int sq_field(const void* params, int params_dtype, int batch, int n, double step
     if (rc) return rc;
     if (!out || (mode != 0 && mode != 1)) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const Grid g{n, step, z0};
+    const Grid g = make_grid(n, step, z0);
     rc = launch_prep(params, params_dtype, batch, mode == 1, g, s.pred, nullptr, nullptr, st);
     if (rc) return rc;
     const size_t total = (size_t)batch * n * n * n;

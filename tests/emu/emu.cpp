@@ -22,7 +22,7 @@ extern "C" {
 // target: [B, n, n] in image orientation (row, col); depth_out optional [B, n, n] image orientation
 int emu_implicit(const double* pred, int B, int n, double step, double z0, const float* target, float tau, float k,
                  double* loss_out, double* grad /*[B,12] or null*/, float* depth_out /*or null*/) {
-    Grid g{n, step, z0};
+    Grid g = make_grid(n, step, z0);
     ImplicitParams P{k * kLog2e, tau * kLog2e, cull_bound(k * kLog2e)};
     double total = 0.0;
     for (int b = 0; b < B; ++b) {
@@ -61,7 +61,7 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
 
 int emu_explicit(const double* tru, const double* pred, int B, int n, double step, double z0, float k, float mult,
                  double* loss_out, double* grad) {
-    Grid g{n, step, z0};
+    Grid g = make_grid(n, step, z0);
     double total = 0.0;
     for (int b = 0; b < B; ++b) {
         double pt[12], pp[12];
@@ -91,7 +91,7 @@ int emu_explicit(const double* tru, const double* pred, int B, int n, double ste
 }
 
 int emu_iou(const double* tru, const double* pred, int B, int n, double step, long long* inter, long long* uni) {
-    Grid g{n, step, 0.0};
+    Grid g = make_grid(n, step, 0.0);
     for (int b = 0; b < B; ++b) {
         double pt[12], pp[12];
         for (int i = 0; i < 12; ++i) { pt[i] = tru[12 * b + i]; pp[i] = pred[12 * b + i]; }
@@ -115,7 +115,7 @@ int emu_iou(const double* tru, const double* pred, int B, int n, double step, lo
 
 // points: [sum m, 3] (x, y, z) with offsets[B+1]
 int emu_lsq(const double* pred, int B, const float* points, const int* offsets, double* loss_out, double* grad) {
-    Grid g{2, 1.0, 0.0};
+    Grid g = make_grid(2, 1.0, 0.0);
     double total = 0.0;
     for (int b = 0; b < B; ++b) {
         double p[12]; for (int i = 0; i < 12; ++i) p[i] = pred[12 * b + i];
