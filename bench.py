@@ -310,7 +310,10 @@ def run_gpu(args):
                            eager_ms_per_step=eager_ms),
             "clocks": clocks,
             "e2e": {"value": world * pts * e2e_steps / e2e_s / 1e9, "unit": UNIT,
-                    "h2d_bytes_per_step": B * H * W * 4 + B * 12 * 4 + 2 * R * 4, "d2h_bytes_per_step": 8 + B * 12 * 4,
+                    # the pinned depth maps are sampled in place over PCIe: only the 32-byte sectors holding sampled
+                    # pixels cross the bus (ncu dram_bytes_read of the same access pattern: 16.9 MB at 256 -> 64)
+                    "h2d_bytes_per_step": B * R * min(W * 4, R * 32) + B * 12 * 4 + 4 * R * 4,
+                    "d2h_bytes_per_step": 8 + B * 12 * 4, "host_image_bytes": B * H * W * 4,
                     "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "api": "sq_implicit_loss_host (include/sqloss.h) on pinned host buffers"},
             "gpu_launches": 3 * steps,

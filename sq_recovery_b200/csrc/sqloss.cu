@@ -566,6 +566,22 @@ field_kernel(const Sample* __restrict__ samples, Grid g, int batch, int mode, fl
     out[idx] = v;
 }
 
+// ------------------------------------------------------------------------------------------------ host-image gather
+// Nearest-neighbour sampling of depth images that live in PINNED HOST memory, read directly over PCIe (zero copy):
+// only the sampled 32-byte sectors cross the bus (1/4 of the bytes at 256 -> 64), instead of the whole images.
+__global__ void __launch_bounds__(256)
+gather_targets_kernel(const float* __restrict__ host_images, long long stride_b, const int* __restrict__ row_off,
+                      const int* __restrict__ col_off, int R, int batch, float* __restrict__ out) {
+    const size_t total = (size_t)batch * R * R;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i % R);
+        const size_t t = i / R;
+        const int row = (int)(t % R);
+        const size_t b = t / R;
+        out[i] = host_images[b * (size_t)stride_b + row_off[row] + col_off[col]];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host helpers
 #define SQ_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
@@ -830,9 +846,16 @@ int sq_implicit_loss_host(sq_ctx* c, const float* pred_host, int batch, int rend
     if (!c || !pred_host || !images_host || batch <= 0 || render_size <= 0) return (int)cudaErrorInvalidValue;
     SQ_TRY(cudaSetDevice(c->device));
     const int R = render_size;
+    // images in pinned (or registered) host memory are sampled in place over PCIe; pageable memory is copied whole
+    cudaPointerAttributes attr;
+    const float* mapped = nullptr;
+    if (cudaPointerGetAttributes(&attr, images_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        mapped = static_cast<const float*>(attr.devicePointer);
+    else
+        cudaGetLastError();
     const size_t b_pred = align_up(sizeof(float) * 12 * (size_t)batch, 256);
-    const size_t b_img = align_up(sizeof(float) * (size_t)batch * height * width, 256);
-    const size_t b_off = align_up(sizeof(int) * 2 * (size_t)R, 256);
+    const size_t b_img = align_up(sizeof(float) * (size_t)batch * (mapped ? (size_t)R * R : (size_t)height * width), 256);
+    const size_t b_off = align_up(sizeof(int) * 4 * (size_t)R, 256);
     const size_t b_out = align_up(sizeof(double) + sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_scr = sq_scratch_bytes(batch, R);
     int rc = ctx_reserve(c, b_pred + b_img + b_off + b_out + b_scr, b_off + b_out);
@@ -849,10 +872,24 @@ int sq_implicit_loss_host(sq_ctx* c, const float* pred_host, int batch, int rend
     nearest_offsets(height, R, width, h_off);
     nearest_offsets(width, R, 1, h_off + R);
     SQ_TRY(cudaMemcpyAsync(d_pred, pred_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
-    SQ_TRY(cudaMemcpyAsync(d_img, images_host, sizeof(float) * (size_t)batch * height * width, cudaMemcpyHostToDevice, c->stream));
     SQ_TRY(cudaMemcpyAsync(d_off, h_off, sizeof(int) * 2 * (size_t)R, cudaMemcpyHostToDevice, c->stream));
-    rc = sq_implicit_loss(d_pred, SQ_F32, batch, R, 1.0 / (double)(R - 1), 1e-4, d_img, (long long)height * width,
-                          d_off, d_off + R, tau, sharpness, d_loss, nullptr, grad_host ? d_grad : nullptr, nullptr,
+    long long stride_b = (long long)height * width;
+    const int* d_row = d_off;
+    const int* d_col = d_off + R;
+    if (mapped) {
+        // gather into a compact [batch, R, R] image, then address it with identity tables kept behind the real ones
+        int* h_id = h_off + 2 * R;
+        for (int i = 0; i < R; ++i) { h_id[i] = i * R; h_id[R + i] = i; }
+        int* d_id = d_off + 2 * R;
+        SQ_TRY(cudaMemcpyAsync(d_id, h_id, sizeof(int) * 2 * (size_t)R, cudaMemcpyHostToDevice, c->stream));
+        gather_targets_kernel<<<1184, 256, 0, c->stream>>>(mapped, stride_b, d_row, d_col, R, batch, d_img);
+        SQ_TRY(cudaGetLastError());
+        stride_b = (long long)R * R; d_row = d_id; d_col = d_id + R;
+    } else {
+        SQ_TRY(cudaMemcpyAsync(d_img, images_host, sizeof(float) * (size_t)batch * height * width, cudaMemcpyHostToDevice, c->stream));
+    }
+    rc = sq_implicit_loss(d_pred, SQ_F32, batch, R, 1.0 / (double)(R - 1), 1e-4, d_img, stride_b,
+                          d_row, d_col, tau, sharpness, d_loss, nullptr, grad_host ? d_grad : nullptr, nullptr,
                           d_scr, b_scr, c->stream);
     if (rc) return rc;
     const size_t out_bytes = sizeof(double) + (grad_host ? sizeof(float) * 12 * (size_t)batch : 0);
