@@ -308,6 +308,12 @@ SQ_HD void finalize_sample(const Sample& S, const Grid& g, const double* acc, do
 // the z range where it can be inside the box |s_i| < bound; the rest is accounted for in closed form.
 SQ_HD float cull_bound(float kl) { return sqrtf((1.0f + 128.0f / kl) * 1.002f); }
 
+// ExplicitLoss has sharpness 5, for which the exact bound is |s| >= 4.3 and culls nothing.  Its terms are differences
+// (o_t - o_p)^2 of numbers in [0,1] accumulated in fp32, so an occupancy below 2^-24 is below the resolution of the
+// difference whenever the other one matters, and contributes < 2^-48 when both are that small.  Outside
+// |s_i| < bound24 the occupancy is < 2^-24 and is taken as 0 (DESIGN.md "culling").
+SQ_HD float cull_bound_bits(float kl, float bits) { return sqrtf((1.0f + bits / kl) * 1.002f); }
+
 // inclusive z-index range [c_lo, c_hi] outside which max|s_i| >= bound; empty when c_hi < c_lo
 SQ_HD void column_range(const Sample& S, const Grid& g, float bound, const float* bh, int& c_lo, int& c_hi) {
     float lo = -1e30f, hi = 1e30f;

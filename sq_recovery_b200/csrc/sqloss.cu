@@ -706,7 +706,7 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int blocks = persistent_blocks(items, SQ_EXP_THREADS / 32, SQ_EXP_MINB);
-    const float kl = sharpness * kLog2e, bound = cull_bound(kl);
+    const float kl = sharpness * kLog2e, bound = cull_bound_bits(kl, 24.0f);
     {
         ColumnKernelTimer timer(st);
         if (grad_pred) explicit_kernel<true><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.ticket + 1, s.partials);

@@ -74,7 +74,7 @@ int emu_explicit(const double* tru, const double* pred, int B, int n, double ste
             column_base(Sp, g, ia, ib, bhp, blp);
             Acc a; acc_zero(a);
             const float dx = (float)(grid_coord(g, ia) - Sp.t[0]), dy = (float)(grid_coord(g, ib) - Sp.t[1]);
-            const float bound = cull_bound(k * kLog2e);
+            const float bound = cull_bound_bits(k * kLog2e, 24.0f);
             Range rt, rp;
             column_range(St, g, bound, bht, rt.lo, rt.hi); warp_range(n, rt.lo, rt.hi);
             column_range(Sp, g, bound, bhp, rp.lo, rp.hi); warp_range(n, rp.lo, rp.hi);

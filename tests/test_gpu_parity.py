@@ -207,6 +207,38 @@ def test_against_oracle(seed, B, R, dev, S):
         assert torch.equal(i, i2.cpu()) and torch.equal(u, u2.cpu())
 
 
+@pytest.mark.parametrize("B,R", [(5, 12), (3, 20), (2, 33)])
+def test_odd_sizes_against_oracle(B, R, dev, S):
+    """Render sizes that are not multiples of 8 (x-fastest column layout, masked lanes, ragged last warp) and batch
+    sizes that do not fill a block; every kernel once.  (compute-sanitizer is closed on this GPU pool, so out-of-range
+    accesses are hunted with these ragged cases + comparison with the oracle.)"""
+    true, pred = O.random_params(B, 61), O.random_params(B, 62)
+    with torch.no_grad():
+        img = O.ImplicitLoss(3 * R + 1, "cpu", 1.5, 260).depth_projection(true).float().unsqueeze(1)   # ragged resize ratio
+    p = pred.clone().requires_grad_(True)
+    oc = O.ImplicitLoss(R, "cpu", 1.0, 100)
+    ref = oc(img, p); ref.backward()
+    l, gr = run(S.ImplicitLoss(R, dev, 1.0, 100), img, pred, dev)
+    check(l, gr, ref.item(), p.grad.double().numpy(), what=f"implicit odd B={B} R={R}", keep=unambiguous(oc, img, pred))
+    p = pred.clone().requires_grad_(True)
+    ref = O.ExplicitLoss(R, "cpu")(true, p); ref.backward()
+    l, gr = run(S.ExplicitLoss(R, dev), true, pred, dev)
+    check(l, gr, ref.item(), p.grad.double().numpy(), what=f"explicit odd B={B} R={R}")
+    i, u = O.IoUAccuracy(R, "cpu").counts(true, pred)
+    i2, u2 = S.IoUAccuracy(R, dev).counts(true.to(dev), pred.to(dev))
+    assert torch.equal(i, i2.cpu()) and torch.equal(u, u2.cpu())
+    p = pred.clone().requires_grad_(True)
+    ref = O.LeastSquares(R, "cpu")(img, p); ref.backward()
+    l, gr = run(S.LeastSquares(R, dev), img, pred, dev)
+    check(l, gr, ref.item(), p.grad.double().numpy(), loss_rtol=1e-4, rtol=2e-3, atol=1e-4, what=f"lsq odd B={B} R={R}")
+    occ = S.ExplicitLoss(R, dev).occupancy(pred.to(dev)).cpu()
+    np.testing.assert_allclose(occ.numpy(), O.ExplicitLoss(R, "cpu").occupancy(pred).numpy(), atol=2e-5)
+    f = S.IoUAccuracy(R, dev).ins_outs(pred.to(dev)).cpu().double()
+    fo = O.IoUAccuracy(R, "cpu").ins_outs(pred)
+    ok = torch.isfinite(fo) & (fo < 1e6)
+    np.testing.assert_allclose(f[ok].numpy(), fo[ok].numpy(), rtol=2e-5)
+
+
 # ------------------------------------------------------------------ full BASELINE sizes through size-independent properties
 def test_full_size_properties(dev, S):
     B, R = 256, 64                                                      # BASELINE config 2
