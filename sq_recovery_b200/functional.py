@@ -108,7 +108,7 @@ class ImplicitLossFn(torch.autograd.Function):
     def backward(ctx, go):
         g = None
         if ctx.grad is not None:
-            g = (ctx.grad * go.to(ctx.grad.dtype)).to(ctx.pred_dtype)
+            g = (ctx.grad * go).to(ctx.pred_dtype)      # 0-dim fp64 `go` does not promote the result: one kernel
         return None, g, None, None, None, None, None
 
 
@@ -153,9 +153,9 @@ class ExplicitLossFn(torch.autograd.Function):
     def backward(ctx, go):
         gt = gp = None
         if ctx.grad_true is not None:
-            gt = (ctx.grad_true * go.to(ctx.grad_true.dtype)).to(ctx.dtypes[0])
+            gt = (ctx.grad_true * go).to(ctx.dtypes[0])
         if ctx.grad_pred is not None:
-            gp = (ctx.grad_pred * go.to(ctx.grad_pred.dtype)).to(ctx.dtypes[1])
+            gp = (ctx.grad_pred * go).to(ctx.dtypes[1])
         return gt, gp, None, None, None, None, None
 
 
@@ -188,7 +188,7 @@ class LeastSquaresFn(torch.autograd.Function):
     def backward(ctx, go):
         g = None
         if ctx.grad is not None:
-            g = (ctx.grad * go.to(ctx.grad.dtype)).to(ctx.pred_dtype)
+            g = (ctx.grad * go).to(ctx.pred_dtype)
         return None, g, None
 
 
