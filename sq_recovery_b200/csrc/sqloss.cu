@@ -138,6 +138,7 @@ struct Scratch {
     double* per_sample;    // [batch]
     unsigned long long* counts;   // [batch][2] (IoU)
     unsigned int* ticket;  // [0] finalize ticket, [1] work-stealing cursor of the column kernel
+    int* order;            // [batch] sample processed at position i (longest columns first)
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -156,6 +157,7 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     const size_t o_ps = take(sizeof(double) * (size_t)batch);
     const size_t o_cnt = take(sizeof(unsigned long long) * 2 * (size_t)batch);
     const size_t o_tick = take(sizeof(unsigned int) * 4);
+    const size_t o_order = take(sizeof(int) * (size_t)batch);
     if (s) {
         s->pred = reinterpret_cast<Sample*>(base + o_pred);
         s->tru = reinterpret_cast<Sample*>(base + o_true);
@@ -163,15 +165,28 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
         s->per_sample = reinterpret_cast<double*>(base + o_ps);
         s->counts = reinterpret_cast<unsigned long long*>(base + o_cnt);
         s->ticket = reinterpret_cast<unsigned int*>(base + o_tick);
+        s->order = reinterpret_cast<int*>(base + o_order);
     }
     return off;
 }
 
 // ------------------------------------------------------------------------------------------------ prep
-__global__ void prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample* out,
-                            unsigned int* ticket, unsigned long long* counts) {
+// Processing order of the samples (implicit kernel): longest grid columns first.  A warp item of a sample whose box
+// spans many z planes is a long serial chain (up to ~35 us when it runs alone at the end of the kernel); started
+// early it overlaps with everything else (longest-processing-time-first).  key = central-column range length.
+__device__ __forceinline__ float order_key(const Sample& S) {
+    return fminf(fminf(fabsf(S.idh[0]), fabsf(S.idh[1])), fabsf(S.idh[2]));
+}
+
+constexpr int kPrepSortMax = 1024;      // batches up to this size are ordered (one block); larger ones keep index order
+
+__global__ void __launch_bounds__(kPrepSortMax)
+prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample* out,
+            unsigned int* ticket, unsigned long long* counts, int* order) {
+    __shared__ float keys[kPrepSortMax];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0 && ticket) { ticket[0] = 0u; ticket[1] = 0u; }
+    float key = 0.f;
     if (b < batch) {
         double p[12];
 #pragma unroll
@@ -181,7 +196,24 @@ __global__ void prep_kernel(const void* params, int dtype, int batch, int clamp,
         Sample S;
         prep_sample(p, clamp != 0, g, S);
         out[b] = S;
+        key = order_key(S);
         if (counts) { counts[2 * b] = 0ull; counts[2 * b + 1] = 0ull; }
+    }
+    if (order) {
+        if (gridDim.x == 1) {                       // whole batch in this block: rank by key, ties by index
+            keys[threadIdx.x] = key;
+            __syncthreads();
+            if (b < batch) {
+                int rank = 0;
+                for (int j = 0; j < batch; ++j) {
+                    const float kj = keys[j];
+                    rank += (kj > key || (kj == key && j < b)) ? 1 : 0;
+                }
+                order[rank] = b;
+            }
+        } else if (b < batch) {
+            order[b] = b;
+        }
     }
 }
 
@@ -282,10 +314,15 @@ __device__ __forceinline__ int next_item(unsigned int* cursor, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ ImplicitLoss
+#ifdef SQ_TIMELINE     // tools/timeline.py: per-warp start / end timestamps and item counts of the implicit kernel
+__device__ unsigned long long g_timeline[3 * 8192];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 template <bool BWD, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitParams P, int total_items,
-                unsigned int* __restrict__ cursor, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
+implicit_kernel(const Sample* __restrict__ samples, const int* __restrict__ order, Grid g, Layout L, ImplicitParams P,
+                int total_items, unsigned int* __restrict__ cursor, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
     __shared__ Sample Ssh[THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -294,20 +331,34 @@ implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitPa
     // static assignment left the SMs idle at the tail.  The next item and its Sample are fetched while the current
     // item is processed.  No block-level barrier anywhere.
     int item = first_item();
+#ifdef SQ_TIMELINE
+    const unsigned long long t_begin = gtime();
+    unsigned long long n_items = 0, t_last_fetch = t_begin;
+#endif
     SampleFetch pre;
-    if (item < total_items) pre.fetch(samples + (L.rows_shift >= 0 ? item >> L.rows_shift : item / L.rows_per_sample), lane);
+    if (item < total_items) pre.fetch(samples + __ldg(order + (L.rows_shift >= 0 ? item >> L.rows_shift : item / L.rows_per_sample)), lane);
     while (item < total_items) {
+#ifdef SQ_TIMELINE
+        ++n_items; t_last_fetch = gtime();
+#endif
         int b, chunk;
         L.split(item, b, chunk);
+        b = __ldg(order + b);                              // position in the processing order -> sample
         pre.commit(&S, lane);
-        const int upcoming = next_item(cursor, lane);
-        if (upcoming < total_items) pre.fetch(samples + (L.rows_shift >= 0 ? upcoming >> L.rows_shift : upcoming / L.rows_per_sample), lane);
+        int upcoming = total_items;
 
         Acc acc;
         acc_zero(acc);
         ColIter it;
         it.init(L, chunk, lane);
         for (int k = 0; k < L.cpt; ++k, it.next(L)) {
+            if (k == L.cpt - 1) {
+                // Claim the next item (and start loading its Sample) only now: a warp that reserved its next item
+                // at the start of a long one kept that work from idle warps during the end-game.
+                upcoming = next_item(cursor, lane);
+                if (upcoming < total_items)
+                    pre.fetch(samples + __ldg(order + (L.rows_shift >= 0 ? upcoming >> L.rows_shift : upcoming / L.rows_per_sample)), lane);
+            }
             const int ia = it.ia, ib = it.ib;
             const bool valid = it.valid(L);
             const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
@@ -332,9 +383,15 @@ implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitPa
                 }
             }
         }
-        if (target) warp_reduce_store(acc, partials + (size_t)item * kAccN, acc.loss != 0.f);   // zero loss => zero gradient
+        if (target) warp_reduce_store(acc, partials + ((size_t)b * L.rows_per_sample + chunk) * kAccN, acc.loss != 0.f);   // zero loss => zero gradient
         item = upcoming;
     }
+#ifdef SQ_TIMELINE
+    if (BWD && lane == 0) {
+        const int w = first_item();
+        if (w < 8192) { g_timeline[3 * w] = t_begin; g_timeline[3 * w + 1] = gtime(); g_timeline[3 * w + 2] = (n_items << 40) | (t_last_fetch - t_begin); }
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ ExplicitLoss
@@ -622,9 +679,14 @@ int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
 }
 
 int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid& g, Sample* out,
-                unsigned int* ticket, unsigned long long* counts, cudaStream_t st) {
+                unsigned int* ticket, unsigned long long* counts, cudaStream_t st, int* order = nullptr) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
-    prep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts);
+    if (order && batch <= kPrepSortMax) {
+        const int threads = (batch + 31) / 32 * 32;
+        prep_kernel<<<1, threads, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
+    } else {
+        prep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
+    }
     return (int)cudaGetLastError();
 }
 
@@ -640,6 +702,12 @@ const char* sq_error_string(int err) { return cudaGetErrorString((cudaError_t)er
 int sq_device_sm_count(int device, int* sm_count) {
     return (int)cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device);
 }
+
+#ifdef SQ_TIMELINE
+int sq_debug_timeline(unsigned long long* host_out, int n) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * 3 * (size_t)n);
+}
+#endif
 
 void sq_profile_events(void* ev_before, void* ev_after) {
     t_ev_before = static_cast<cudaEvent_t>(ev_before);
@@ -664,7 +732,7 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, grad_pred ? SQ_IMPB_CPT : SQ_IMPF_CPT);
     const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, cull_bound(sharpness * kLog2e)};
-    rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
+    rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st, s.order);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     {
@@ -672,11 +740,11 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
         if (grad_pred) {
             const int blocks = persistent_blocks(items, SQ_IMPB_THREADS / 32, SQ_IMPB_MINB);
             implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB><<<blocks, SQ_IMPB_THREADS, 0, st>>>(
-                s.pred, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+                s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
         } else {
             const int blocks = persistent_blocks(items, SQ_IMPF_THREADS / 32, SQ_IMPF_MINB);
             implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB><<<blocks, SQ_IMPF_THREADS, 0, st>>>(
-                s.pred, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+                s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
         }
     }
     SQ_TRY(cudaGetLastError());

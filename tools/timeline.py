@@ -1,0 +1,63 @@
+"""Per-warp timeline of the implicit fwd+bwd kernel (debug build with -DSQ_TIMELINE): when each persistent warp
+started, fetched its last item and finished.  Shows how much of the kernel is end-game (warps idle, work left elsewhere).
+
+    python tools/timeline.py [extra -D defs]
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import sq_oracle as O
+from sq_recovery_b200 import _lib as L0
+import sq_recovery_b200 as S
+from sq_recovery_b200.functional import nearest_offsets
+
+defs = ["-DSQ_TIMELINE"] + [f"-D{d}" for d in sys.argv[1:]]
+out = "/tmp/libsq_timeline.so"
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-ftz=true", "-std=c++17",
+                       "-shared", "-Xcompiler", "-fPIC", "-o", out, os.path.join(ROOT, "sq_recovery_b200", "csrc", "sqloss.cu")] + defs)
+h = ctypes.CDLL(out)
+for name, (res, args) in L0._PROTOS.items():
+    fn = getattr(h, name); fn.restype, fn.argtypes = res, args
+B, R = int(os.environ.get("SQ_B", 256)), 64
+dev = torch.device("cuda:0")
+true = O.random_params(B, 0)
+pred = O.perturbed_params(true, 7)
+if os.environ.get("SQ_SORT"):
+    vol = pred[:, 0].clamp(0.05, 1) * pred[:, 1].clamp(0.05, 1) * pred[:, 2].clamp(0.05, 1)
+    order = torch.argsort(vol, descending=os.environ["SQ_SORT"] == "desc")
+    true, pred = true[order].contiguous(), pred[order].contiguous()
+true, pred = true.to(dev), pred.to(dev)
+img = S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(true).unsqueeze(1).contiguous()
+row_off, col_off = nearest_offsets(256, 256, R, dev)
+loss = torch.empty((), dtype=torch.float64, device=dev); grad = torch.empty_like(pred)
+nb = h.sq_scratch_bytes(B, R); scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+for _ in range(5):
+    rc = h.sq_implicit_loss(P(pred), 0, B, R, 1.0 / (R - 1), 1e-4, P(img), 256 * 256, P(row_off), P(col_off), 1.5, 260.0,
+                            P(loss), None, P(grad), None, P(scratch), nb, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+torch.cuda.synchronize()
+n = 8192
+buf = np.zeros(3 * n, dtype=np.uint64)
+h.sq_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
+assert h.sq_debug_timeline(buf.ctypes.data_as(ctypes.c_void_p), n) == 0
+buf = buf.reshape(n, 3)
+buf = buf[buf[:, 1] > 0]
+t0 = buf[:, 0].min()
+start, end = (buf[:, 0] - t0) / 1e3, (buf[:, 1] - t0) / 1e3
+items = buf[:, 2] >> np.uint64(40)
+last_fetch = (buf[:, 2] & np.uint64((1 << 40) - 1)) / 1e3 + start
+print(f"warps {len(buf)}  kernel span {end.max():.1f} us")
+print(f"start  : min {start.min():.1f} p50 {np.median(start):.1f} max {start.max():.1f}")
+print(f"end    : min {end.min():.1f} p10 {np.percentile(end,10):.1f} p50 {np.median(end):.1f} p90 {np.percentile(end,90):.1f} max {end.max():.1f}")
+print(f"last item fetched at: p50 {np.median(last_fetch):.1f} max {last_fetch.max():.1f};  duration of last item: p50 {np.median(end-last_fetch):.1f} p90 {np.percentile(end-last_fetch,90):.1f} max {(end-last_fetch).max():.1f}")
+print(f"items per warp: min {items.min()} p50 {np.median(items)} max {items.max()}")
+busy = (end - start).sum() / (len(buf) * end.max())
+print(f"warp-slot utilisation (sum of warp lifetimes / warps x span): {busy:.3f}")
