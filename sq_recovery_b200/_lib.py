@@ -6,7 +6,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsqloss.so")
+LIB_PATH = os.environ.get("SQ_LIBSQLOSS") or os.path.join(HERE, "libsqloss.so")   # override: tuning builds only
 SQ_F32, SQ_F64 = 0, 1
 
 _lib = None

@@ -29,7 +29,10 @@ namespace sq {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr double kLn2 = 0.6931471805599453;
 constexpr float kAbsFix = 1e-2f;          // |s| used when s == 0  (s^2 := 1e-4, classes.py:171-173)
-constexpr float kActive = 32.0f;          // |log2 of the sigmoid odds| beyond which o(1-o) < 2^-32 is dropped
+#ifndef SQ_KACTIVE
+#define SQ_KACTIVE 32.0f
+#endif
+constexpr float kActive = SQ_KACTIVE;     // |log2 of the sigmoid odds| beyond which o(1-o) < 2^-kActive is dropped
 
 // ---------------------------------------------------------------- MUFU primitives
 SQ_HD float ex2(float x) {
@@ -357,7 +360,10 @@ SQ_HD void warp_range(int n, int& c_lo, int& c_hi) {
 // gradient, which keeps the subtraction well conditioned.
 struct ImplicitParams { float kl; float tl; float bound; };     // k log2(e), tau log2(e), cull_bound(kl)
 
-constexpr float kDeep = 40.0f;       // points behind 2^-kDeep of transmittance carry no gradient (S_c < n 2^-kDeep)
+#ifndef SQ_KDEEP
+#define SQ_KDEEP 40.0f
+#endif
+constexpr float kDeep = SQ_KDEEP;       // points behind 2^-kDeep of transmittance carry no gradient (S_c < n 2^-kDeep)
 
 struct ColGrad {       // two-moment accumulators of one column
     float gs0[3], gs1[3], gz0[3], gz1[3], wa0[3], wa1[3], ge0[2], ge1[2];

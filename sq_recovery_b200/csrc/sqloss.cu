@@ -170,23 +170,37 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     return off;
 }
 
+// ------------------------------------------------------------------------------------------------ PDL
+// Programmatic dependent launch: the three kernels of a call are short (6 / 70 / 5 us) and strictly ordered; letting
+// the next one get resident while the previous one drains hides its launch latency.  pdl_wait() returns once the
+// preceding kernel has completed and its writes are visible; pdl_trigger() lets the following kernel start launching.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // ------------------------------------------------------------------------------------------------ prep
 // Processing order of the samples (implicit kernel): longest grid columns first.  A warp item of a sample whose box
 // spans many z planes is a long serial chain (up to ~35 us when it runs alone at the end of the kernel); started
-// early it overlaps with everything else (longest-processing-time-first).  key = central-column range length.
-__device__ __forceinline__ float order_key(const Sample& S) {
-    return fminf(fminf(fabsf(S.idh[0]), fabsf(S.idh[1])), fabsf(S.idh[2]));
+// early it overlaps with everything else (longest-processing-time-first).  Only the work ORDER depends on this, never
+// a result, so a counting sort into 32 length classes (arbitrary order inside a class) is enough.
+constexpr int kOrderBuckets = 32;
+__device__ __forceinline__ int order_bucket(const Sample& S, const Grid& g) {
+    const float key = fminf(fminf(fabsf(S.idh[0]), fabsf(S.idh[1])), fabsf(S.idh[2]));   // planes per unit of |s|
+    const float len = fminf(2.4f * key * g.inv_n, 1.0f);                                  // central column range / n
+    return (kOrderBuckets - 1) - (int)(len * (float)(kOrderBuckets - 1));                 // 0 = longest
 }
 
 constexpr int kPrepSortMax = 1024;      // batches up to this size are ordered (one block); larger ones keep index order
 
-__global__ void __launch_bounds__(kPrepSortMax)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
 prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample* out,
             unsigned int* ticket, unsigned long long* counts, int* order) {
-    __shared__ float keys[kPrepSortMax];
+    __shared__ int cnt[kOrderBuckets], off[kOrderBuckets];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool sort = order && gridDim.x == 1;           // whole batch in this block
+    if (sort && threadIdx.x < kOrderBuckets) cnt[threadIdx.x] = 0;
     if (b == 0 && ticket) { ticket[0] = 0u; ticket[1] = 0u; }
-    float key = 0.f;
+    int bucket = 0;
     if (b < batch) {
         double p[12];
 #pragma unroll
@@ -196,24 +210,20 @@ prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample*
         Sample S;
         prep_sample(p, clamp != 0, g, S);
         out[b] = S;
-        key = order_key(S);
+        bucket = order_bucket(S, g);
         if (counts) { counts[2 * b] = 0ull; counts[2 * b + 1] = 0ull; }
+        if (order && !sort) order[b] = b;
     }
-    if (order) {
-        if (gridDim.x == 1) {                       // whole batch in this block: rank by key, ties by index
-            keys[threadIdx.x] = key;
-            __syncthreads();
-            if (b < batch) {
-                int rank = 0;
-                for (int j = 0; j < batch; ++j) {
-                    const float kj = keys[j];
-                    rank += (kj > key || (kj == key && j < b)) ? 1 : 0;
-                }
-                order[rank] = b;
-            }
-        } else if (b < batch) {
-            order[b] = b;
+    if (sort) {
+        __syncthreads();
+        if (b < batch) atomicAdd(&cnt[bucket], 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int k = 0; k < kOrderBuckets; ++k) { off[k] = run; run += cnt[k]; }
         }
+        __syncthreads();
+        if (b < batch) order[atomicAdd(&off[bucket], 1)] = b;
     }
 }
 
@@ -327,6 +337,8 @@ implicit_kernel(const Sample* __restrict__ samples, const int* __restrict__ orde
     __shared__ Sample Ssh[THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& S = Ssh[warp];
+    pdl_wait();                                           // prep_kernel's Samples, order and cursor
+    pdl_trigger();                                        // finalize_kernel may get resident (it waits for us)
     // Persistent warps pull work items from a global cursor: item cost varies a lot with the culled z range, and a
     // static assignment left the SMs idle at the tail.  The next item and its Sample are fetched while the current
     // item is processed.  No block-level barrier anywhere.
@@ -548,6 +560,7 @@ finalize_kernel(const Sample* __restrict__ samples, Grid g, int batch, int items
     const int b = blockIdx.x, lane = threadIdx.x;
     __shared__ double acc[kAccN];
     __shared__ double part[32][kAccN + 1];
+    pdl_wait();                                           // partial rows of the column kernel
     {   // lane l sums rows l, l+32, ... (independent loads in flight), then a fixed-order sum over the 32 lanes
         double s[kAccN];
 #pragma unroll
@@ -662,6 +675,18 @@ int check_scratch(int batch, int n, void* scratch, size_t bytes, Scratch* s) {
     return 0;
 }
 
+// kernel launch that may overlap the tail of the preceding kernel in the stream (the kernel must call pdl_wait())
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // blocks of a persistent column kernel: enough to fill every SM at the kernel's occupancy, no more than the work
 int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
     static int sms[64] = {0};
@@ -681,12 +706,13 @@ int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
 int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid& g, Sample* out,
                 unsigned int* ticket, unsigned long long* counts, cudaStream_t st, int* order = nullptr) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
-    if (order && batch <= kPrepSortMax) {
-        const int threads = (batch + 31) / 32 * 32;
-        prep_kernel<<<1, threads, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
-    } else {
-        prep_kernel<<<(batch + 127) / 128, 128, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
-    }
+    const int threads = (batch + 31) / 32 * 32;
+    if (order && batch <= 256)
+        prep_kernel<256><<<1, threads, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
+    else if (order && batch <= kPrepSortMax)
+        prep_kernel<kPrepSortMax><<<1, threads, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
+    else
+        prep_kernel<128><<<(batch + 127) / 128, 128, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
     return (int)cudaGetLastError();
 }
 
@@ -735,25 +761,46 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
     rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st, s.order);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
+    // Programmatic dependent launch measured 4.6 us SLOWER per step inside CUDA-graph replay on B200 (resident
+    // waiting blocks delay prep's tail; profiles/tune_r01.txt), so it is compiled in only with -DSQ_PDL.
+#ifdef SQ_PDL
+    const bool pdl = (t_ev_before == nullptr && t_ev_after == nullptr);   // an event record in between breaks the chain
+#else
+    const bool pdl = false;
+#endif
     {
         ColumnKernelTimer timer(st);
         if (grad_pred) {
             const int blocks = persistent_blocks(items, SQ_IMPB_THREADS / 32, SQ_IMPB_MINB);
-            implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB><<<blocks, SQ_IMPB_THREADS, 0, st>>>(
-                s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+            if (pdl)
+                SQ_TRY(launch_pdl(implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB>, blocks, SQ_IMPB_THREADS, st,
+                                  s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off,
+                                  s.partials, depth_out));
+            else
+                implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB><<<blocks, SQ_IMPB_THREADS, 0, st>>>(
+                    s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
         } else {
             const int blocks = persistent_blocks(items, SQ_IMPF_THREADS / 32, SQ_IMPF_MINB);
-            implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB><<<blocks, SQ_IMPF_THREADS, 0, st>>>(
-                s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+            if (pdl)
+                SQ_TRY(launch_pdl(implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB>, blocks, SQ_IMPF_THREADS, st,
+                                  s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off,
+                                  s.partials, depth_out));
+            else
+                implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB><<<blocks, SQ_IMPF_THREADS, 0, st>>>(
+                    s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
         }
     }
     SQ_TRY(cudaGetLastError());
     if (target) {
         const double nn = (double)n * n;
-        finalize_kernel<FIN_IMPLICIT><<<batch, 32, 0, st>>>(
-            s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn,
-            -(double)sharpness * (double)tau / (nn * n * (double)batch), pred_dtype, grad_pred, s.per_sample,
-            per_sample, loss_out, s.ticket);
+        const double gscale = -(double)sharpness * (double)tau / (nn * n * (double)batch);
+        if (pdl)
+            SQ_TRY(launch_pdl(finalize_kernel<FIN_IMPLICIT>, batch, 32, st, s.pred, g, batch, L.rows_per_sample, s.partials,
+                              1.0 / nn, gscale, pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, s.ticket));
+        else
+            finalize_kernel<FIN_IMPLICIT><<<batch, 32, 0, st>>>(s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn,
+                                                               gscale, pred_dtype, grad_pred, s.per_sample, per_sample,
+                                                               loss_out, s.ticket);
         SQ_TRY(cudaGetLastError());
     }
     return 0;
