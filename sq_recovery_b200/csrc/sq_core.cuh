@@ -168,18 +168,14 @@ struct Fwd {
     float d1, t1, h1;         // lA - lB, 2^-|d1|, lg2(1 + t1)
     float d2, t2, h2;         // lE - lC, 2^-|d2|, lg2(1 + t2)
     float lG, F;
-    bool zx, zy, zz;          // exact-zero flags (fix-up applied)
 };
 
 template <bool FIX>
 SQ_HD void point_forward(const Sample& S, float sx, float sy, float sz, Fwd& f) {
     f.sx = sx; f.sy = sy; f.sz = sz;
     float mx = sx, my = sy, mz = sz;
-    if (FIX) {
-        f.zx = (sx == 0.0f); f.zy = (sy == 0.0f); f.zz = (sz == 0.0f);
-        mx = f.zx ? kAbsFix : mx; my = f.zy ? kAbsFix : my; mz = f.zz ? kAbsFix : mz;
-    } else {
-        f.zx = f.zy = f.zz = false;
+    if (FIX) {      // s == 0 exactly -> |s| := 1e-2 (the reference's "s^2 == 0 -> 1e-4")
+        mx = (sx == 0.0f) ? kAbsFix : mx; my = (sy == 0.0f) ? kAbsFix : my; mz = (sz == 0.0f) ? kAbsFix : mz;
     }
     const float lA = S.pxy * lg2_abs(mx);
     const float lB = S.pxy * lg2_abs(my);
@@ -228,19 +224,19 @@ SQ_HD void point_backward(const Fwd& f, float W, Bwd& b) {
     b.ge[0] = WF * fmaf(s2, fabsf(f.d2), f.h2);
     b.ge[1] = wxy * fmaf(s1, fabsf(f.d1), f.h1);
     // exact zeros: the fix-up replaces s^2 by a constant, so no gradient reaches s or a through that term
-    b.wa[0] = f.zx ? 0.0f : wx;
-    b.wa[1] = f.zy ? 0.0f : wy;
-    b.wa[2] = f.zz ? 0.0f : wz;
-    b.gs[0] = f.zx ? 0.0f : wx * rcp(f.sx);
-    b.gs[1] = f.zy ? 0.0f : wy * rcp(f.sy);
-    b.gs[2] = f.zz ? 0.0f : wz * rcp(f.sz);
+    const bool zx = (f.sx == 0.0f), zy = (f.sy == 0.0f), zz = (f.sz == 0.0f);
+    b.wa[0] = zx ? 0.0f : wx;
+    b.wa[1] = zy ? 0.0f : wy;
+    b.wa[2] = zz ? 0.0f : wz;
+    b.gs[0] = zx ? 0.0f : wx * rcp(f.sx);
+    b.gs[1] = zy ? 0.0f : wy * rcp(f.sy);
+    b.gs[2] = zz ? 0.0f : wz * rcp(f.sz);
 }
 
 // a harmless point for lanes that carry no gradient but run the backward with their warp (weight 0)
 SQ_HD void fwd_neutral(Fwd& f) {
     f.sx = f.sy = f.sz = 1.f;
     f.d1 = f.d2 = 0.f; f.t1 = f.t2 = 1.f; f.h1 = f.h2 = 1.f; f.lG = 0.f; f.F = 1.f;
-    f.zx = f.zy = f.zz = false;
 }
 
 // ---------------------------------------------------------------- per-thread accumulators
