@@ -191,28 +191,50 @@ __device__ __forceinline__ int order_bucket(const Sample& S, const Grid& g) {
 
 constexpr int kPrepSortMax = 1024;      // batches up to this size are ordered (one block); larger ones keep index order
 
+constexpr int kPrepWords = (int)(sizeof(Sample) / 4);
+
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT)
 prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample* out,
             unsigned int* ticket, unsigned long long* counts, int* order) {
     __shared__ int cnt[kOrderBuckets], off[kOrderBuckets];
+    // Samples are 328-byte records: written straight from the threads, a warp's stores touch 32 distinct sectors each
+    // (21 k sector writes from one SM, ~10 us).  They are staged per warp in shared memory, kStage records at a time,
+    // and copied out with coalesced stores instead.
+    constexpr int kStage = MAXT <= 256 ? 8 : 4;
+    __shared__ uint32_t stage[MAXT / 32][kStage * kPrepWords];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const bool sort = order && gridDim.x == 1;           // whole batch in this block
     if (sort && threadIdx.x < kOrderBuckets) cnt[threadIdx.x] = 0;
     if (b == 0 && ticket) { ticket[0] = 0u; ticket[1] = 0u; }
     int bucket = 0;
+    Sample S;
     if (b < batch) {
         double p[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i)
             p[i] = dtype == SQ_F64 ? static_cast<const double*>(params)[12 * (size_t)b + i]
                                    : (double)static_cast<const float*>(params)[12 * (size_t)b + i];
-        Sample S;
         prep_sample(p, clamp != 0, g, S);
-        out[b] = S;
         bucket = order_bucket(S, g);
         if (counts) { counts[2 * b] = 0ull; counts[2 * b + 1] = 0ull; }
         if (order && !sort) order[b] = b;
+    }
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int warp_first = b - lane;                  // first sample of this warp
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(&S);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out);
+        for (int r = 0; r < 32 / kStage; ++r) {
+            if (lane / kStage == r && b < batch)
+                for (int w = 0; w < kPrepWords; ++w) stage[warp][(lane % kStage) * kPrepWords + w] = mine[w];
+            __syncwarp();
+            const int first = warp_first + r * kStage;    // records first .. first + kStage - 1 are staged
+            int nrec = batch - first;
+            nrec = nrec < 0 ? 0 : (nrec > kStage ? kStage : nrec);
+            for (int w = lane; w < nrec * kPrepWords; w += 32) dst[(size_t)first * kPrepWords + w] = stage[warp][w];
+            __syncwarp();
+        }
     }
     if (sort) {
         __syncthreads();
