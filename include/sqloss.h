@@ -38,8 +38,17 @@ int sq_device_sm_count(int device, int* sm_count);
  * stream.  One-shot; pass cudaEvent_t handles created with timing enabled.  bench.py uses it for the roofline. */
 void sq_profile_events(void* ev_before, void* ev_after);
 
-/* Bytes of device scratch a call with this batch size and grid size needs (same for all entry points). */
+/* Bytes of device scratch a call with this batch size and grid size needs (same for all entry points).
+ *
+ * Scratch contract: the first 256 bytes of a scratch buffer are a control block (work-queue counters of the
+ * persistent kernels) that must be ZERO when a call starts.  Call sq_scratch_init() once after allocating the buffer
+ * (or zero it yourself); every entry point leaves the block zero again when its kernels have finished, so one buffer
+ * can be reused by any sequence of stream-ordered calls, with any batch / grid sizes it is large enough for, without
+ * a memset on the per-call path.  A buffer must not be used by two streams at once.  After a call that returned an
+ * error, call sq_scratch_init() again.
+ */
 size_t sq_scratch_bytes(int batch, int n);
+int sq_scratch_init(void* scratch, size_t scratch_bytes, sq_stream_t stream);
 
 /* ImplicitLoss.__call__ + depth_projection (torch/classes.py:232-295), forward and backward in one pass.
  *   pred        [batch,12] parameters (pred_dtype)

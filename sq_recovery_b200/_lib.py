@@ -17,6 +17,7 @@ _PROTOS = {
     "sq_device_sm_count": (c_int, [c_int, POINTER(c_int)]),
     "sq_profile_events": (None, [c_void_p, c_void_p]),
     "sq_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "sq_scratch_init": (c_int, [c_void_p, c_size_t, c_void_p]),
     "sq_implicit_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_longlong, c_void_p,
                                  c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),

@@ -77,6 +77,9 @@ struct Layout {
         if (rows_shift >= 0) { b = item >> rows_shift; chunk = item & (rows_per_sample - 1); }
         else { b = item / rows_per_sample; chunk = item - b * rows_per_sample; }
     }
+    __host__ __device__ __forceinline__ int sample_of(int item) const {
+        return rows_shift >= 0 ? item >> rows_shift : item / rows_per_sample;
+    }
 };
 
 __host__ __device__ inline Layout make_layout(int n, int max_cpt) {
@@ -131,14 +134,35 @@ struct ColIter {
 };
 
 // ------------------------------------------------------------------------------------------------ scratch
+// Work items are handed to the persistent warps in order of estimated cost (longest first, empty last): the plan
+// kernel sorts them into kClasses cost classes, one queue per class.  Class k holds items whose estimated number of
+// z planes is in (max / 2^(k+1), max / 2^k]; the last class holds items estimated empty.
+constexpr int kClasses = 8;
+constexpr int kPlanThreads = 128;
+constexpr int kPlanMaxItems = 8192;      // items per sample the plan kernel can classify (more: index order)
+
+// First 256 bytes of every scratch buffer.  qcount and retired must be ZERO when a call starts: sq_scratch_init()
+// zeroes them once and every kernel that uses them leaves them zero again (the last warp to retire cleans up), so no
+// memset sits on the per-call critical path.  ticket and cursor are reset by the plan / prep kernel of each call.
+struct Control {
+    unsigned int ticket;                 // samples finalized so far (the last one averages the batch)
+    unsigned int cursor;                 // work-stealing cursor of the column kernel
+    unsigned int retired;                // items retired by warps that have left the column kernel
+    unsigned int pad0;
+    unsigned int qcount[kClasses];       // items per cost class
+    unsigned int pad1[64 - 4 - kClasses];
+};
+static_assert(sizeof(Control) == 256, "Control block is 256 bytes");
+
 struct Scratch {
+    Control* ctl;
     Sample* pred;          // [batch]
     Sample* tru;           // [batch]
     float* partials;       // [batch * rows_per_sample][kAccN]
     double* per_sample;    // [batch]
     unsigned long long* counts;   // [batch][2] (IoU)
-    unsigned int* ticket;  // [0] finalize ticket, [1] work-stealing cursor of the column kernel
-    int* order;            // [batch] sample processed at position i (longest columns first)
+    int* queue;            // [kClasses][queue_cap] item ids by cost class; nullptr: items are taken in index order
+    int queue_cap;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -147,6 +171,7 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     const Layout L = make_layout(n > 0 ? n : 1, 1);      // cpt = 1: the most rows any kernel configuration writes
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_ctl = take(sizeof(Control));          // always at offset 0
     const size_t o_pred = take(sizeof(Sample) * (size_t)batch);
     const size_t o_true = take(sizeof(Sample) * (size_t)batch);
     // partial rows: one per warp item for the column kernels, one per 256 pixels for the point-list kernel
@@ -156,96 +181,134 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     const size_t o_part = take(sizeof(float) * kAccN * rows_ps * (size_t)batch);
     const size_t o_ps = take(sizeof(double) * (size_t)batch);
     const size_t o_cnt = take(sizeof(unsigned long long) * 2 * (size_t)batch);
-    const size_t o_tick = take(sizeof(unsigned int) * 4);
-    const size_t o_order = take(sizeof(int) * (size_t)batch);
+    const size_t cap = (size_t)L.rows_per_sample * (size_t)batch;
+    const bool queued = L.rows_per_sample <= kPlanMaxItems && cap < (1u << 30);
+    const size_t o_queue = take(queued ? sizeof(int) * kClasses * cap : 0);
     if (s) {
+        s->ctl = reinterpret_cast<Control*>(base + o_ctl);
         s->pred = reinterpret_cast<Sample*>(base + o_pred);
         s->tru = reinterpret_cast<Sample*>(base + o_true);
         s->partials = reinterpret_cast<float*>(base + o_part);
         s->per_sample = reinterpret_cast<double*>(base + o_ps);
         s->counts = reinterpret_cast<unsigned long long*>(base + o_cnt);
-        s->ticket = reinterpret_cast<unsigned int*>(base + o_tick);
-        s->order = reinterpret_cast<int*>(base + o_order);
+        s->queue = queued ? reinterpret_cast<int*>(base + o_queue) : nullptr;
+        s->queue_cap = (int)cap;
     }
     return off;
 }
 
-// ------------------------------------------------------------------------------------------------ PDL
-// Programmatic dependent launch: the three kernels of a call are short (6 / 70 / 5 us) and strictly ordered; letting
-// the next one get resident while the previous one drains hides its launch latency.  pdl_wait() returns once the
-// preceding kernel has completed and its writes are visible; pdl_trigger() lets the following kernel start launching.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+// ------------------------------------------------------------------------------------------------ prep / plan
+constexpr int kSampleWords = (int)(sizeof(Sample) / 4);
+static_assert(sizeof(Sample) % 4 == 0, "Sample must be word-copyable");
 
-// ------------------------------------------------------------------------------------------------ prep
-// Processing order of the samples (implicit kernel): longest grid columns first.  A warp item of a sample whose box
-// spans many z planes is a long serial chain (up to ~35 us when it runs alone at the end of the kernel); started
-// early it overlaps with everything else (longest-processing-time-first).  Only the work ORDER depends on this, never
-// a result, so a counting sort into 32 length classes (arbitrary order inside a class) is enough.
-constexpr int kOrderBuckets = 32;
-__device__ __forceinline__ int order_bucket(const Sample& S, const Grid& g) {
-    const float key = fminf(fminf(fabsf(S.idh[0]), fabsf(S.idh[1])), fabsf(S.idh[2]));   // planes per unit of |s|
-    const float len = fminf(2.4f * key * g.inv_n, 1.0f);                                  // central column range / n
-    return (kOrderBuckets - 1) - (int)(len * (float)(kOrderBuckets - 1));                 // 0 = longest
+__device__ __forceinline__ void load_params(const void* params, int dtype, int b, double* p) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+        p[i] = dtype == SQ_F64 ? static_cast<const double*>(params)[12 * (size_t)b + i]
+                               : (double)static_cast<const float*>(params)[12 * (size_t)b + i];
 }
 
-constexpr int kPrepSortMax = 1024;      // batches up to this size are ordered (one block); larger ones keep index order
-
-constexpr int kPrepWords = (int)(sizeof(Sample) / 4);
-
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT)
-prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample* out,
-            unsigned int* ticket, unsigned long long* counts, int* order) {
-    __shared__ int cnt[kOrderBuckets], off[kOrderBuckets];
-    // Samples are 328-byte records: written straight from the threads, a warp's stores touch 32 distinct sectors each
-    // (21 k sector writes from one SM, ~10 us).  They are staged per warp in shared memory, kStage records at a time,
-    // and copied out with coalesced stores instead.
-    constexpr int kStage = MAXT <= 256 ? 8 : 4;
-    __shared__ uint32_t stage[MAXT / 32][kStage * kPrepWords];
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool sort = order && gridDim.x == 1;           // whole batch in this block
-    if (sort && threadIdx.x < kOrderBuckets) cnt[threadIdx.x] = 0;
-    if (b == 0 && ticket) { ticket[0] = 0u; ticket[1] = 0u; }
-    int bucket = 0;
-    Sample S;
-    if (b < batch) {
+// prep (point-list and field kernels): one warp per sample; lane 0 does the fp64 work into shared memory, the warp
+// copies the 328-byte record out with coalesced stores.
+__global__ void __launch_bounds__(128)
+prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample* out, Control* ctl) {
+    __shared__ Sample Ssh[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + warp;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ctl) { ctl->ticket = 0u; ctl->cursor = 0u; }
+    if (b >= batch) return;
+    if (lane == 0) {
         double p[12];
+        load_params(params, dtype, b, p);
+        prep_sample(p, clamp != 0, g, Ssh[warp]);
+    }
+    __syncwarp();
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&Ssh[warp]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + b);
+    for (int w = lane; w < kSampleWords; w += 32) dst[w] = src[w];
+}
+
+// Estimated z planes a 32-column group of one sample walks: union of the culled ranges of five probe columns (the
+// corners and the middle of the warp's patch).  Only the ORDER in which work is handed out depends on this, never a
+// result.
+__device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, float bound, int group) {
+    int lo = g.n, hi = -1;
+    const int probes[5] = {0, 7, 12, 24, 31};
 #pragma unroll
-        for (int i = 0; i < 12; ++i)
-            p[i] = dtype == SQ_F64 ? static_cast<const double*>(params)[12 * (size_t)b + i]
-                                   : (double)static_cast<const float*>(params)[12 * (size_t)b + i];
-        prep_sample(p, clamp != 0, g, S);
-        bucket = order_bucket(S, g);
+    for (int q = 0; q < 5; ++q) {
+        const int lane = probes[q], slot = group * 32 + lane;
+        if (slot >= L.slots) continue;
+        int ia, ib;
+        if (L.patched) {
+            const int pw = L.n >> 3, pb = group / pw, pa = group - pb * pw;
+            ia = (pa << 3) + (lane & 7);
+            ib = (pb << 2) + (lane >> 3);
+        } else {
+            ib = slot / L.n;
+            ia = slot - ib * L.n;
+        }
+        float bh[3], bl[3];
+        column_base(S, g, ia, ib, bh, bl);
+        int c_lo, c_hi;
+        column_range(S, g, bound, bh, c_lo, c_hi);
+        if (c_hi >= c_lo) { lo = c_lo < lo ? c_lo : lo; hi = c_hi > hi ? c_hi : hi; }
+    }
+    return hi >= lo ? hi - lo + 1 : 0;
+}
+
+// plan (column kernels): one block per sample.  Builds the Sample record(s) like prep, then estimates the cost of each
+// of the sample's work items and appends the item to the queue of its cost class.  NS = SQs per item (2: true + pred).
+template <int NS>
+__global__ void __launch_bounds__(kPlanThreads)
+plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Grid g, Layout L, float bound,
+            Sample* out_a, Sample* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap) {
+    __shared__ Sample Ssh[NS];
+    __shared__ unsigned char cls[kPlanMaxItems];
+    __shared__ unsigned int ccnt[kClasses], cbase[kClasses];
+    const int b = blockIdx.x;
+    if (threadIdx.x < kClasses) ccnt[threadIdx.x] = 0u;
+    if (threadIdx.x == 64) {
+        if (b == 0) { ctl->ticket = 0u; ctl->cursor = 0u; }
         if (counts) { counts[2 * b] = 0ull; counts[2 * b + 1] = 0ull; }
-        if (order && !sort) order[b] = b;
     }
-    {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int warp_first = b - lane;                  // first sample of this warp
-        const uint32_t* mine = reinterpret_cast<const uint32_t*>(&S);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(out);
-        for (int r = 0; r < 32 / kStage; ++r) {
-            if (lane / kStage == r && b < batch)
-                for (int w = 0; w < kPrepWords; ++w) stage[warp][(lane % kStage) * kPrepWords + w] = mine[w];
-            __syncwarp();
-            const int first = warp_first + r * kStage;    // records first .. first + kStage - 1 are staged
-            int nrec = batch - first;
-            nrec = nrec < 0 ? 0 : (nrec > kStage ? kStage : nrec);
-            for (int w = lane; w < nrec * kPrepWords; w += 32) dst[(size_t)first * kPrepWords + w] = stage[warp][w];
-            __syncwarp();
-        }
+    if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < NS) {        // lane 0 of warp 0 (and of warp 1 for the second SQ)
+        const int w = threadIdx.x >> 5;
+        double p[12];
+        load_params(w == 0 ? params_a : params_b, dtype, b, p);
+        prep_sample(p, clamp != 0, g, Ssh[w]);
     }
-    if (sort) {
-        __syncthreads();
-        if (b < batch) atomicAdd(&cnt[bucket], 1);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int run = 0;
-            for (int k = 0; k < kOrderBuckets; ++k) { off[k] = run; run += cnt[k]; }
+    __syncthreads();
+    for (int w = threadIdx.x; w < NS * kSampleWords; w += kPlanThreads) {
+        const int which = w / kSampleWords, i = w - which * kSampleWords;
+        reinterpret_cast<uint32_t*>((which == 0 ? out_a : out_b) + b)[i] = reinterpret_cast<const uint32_t*>(&Ssh[which])[i];
+    }
+    if (!queue) return;
+    const int J = L.rows_per_sample;
+    const int max_cost = L.cpt * L.n * NS;
+    for (int j = threadIdx.x; j < J; j += kPlanThreads) {
+        int cost = 0;
+        for (int k = 0; k < L.cpt; ++k) {
+            const int group = j + k * J;
+            if (group * 32 >= L.slots) break;
+#pragma unroll
+            for (int w = 0; w < NS; ++w) cost += group_planes(Ssh[w], g, L, bound, group);
         }
-        __syncthreads();
-        if (b < batch) order[atomicAdd(&off[bucket], 1)] = b;
+        int c = kClasses - 1;                              // estimated empty
+        if (cost > 0) { c = 0; while (c < kClasses - 2 && (cost << (c + 1)) <= max_cost) ++c; }
+        cls[j] = (unsigned char)c;
+        atomicAdd(&ccnt[c], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kClasses) {
+        const unsigned int c = ccnt[threadIdx.x];
+        cbase[threadIdx.x] = c ? atomicAdd(&ctl->qcount[threadIdx.x], c) : 0u;
+        ccnt[threadIdx.x] = 0u;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < J; j += kPlanThreads) {
+        const int c = cls[j];
+        const unsigned int r = atomicAdd(&ccnt[c], 1u);
+        queue[(size_t)c * cap + cbase[c] + r] = b * J + j;
     }
 }
 
@@ -264,22 +327,37 @@ __device__ __forceinline__ void acc_to_array(const Acc& a, float* v) {
     v[15] = a.ge[0]; v[16] = a.ge[1]; v[17] = a.loss;
 }
 
-// per-thread Acc -> one row of kAccN floats per WARP (lane i ends up holding and storing sum i)
-__device__ __forceinline__ void warp_reduce_store(const Acc& a, float* row, bool nonzero) {
+// per-thread Acc -> one row of kAccN floats per WARP, through the warp's own shared-memory tile: every lane writes
+// its 18 sums (5 vector stores), lane i < 18 adds up column i over the 32 lanes in a fixed order.  37 shared-memory
+// instructions and 32 adds per warp instead of the 90 shuffles + 90 adds of a butterfly per value.
+constexpr int kRedStride = 20;           // floats per lane in the tile (18 used; 80 bytes keeps float4 alignment)
+constexpr int kRedFloats = 32 * kRedStride;
+
+__device__ __forceinline__ void warp_reduce_store(const Acc& a, float* tile, float* row, bool nonzero) {
     const int lane = threadIdx.x & 31;
     if (!__any_sync(0xffffffffu, nonzero)) {          // e.g. image-border patches: no object, no loss, no gradient
         if (lane < kAccN) row[lane] = 0.f;
         return;
     }
-    float v[kAccN];
+    float v[kRedStride];
     acc_to_array(a, v);
-    float mine = 0.f;
+    v[18] = v[19] = 0.f;
+    float4* mine = reinterpret_cast<float4*>(tile + lane * kRedStride);
 #pragma unroll
-    for (int i = 0; i < kAccN; ++i) {
-        const float s = warp_sum(v[i]);
-        if (lane == i) mine = s;
+    for (int q = 0; q < kRedStride / 4; ++q) mine[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+    if (lane < kAccN) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; r += 4) {
+            s0 += tile[(r + 0) * kRedStride + lane];
+            s1 += tile[(r + 1) * kRedStride + lane];
+            s2 += tile[(r + 2) * kRedStride + lane];
+            s3 += tile[(r + 3) * kRedStride + lane];
+        }
+        row[lane] = (s0 + s1) + (s2 + s3);
     }
-    if (lane < kAccN) row[lane] = mine;
+    __syncwarp();
 }
 
 // per-thread Acc -> one row of kAccN floats per BLOCK (point-list kernel)
@@ -302,15 +380,13 @@ __device__ __forceinline__ void block_reduce_store(const Acc& a, float (*red)[kA
 }
 
 __device__ __forceinline__ void load_sample(Sample* dst, const Sample* src) {       // whole block
-    static_assert(sizeof(Sample) % 4 == 0, "Sample must be word-copyable");
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-    for (int i = threadIdx.x; i < (int)(sizeof(Sample) / 4); i += blockDim.x) d[i] = s[i];
+    for (int i = threadIdx.x; i < kSampleWords; i += blockDim.x) d[i] = s[i];
 }
 
 // Register-staged copy of one Sample by one warp: fetch() issues the global loads (their latency overlaps whatever
 // the warp does next), commit() writes them to the warp's private shared-memory copy.
-constexpr int kSampleWords = (int)(sizeof(Sample) / 4);
 constexpr int kSampleRegs = (kSampleWords + 31) / 32;
 struct SampleFetch {
     uint32_t w[kSampleRegs];
@@ -334,15 +410,78 @@ struct SampleFetch {
     }
 };
 
-// Work distribution: the first item of a warp is its global warp index (no atomic burst when 3000 warps start at
-// once), later items come from a cursor that counts on from there.
-__device__ __forceinline__ int first_item() {
+// ------------------------------------------------------------------------------------------------ work distribution
+// Positions 0 .. total-1 of the processing order.  The first position of a warp is its global warp index (no atomic
+// burst when 2400 warps start at once; every position below the warp count has exactly one owner whenever that warp
+// starts), later positions come from a cursor that counts on from there.
+__device__ __forceinline__ int first_position() {
     return (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
 }
-__device__ __forceinline__ int next_item(unsigned int* cursor, int lane) {
-    int item = 0;
-    if (lane == 0) item = (int)(atomicAdd(cursor, 1u) + gridDim.x * (blockDim.x >> 5));
-    return __shfl_sync(0xffffffffu, item, 0);
+__device__ __forceinline__ int next_position(unsigned int* cursor, int lane) {
+    int pos = 0;
+    if (lane == 0) pos = (int)(atomicAdd(cursor, 1u) + gridDim.x * (blockDim.x >> 5));
+    return __shfl_sync(0xffffffffu, pos, 0);
+}
+
+// position -> work item through the cost-class queues the plan kernel filled (class 0 first)
+struct WorkMap {
+    unsigned int excl;       // lane k < kClasses: items in classes before k; other lanes: all items
+    __device__ __forceinline__ void init(const Control* ctl, int lane) {
+        const unsigned int cnt = lane < kClasses ? __ldcg(&ctl->qcount[lane]) : 0u;
+        unsigned int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < kClasses; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        excl = incl - cnt;
+    }
+    __device__ __forceinline__ int item(const int* __restrict__ queue, int cap, int pos, int lane) const {
+        if (!queue) return pos;
+        const unsigned int m = __ballot_sync(0xffffffffu, lane < kClasses && (unsigned int)pos >= excl);
+        const int c = 31 - __clz((int)m);                  // the highest class that starts at or before pos
+        const unsigned int start = __shfl_sync(0xffffffffu, excl, c);
+        return __ldg(queue + (size_t)c * cap + ((unsigned int)pos - start));
+    }
+};
+
+// Depth-1 work pipeline of a persistent warp: the current item, and the next one claimed while the current one is
+// being processed (claim() is called when the last column group of the current item starts: claimed earlier, the item
+// would be kept from idle warps during the end-game; claimed later, the cursor -> queue -> Sample chain of L2 round
+// trips would not be hidden).  Deeper pipelines (claims 2-3 items ahead) were measured 25 % slower: they undo the
+// longest-first order while the items are still expensive.
+struct WorkPipe {
+    WorkMap wm;
+    const int* queue; unsigned int* cursor;
+    int cap, total;
+    int item, next;              // current / next work item (-1: none)
+    __device__ __forceinline__ void start(Control* ctl, const int* q, int cap_, int total_, int lane) {
+        queue = q; cursor = &ctl->cursor; cap = cap_; total = total_;
+        item = next = -1;
+        const int p0 = first_position();
+        if (p0 >= total) return;
+        wm.init(ctl, lane);
+        item = wm.item(queue, cap, p0, lane);
+    }
+    __device__ __forceinline__ bool claim(int lane) {
+        const int pos = next_position(cursor, lane);
+        next = pos < total ? wm.item(queue, cap, pos, lane) : -1;
+        return next >= 0;
+    }
+    __device__ __forceinline__ void rotate() { item = next; next = -1; }
+};
+
+// A warp leaving a column kernel reports how many items it processed; the one that completes the count puts the
+// control block back to its between-calls state (every warp that had work read qcount before it processed anything).
+__device__ __forceinline__ void retire(Control* ctl, unsigned int n_items, unsigned int total, int lane) {
+    if (lane == 0 && n_items) {
+        const unsigned int before = atomicAdd(&ctl->retired, n_items);
+        if (before + n_items == total) {
+            ctl->retired = 0u;
+#pragma unroll
+            for (int k = 0; k < kClasses; ++k) ctl->qcount[k] = 0u;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ ImplicitLoss
@@ -353,77 +492,83 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 
 template <bool BWD, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-implicit_kernel(const Sample* __restrict__ samples, const int* __restrict__ order, Grid g, Layout L, ImplicitParams P,
-                int total_items, unsigned int* __restrict__ cursor, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
+implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitParams P, int total_items,
+                Control* __restrict__ ctl, const int* __restrict__ queue, int cap,
+                const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
     __shared__ Sample Ssh[THREADS / 32];
+    __shared__ __align__(16) float tiles[THREADS / 32][kRedFloats];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& S = Ssh[warp];
-    pdl_wait();                                           // prep_kernel's Samples, order and cursor
-    pdl_trigger();                                        // finalize_kernel may get resident (it waits for us)
     // Persistent warps pull work items from a global cursor: item cost varies a lot with the culled z range, and a
     // static assignment left the SMs idle at the tail.  The next item and its Sample are fetched while the current
     // item is processed.  No block-level barrier anywhere.
-    int item = first_item();
+    unsigned int n_items = 0;
 #ifdef SQ_TIMELINE
     const unsigned long long t_begin = gtime();
-    unsigned long long n_items = 0, t_last_fetch = t_begin;
+    unsigned long long t_last_fetch = t_begin;
 #endif
-    SampleFetch pre;
-    if (item < total_items) pre.fetch(samples + __ldg(order + (L.rows_shift >= 0 ? item >> L.rows_shift : item / L.rows_per_sample)), lane);
-    while (item < total_items) {
+    WorkPipe wp;
+    wp.start(ctl, queue, cap, total_items, lane);
+    {
+        SampleFetch pre;
+        if (wp.item >= 0) pre.fetch(samples + L.sample_of(wp.item), lane);
+        while (wp.item >= 0) {
 #ifdef SQ_TIMELINE
-        ++n_items; t_last_fetch = gtime();
+            t_last_fetch = gtime();
 #endif
-        int b, chunk;
-        L.split(item, b, chunk);
-        b = __ldg(order + b);                              // position in the processing order -> sample
-        pre.commit(&S, lane);
-        int upcoming = total_items;
+            int b, chunk;
+            L.split(wp.item, b, chunk);
+            pre.commit(&S, lane);
 
-        Acc acc;
-        acc_zero(acc);
-        ColIter it;
-        it.init(L, chunk, lane);
-        for (int k = 0; k < L.cpt; ++k, it.next(L)) {
-            if (k == L.cpt - 1) {
-                // Claim the next item (and start loading its Sample) only now: a warp that reserved its next item
-                // at the start of a long one kept that work from idle warps during the end-game.
-                upcoming = next_item(cursor, lane);
-                if (upcoming < total_items)
-                    pre.fetch(samples + __ldg(order + (L.rows_shift >= 0 ? upcoming >> L.rows_shift : upcoming / L.rows_per_sample)), lane);
-            }
-            const int ia = it.ia, ib = it.ib;
-            const bool valid = it.valid(L);
-            const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
-            float tv = 0.f;                                // issued now, needed after the z walk
-            if (valid && target) tv = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
-            float bh[3], bl[3], cg[11], dxy[2];
-            column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
-            int c_lo, c_hi;
-            column_range(S, g, P.bound, bh, c_lo, c_hi);
-            if (!valid) { c_lo = 0; c_hi = -1; }           // masked lanes do not widen the warp's range
-            warp_range(g.n, c_lo, c_hi);
-            const float depth = implicit_column<BWD>(S, g, P, bh, bl, c_lo, c_hi, cg);
-            if (valid) {
-                if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
-                if (target) {
-                    const float diff = depth - tv;
-                    acc.loss += fabsf(diff);
-                    if (BWD) {
-                        const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                        implicit_fold(acc, cg, w, dxy[0], dxy[1]);
+            Acc acc;
+            acc_zero(acc);
+            ColIter it;
+            it.init(L, chunk, lane);
+            for (int k = 0; k < L.cpt; ++k, it.next(L)) {
+                if (k == L.cpt - 1 && wp.claim(lane)) pre.fetch(samples + L.sample_of(wp.next), lane);
+                const int ia = it.ia, ib = it.ib;
+                const bool valid = it.valid(L);
+                const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
+                float tv = 0.f;                                // issued now, needed after the z walk
+                if (valid && target) tv = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
+                float bh[3], bl[3], cg[11], dxy[2];
+                column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
+                int c_lo, c_hi;
+                column_range(S, g, P.bound, bh, c_lo, c_hi);
+                if (!valid) { c_lo = 0; c_hi = -1; }           // masked lanes do not widen the warp's range
+                warp_range(g.n, c_lo, c_hi);
+                float depth;
+#ifndef SQ_FIXHOIST
+                depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
+#else
+                if (__any_sync(0xffffffffu, column_zero_possible(S, bh)))
+                    depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
+                else
+                    depth = implicit_column<BWD, false>(S, g, P, bh, bl, c_lo, c_hi, cg);
+#endif
+                if (valid) {
+                    if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
+                    if (target) {
+                        const float diff = depth - tv;
+                        acc.loss += fabsf(diff);
+                        if (BWD) {
+                            const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                            implicit_fold(acc, cg, w, dxy[0], dxy[1]);
+                        }
                     }
                 }
             }
+            if (target) warp_reduce_store(acc, tiles[warp], partials + ((size_t)b * L.rows_per_sample + chunk) * kAccN, acc.loss != 0.f);   // zero loss => zero gradient
+            ++n_items;
+            wp.rotate();
         }
-        if (target) warp_reduce_store(acc, partials + ((size_t)b * L.rows_per_sample + chunk) * kAccN, acc.loss != 0.f);   // zero loss => zero gradient
-        item = upcoming;
     }
+    retire(ctl, n_items, (unsigned int)total_items, lane);
 #ifdef SQ_TIMELINE
     if (BWD && lane == 0) {
-        const int w = first_item();
-        if (w < 8192) { g_timeline[3 * w] = t_begin; g_timeline[3 * w + 1] = gtime(); g_timeline[3 * w + 2] = (n_items << 40) | (t_last_fetch - t_begin); }
+        const int w = first_position();
+        if (w < 8192) { g_timeline[3 * w] = t_begin; g_timeline[3 * w + 1] = gtime(); g_timeline[3 * w + 2] = ((unsigned long long)n_items << 40) | (t_last_fetch - t_begin); }
     }
 #endif
 }
@@ -432,110 +577,116 @@ implicit_kernel(const Sample* __restrict__ samples, const int* __restrict__ orde
 template <bool BWD>
 __global__ void __launch_bounds__(SQ_EXP_THREADS, SQ_EXP_MINB)
 explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, float kl,
-                float bound, int total_items, unsigned int* __restrict__ cursor, float* __restrict__ partials) {
+                float bound, int total_items, Control* __restrict__ ctl, const int* __restrict__ queue, int cap,
+                float* __restrict__ partials) {
     __shared__ Sample Tsh[SQ_EXP_THREADS / 32], Psh[SQ_EXP_THREADS / 32];
+    __shared__ __align__(16) float tiles[SQ_EXP_THREADS / 32][kRedFloats];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& St = Tsh[warp];
     Sample& Sp = Psh[warp];
-    int item = first_item();
-    SampleFetch pre_t, pre_p;
-    if (item < total_items) { const int b0 = L.rows_shift >= 0 ? item >> L.rows_shift : item / L.rows_per_sample; pre_t.fetch(tru + b0, lane); pre_p.fetch(pred + b0, lane); }
-    while (item < total_items) {
-        int b, chunk;
-        L.split(item, b, chunk);
-        pre_t.commit(&St, lane);
-        pre_p.commit(&Sp, lane);
-        const int upcoming = next_item(cursor, lane);
-        if (upcoming < total_items) {
-            const int b1 = L.rows_shift >= 0 ? upcoming >> L.rows_shift : upcoming / L.rows_per_sample;
-            pre_t.fetch(tru + b1, lane);
-            pre_p.fetch(pred + b1, lane);
-        }
-        Acc acc;
-        acc_zero(acc);
-        ColIter it;
-        it.init(L, chunk, lane);
-        for (int k = 0; k < L.cpt; ++k, it.next(L)) {
-            const bool valid = it.valid(L);
-            const int ia = valid ? it.ia : 0, ib = valid ? it.ib : 0;
-            float bht[3], blt[3], bhp[3], blp[3];
-            float dxy[2];
-            column_base(St, g, ia, ib, bht, blt);
-            column_base(Sp, g, ia, ib, bhp, blp, dxy);
-            Range rt, rp;
-            column_range(St, g, bound, bht, rt.lo, rt.hi);
-            column_range(Sp, g, bound, bhp, rp.lo, rp.hi);
-            if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }      // masked lanes do not widen the warp's range
-            warp_range(g.n, rt.lo, rt.hi);
-            warp_range(g.n, rp.lo, rp.hi);
-            Acc col;
-            acc_zero(col);
-            const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, rt, rp, dxy[0], dxy[1], col);
-            if (valid) {
-                acc.loss += sq;
-                if (BWD) {
+    unsigned int n_items = 0;
+    WorkPipe wp;
+    wp.start(ctl, queue, cap, total_items, lane);
+    {
+        SampleFetch pre_t, pre_p;
+        if (wp.item >= 0) { pre_t.fetch(tru + L.sample_of(wp.item), lane); pre_p.fetch(pred + L.sample_of(wp.item), lane); }
+        while (wp.item >= 0) {
+            const int item = wp.item;
+            int b, chunk;
+            L.split(item, b, chunk);
+            pre_t.commit(&St, lane);
+            pre_p.commit(&Sp, lane);
+            if (wp.claim(lane)) { pre_t.fetch(tru + L.sample_of(wp.next), lane); pre_p.fetch(pred + L.sample_of(wp.next), lane); }
+            Acc acc;
+            acc_zero(acc);
+            ColIter it;
+            it.init(L, chunk, lane);
+            for (int k = 0; k < L.cpt; ++k, it.next(L)) {
+                const bool valid = it.valid(L);
+                const int ia = valid ? it.ia : 0, ib = valid ? it.ib : 0;
+                float bht[3], blt[3], bhp[3], blp[3];
+                float dxy[2];
+                column_base(St, g, ia, ib, bht, blt);
+                column_base(Sp, g, ia, ib, bhp, blp, dxy);
+                Range rt, rp;
+                column_range(St, g, bound, bht, rt.lo, rt.hi);
+                column_range(Sp, g, bound, bhp, rp.lo, rp.hi);
+                if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }      // masked lanes do not widen the warp's range
+                warp_range(g.n, rt.lo, rt.hi);
+                warp_range(g.n, rp.lo, rp.hi);
+                Acc col;
+                acc_zero(col);
+                const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, rt, rp, dxy[0], dxy[1], col);
+                if (valid) {
+                    acc.loss += sq;
+                    if (BWD) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) { acc.gs[i] += col.gs[i]; acc.wa[i] += col.wa[i]; }
+                        for (int i = 0; i < 3; ++i) { acc.gs[i] += col.gs[i]; acc.wa[i] += col.wa[i]; }
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) acc.gm[i] += col.gm[i];
-                    acc.ge[0] += col.ge[0]; acc.ge[1] += col.ge[1];
+                        for (int i = 0; i < 9; ++i) acc.gm[i] += col.gm[i];
+                        acc.ge[0] += col.ge[0]; acc.ge[1] += col.ge[1];
+                    }
                 }
             }
+            warp_reduce_store(acc, tiles[warp], partials + (size_t)item * kAccN, acc.loss != 0.f);
+            ++n_items;
+            wp.rotate();
         }
-        warp_reduce_store(acc, partials + (size_t)item * kAccN, acc.loss != 0.f);
-        item = upcoming;
     }
+    retire(ctl, n_items, (unsigned int)total_items, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ IoU
 __global__ void __launch_bounds__(SQ_IOU_THREADS, SQ_IOU_MINB)
 iou_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, int total_items,
-           unsigned int* __restrict__ cursor, unsigned long long* __restrict__ counts) {
+           Control* __restrict__ ctl, const int* __restrict__ queue, int cap, unsigned long long* __restrict__ counts) {
     __shared__ Sample Tsh[SQ_IOU_THREADS / 32], Psh[SQ_IOU_THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& St = Tsh[warp];
     Sample& Sp = Psh[warp];
-    int item = first_item();
-    SampleFetch pre_t, pre_p;
-    if (item < total_items) { const int b0 = L.rows_shift >= 0 ? item >> L.rows_shift : item / L.rows_per_sample; pre_t.fetch(tru + b0, lane); pre_p.fetch(pred + b0, lane); }
-    while (item < total_items) {
-        int b, chunk;
-        L.split(item, b, chunk);
-        pre_t.commit(&St, lane);
-        pre_p.commit(&Sp, lane);
-        const int upcoming = next_item(cursor, lane);
-        if (upcoming < total_items) {
-            const int b1 = L.rows_shift >= 0 ? upcoming >> L.rows_shift : upcoming / L.rows_per_sample;
-            pre_t.fetch(tru + b1, lane);
-            pre_p.fetch(pred + b1, lane);
+    unsigned int n_items = 0;
+    WorkPipe wp;
+    wp.start(ctl, queue, cap, total_items, lane);
+    {
+        SampleFetch pre_t, pre_p;
+        if (wp.item >= 0) { pre_t.fetch(tru + L.sample_of(wp.item), lane); pre_p.fetch(pred + L.sample_of(wp.item), lane); }
+        while (wp.item >= 0) {
+            const int item = wp.item;
+            int b, chunk;
+            L.split(item, b, chunk);
+            pre_t.commit(&St, lane);
+            pre_p.commit(&Sp, lane);
+            if (wp.claim(lane)) { pre_t.fetch(tru + L.sample_of(wp.next), lane); pre_p.fetch(pred + L.sample_of(wp.next), lane); }
+            unsigned inter = 0, uni = 0;
+            ColIter it;
+            it.init(L, chunk, lane);
+            for (int k = 0; k < L.cpt; ++k, it.next(L)) {
+                const bool valid = it.valid(L);
+                const int ia = valid ? it.ia : 0, ib = valid ? it.ib : 0;
+                float bht[3], blt[3], bhp[3], blp[3];
+                column_base(St, g, ia, ib, bht, blt);
+                column_base(Sp, g, ia, ib, bhp, blp);
+                Range rt, rp;
+                column_range(St, g, kIoUBound, bht, rt.lo, rt.hi);
+                column_range(Sp, g, kIoUBound, bhp, rp.lo, rp.hi);
+                if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }
+                warp_range(g.n, rt.lo, rt.hi);
+                warp_range(g.n, rp.lo, rp.hi);
+                unsigned i = 0, u = 0;
+                iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
+                if (valid) { inter += i; uni += u; }
+            }
+            inter = __reduce_add_sync(0xffffffffu, inter);
+            uni = __reduce_add_sync(0xffffffffu, uni);
+            if (lane == 0 && (inter | uni)) {                 // integer atomics: order-independent, exact
+                atomicAdd(counts + 2 * b, (unsigned long long)inter);
+                atomicAdd(counts + 2 * b + 1, (unsigned long long)uni);
+            }
+            ++n_items;
+            wp.rotate();
         }
-        unsigned inter = 0, uni = 0;
-        ColIter it;
-        it.init(L, chunk, lane);
-        for (int k = 0; k < L.cpt; ++k, it.next(L)) {
-            const bool valid = it.valid(L);
-            const int ia = valid ? it.ia : 0, ib = valid ? it.ib : 0;
-            float bht[3], blt[3], bhp[3], blp[3];
-            column_base(St, g, ia, ib, bht, blt);
-            column_base(Sp, g, ia, ib, bhp, blp);
-            Range rt, rp;
-            column_range(St, g, kIoUBound, bht, rt.lo, rt.hi);
-            column_range(Sp, g, kIoUBound, bhp, rp.lo, rp.hi);
-            if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }
-            warp_range(g.n, rt.lo, rt.hi);
-            warp_range(g.n, rp.lo, rp.hi);
-            unsigned i = 0, u = 0;
-            iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
-            if (valid) { inter += i; uni += u; }
-        }
-        inter = __reduce_add_sync(0xffffffffu, inter);
-        uni = __reduce_add_sync(0xffffffffu, uni);
-        if (lane == 0) {                                  // integer atomics: order-independent, exact
-            atomicAdd(counts + 2 * b, (unsigned long long)inter);
-            atomicAdd(counts + 2 * b + 1, (unsigned long long)uni);
-        }
-        item = upcoming;
     }
+    retire(ctl, n_items, (unsigned int)total_items, lane);
 }
 
 __global__ void iou_export_kernel(const unsigned long long* counts, int batch, long long* inter, long long* uni) {
@@ -582,7 +733,6 @@ finalize_kernel(const Sample* __restrict__ samples, Grid g, int batch, int items
     const int b = blockIdx.x, lane = threadIdx.x;
     __shared__ double acc[kAccN];
     __shared__ double part[32][kAccN + 1];
-    pdl_wait();                                           // partial rows of the column kernel
     {   // lane l sums rows l, l+32, ... (independent loads in flight), then a fixed-order sum over the 32 lanes
         double s[kAccN];
 #pragma unroll
@@ -697,18 +847,6 @@ int check_scratch(int batch, int n, void* scratch, size_t bytes, Scratch* s) {
     return 0;
 }
 
-// kernel launch that may overlap the tail of the preceding kernel in the stream (the kernel must call pdl_wait())
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 // blocks of a persistent column kernel: enough to fill every SM at the kernel's occupancy, no more than the work
 int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
     static int sms[64] = {0};
@@ -725,16 +863,24 @@ int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
     return need < fill ? need : fill;
 }
 
-int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid& g, Sample* out,
-                unsigned int* ticket, unsigned long long* counts, cudaStream_t st, int* order = nullptr) {
+int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid& g, Sample* out, Control* ctl,
+                cudaStream_t st) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
-    const int threads = (batch + 31) / 32 * 32;
-    if (order && batch <= 256)
-        prep_kernel<256><<<1, threads, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
-    else if (order && batch <= kPrepSortMax)
-        prep_kernel<kPrepSortMax><<<1, threads, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
+    prep_kernel<<<(batch + 3) / 4, 128, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ctl);
+    return (int)cudaGetLastError();
+}
+
+// plan kernel of a column-kernel call: Samples, per-sample counters, cost-class queues
+int launch_plan(const void* params_a, const void* params_b, int dtype, int batch, bool clamp, const Grid& g,
+                const Layout& L, float bound, const Scratch& s, unsigned long long* counts, cudaStream_t st) {
+    if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
+    int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
+    if (params_b)
+        plan_kernel<2><<<batch, kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, g, L, bound, s.tru, s.pred,
+                                                       s.ctl, counts, queue, s.queue_cap);
     else
-        prep_kernel<128><<<(batch + 127) / 128, 128, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ticket, counts, order);
+        plan_kernel<1><<<batch, kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, g, L, bound, s.pred, nullptr,
+                                                       s.ctl, counts, queue, s.queue_cap);
     return (int)cudaGetLastError();
 }
 
@@ -767,6 +913,11 @@ size_t sq_scratch_bytes(int batch, int n) {
     return scratch_layout(batch, n, nullptr, nullptr);
 }
 
+int sq_scratch_init(void* scratch, size_t scratch_bytes, sq_stream_t stream) {
+    if (!scratch || scratch_bytes < sizeof(Control)) return (int)cudaErrorInvalidValue;
+    return (int)cudaMemsetAsync(scratch, 0, sizeof(Control), static_cast<cudaStream_t>(stream));
+}
+
 int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double step, double z0,
                      const float* target, long long target_stride_b, const int* row_off, const int* col_off,
                      float tau, float sharpness, double* loss_out, double* per_sample, void* grad_pred,
@@ -780,49 +931,30 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, grad_pred ? SQ_IMPB_CPT : SQ_IMPF_CPT);
     const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, cull_bound(sharpness * kLog2e)};
-    rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st, s.order);
+    rc = launch_plan(pred, nullptr, pred_dtype, batch, true, g, L, P.bound, s, nullptr, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
-    // Programmatic dependent launch measured 4.6 us SLOWER per step inside CUDA-graph replay on B200 (resident
-    // waiting blocks delay prep's tail; profiles/tune_r01.txt), so it is compiled in only with -DSQ_PDL.
-#ifdef SQ_PDL
-    const bool pdl = (t_ev_before == nullptr && t_ev_after == nullptr);   // an event record in between breaks the chain
-#else
-    const bool pdl = false;
-#endif
+    const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
     {
         ColumnKernelTimer timer(st);
         if (grad_pred) {
             const int blocks = persistent_blocks(items, SQ_IMPB_THREADS / 32, SQ_IMPB_MINB);
-            if (pdl)
-                SQ_TRY(launch_pdl(implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB>, blocks, SQ_IMPB_THREADS, st,
-                                  s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off,
-                                  s.partials, depth_out));
-            else
-                implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB><<<blocks, SQ_IMPB_THREADS, 0, st>>>(
-                    s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+            implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB><<<blocks, SQ_IMPB_THREADS, 0, st>>>(
+                s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off, s.partials,
+                depth_out);
         } else {
             const int blocks = persistent_blocks(items, SQ_IMPF_THREADS / 32, SQ_IMPF_MINB);
-            if (pdl)
-                SQ_TRY(launch_pdl(implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB>, blocks, SQ_IMPF_THREADS, st,
-                                  s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off,
-                                  s.partials, depth_out));
-            else
-                implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB><<<blocks, SQ_IMPF_THREADS, 0, st>>>(
-                    s.pred, s.order, g, L, P, items, s.ticket + 1, target, target_stride_b, row_off, col_off, s.partials, depth_out);
+            implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB><<<blocks, SQ_IMPF_THREADS, 0, st>>>(
+                s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off, s.partials,
+                depth_out);
         }
     }
     SQ_TRY(cudaGetLastError());
     if (target) {
         const double nn = (double)n * n;
-        const double gscale = -(double)sharpness * (double)tau / (nn * n * (double)batch);
-        if (pdl)
-            SQ_TRY(launch_pdl(finalize_kernel<FIN_IMPLICIT>, batch, 32, st, s.pred, g, batch, L.rows_per_sample, s.partials,
-                              1.0 / nn, gscale, pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, s.ticket));
-        else
-            finalize_kernel<FIN_IMPLICIT><<<batch, 32, 0, st>>>(s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn,
-                                                               gscale, pred_dtype, grad_pred, s.per_sample, per_sample,
-                                                               loss_out, s.ticket);
+        finalize_kernel<FIN_IMPLICIT><<<batch, 32, 0, st>>>(
+            s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn, -(double)sharpness * (double)tau / (nn * n * (double)batch),
+            pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket);
         SQ_TRY(cudaGetLastError());
     }
     return 0;
@@ -834,27 +966,27 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     Scratch s;
     int rc = check_scratch(batch, n, scratch, scratch_bytes, &s);
     if (rc) return rc;
+    if (!true_params || !pred) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, SQ_EXP_CPT);
-    rc = launch_prep(true_params, params_dtype, batch, true, g, s.tru, nullptr, nullptr, st);
-    if (rc) return rc;
-    rc = launch_prep(pred, params_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
+    const float kl = sharpness * kLog2e, bound = cull_bound_bits(kl, 24.0f);
+    rc = launch_plan(true_params, pred, params_dtype, batch, true, g, L, bound, s, nullptr, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
+    const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
     const int blocks = persistent_blocks(items, SQ_EXP_THREADS / 32, SQ_EXP_MINB);
-    const float kl = sharpness * kLog2e, bound = cull_bound_bits(kl, 24.0f);
     {
         ColumnKernelTimer timer(st);
-        if (grad_pred) explicit_kernel<true><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.ticket + 1, s.partials);
-        else explicit_kernel<false><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.ticket + 1, s.partials);
+        if (grad_pred) explicit_kernel<true><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.ctl, queue, s.queue_cap, s.partials);
+        else explicit_kernel<false><<<blocks, SQ_EXP_THREADS, 0, st>>>(s.tru, s.pred, g, L, kl, bound, items, s.ctl, queue, s.queue_cap, s.partials);
     }
     SQ_TRY(cudaGetLastError());
     const double n3 = (double)n * n * n;
     finalize_kernel<FIN_EXPLICIT><<<batch, 32, 0, st>>>(
         s.pred, g, batch, L.rows_per_sample, s.partials, (double)mult / n3,
         2.0 * (double)sharpness * (double)mult / (n3 * (double)batch), params_dtype, grad_pred, s.per_sample,
-        per_sample, loss_out, s.ticket);
+        per_sample, loss_out, &s.ctl->ticket);
     SQ_TRY(cudaGetLastError());
     return 0;
 }
@@ -865,19 +997,18 @@ int sq_iou_counts(const void* true_params, const void* pred, int params_dtype, i
     Scratch s;
     int rc = check_scratch(batch, n, scratch, scratch_bytes, &s);
     if (rc) return rc;
-    if (!inter || !uni) return (int)cudaErrorInvalidValue;
+    if (!true_params || !pred || !inter || !uni) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, SQ_IOU_CPT);
-    rc = launch_prep(true_params, params_dtype, batch, false, g, s.tru, nullptr, nullptr, st);
-    if (rc) return rc;
-    rc = launch_prep(pred, params_dtype, batch, false, g, s.pred, s.ticket, s.counts, st);
+    rc = launch_plan(true_params, pred, params_dtype, batch, false, g, L, kIoUBound, s, s.counts, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
+    const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
     const int blocks = persistent_blocks(items, SQ_IOU_THREADS / 32, SQ_IOU_MINB);
     {
         ColumnKernelTimer timer(st);
-        iou_kernel<<<blocks, SQ_IOU_THREADS, 0, st>>>(s.tru, s.pred, g, L, items, s.ticket + 1, s.counts);
+        iou_kernel<<<blocks, SQ_IOU_THREADS, 0, st>>>(s.tru, s.pred, g, L, items, s.ctl, queue, s.queue_cap, s.counts);
     }
     SQ_TRY(cudaGetLastError());
     iou_export_kernel<<<(batch + 127) / 128, 128, 0, st>>>(s.counts, batch, inter, uni);
@@ -894,7 +1025,7 @@ int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_siz
     if (!target || !row_off || !col_off) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g = make_grid(2, 1.0, 0.0);     // the point list carries its own coordinates; the grid is unused
-    rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ticket, nullptr, st);
+    rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ctl, st);
     if (rc) return rc;
     const int R = render_size;
     const int ips = (R * R + kThreads - 1) / kThreads;
@@ -902,7 +1033,7 @@ int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_siz
     else lsq_kernel<false><<<batch * ips, kThreads, 0, st>>>(s.pred, R, ips, target, target_stride_b, row_off, col_off, s.partials);
     SQ_TRY(cudaGetLastError());
     finalize_kernel<FIN_LSQ><<<batch, 32, 0, st>>>(s.pred, g, batch, ips, s.partials, 1.0, 2.0 / (double)batch,
-                                                   pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, s.ticket);
+                                                   pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket);
     SQ_TRY(cudaGetLastError());
     return 0;
 }
@@ -915,7 +1046,7 @@ int sq_field(const void* params, int params_dtype, int batch, int n, double step
     if (!out || (mode != 0 && mode != 1)) return (int)cudaErrorInvalidValue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g = make_grid(n, step, z0);
-    rc = launch_prep(params, params_dtype, batch, mode == 1, g, s.pred, nullptr, nullptr, st);
+    rc = launch_prep(params, params_dtype, batch, mode == 1, g, s.pred, nullptr, st);
     if (rc) return rc;
     const size_t total = (size_t)batch * n * n * n;
     field_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s.pred, g, batch, mode, sharpness * kLog2e, out);
@@ -927,7 +1058,8 @@ int sq_field(const void* params, int params_dtype, int batch, int n, double step
 struct sq_ctx {
     int device;
     cudaStream_t stream;
-    char* dev; size_t dev_bytes;          // one device arena, carved per call
+    char* dev; size_t dev_bytes;          // one device arena, carved per call; the scratch (with its Control block,
+                                          // zeroed when the arena is allocated) always sits at its start
     char* pin; size_t pin_bytes;          // pinned staging for results
 };
 
@@ -937,6 +1069,7 @@ static int ctx_reserve(sq_ctx* c, size_t dev_bytes, size_t pin_bytes) {
         c->dev = nullptr; c->dev_bytes = 0;
         SQ_TRY(cudaMalloc(&c->dev, dev_bytes));
         c->dev_bytes = dev_bytes;
+        SQ_TRY(cudaMemsetAsync(c->dev, 0, sizeof(Control), c->stream));
     }
     if (pin_bytes > c->pin_bytes) {
         if (c->pin) SQ_TRY(cudaFreeHost(c->pin));
@@ -995,15 +1128,15 @@ int sq_implicit_loss_host(sq_ctx* c, const float* pred_host, int batch, int rend
     const size_t b_off = align_up(sizeof(int) * 4 * (size_t)R, 256);
     const size_t b_out = align_up(sizeof(double) + sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_scr = sq_scratch_bytes(batch, R);
-    int rc = ctx_reserve(c, b_pred + b_img + b_off + b_out + b_scr, b_off + b_out);
+    int rc = ctx_reserve(c, align_up(b_scr, 256) + b_pred + b_img + b_off + b_out, b_off + b_out);
     if (rc) return rc;
     char* d = c->dev;
+    void* d_scr = d; d += align_up(b_scr, 256);
     float* d_pred = reinterpret_cast<float*>(d); d += b_pred;
     float* d_img = reinterpret_cast<float*>(d); d += b_img;
     int* d_off = reinterpret_cast<int*>(d); d += b_off;
     double* d_loss = reinterpret_cast<double*>(d);
     float* d_grad = reinterpret_cast<float*>(d + sizeof(double)); d += b_out;
-    void* d_scr = d;
     int* h_off = reinterpret_cast<int*>(c->pin);
     char* h_out = c->pin + b_off;
     nearest_offsets(height, R, width, h_off);
@@ -1047,9 +1180,10 @@ int sq_explicit_loss_host(sq_ctx* c, const float* true_host, const float* pred_h
     const size_t b_par = align_up(sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_out = align_up(sizeof(double) + sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_scr = sq_scratch_bytes(batch, n);
-    int rc = ctx_reserve(c, 2 * b_par + b_out + b_scr, b_out);
+    int rc = ctx_reserve(c, align_up(b_scr, 256) + 2 * b_par + b_out, b_out);
     if (rc) return rc;
     char* d = c->dev;
+    void* d_scr = d; d += align_up(b_scr, 256);
     float* d_true = reinterpret_cast<float*>(d); d += b_par;
     float* d_pred = reinterpret_cast<float*>(d); d += b_par;
     double* d_loss = reinterpret_cast<double*>(d);
@@ -1057,7 +1191,7 @@ int sq_explicit_loss_host(sq_ctx* c, const float* true_host, const float* pred_h
     SQ_TRY(cudaMemcpyAsync(d_true, true_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
     SQ_TRY(cudaMemcpyAsync(d_pred, pred_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
     rc = sq_explicit_loss(d_true, d_pred, SQ_F32, batch, n, step, 1e-4, 5.0f, 100.0f, d_loss, nullptr,
-                          grad_host ? d_grad : nullptr, d, b_scr, c->stream);
+                          grad_host ? d_grad : nullptr, d_scr, b_scr, c->stream);
     if (rc) return rc;
     const size_t out_bytes = sizeof(double) + (grad_host ? sizeof(float) * 12 * (size_t)batch : 0);
     SQ_TRY(cudaMemcpyAsync(c->pin, d_loss, out_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -1076,15 +1210,16 @@ int sq_iou_counts_host(sq_ctx* c, const float* true_host, const float* pred_host
     const size_t b_par = align_up(sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_out = align_up(sizeof(long long) * 2 * (size_t)batch, 256);
     const size_t b_scr = sq_scratch_bytes(batch, n);
-    int rc = ctx_reserve(c, 2 * b_par + b_out + b_scr, b_out);
+    int rc = ctx_reserve(c, align_up(b_scr, 256) + 2 * b_par + b_out, b_out);
     if (rc) return rc;
     char* d = c->dev;
+    void* d_scr = d; d += align_up(b_scr, 256);
     float* d_true = reinterpret_cast<float*>(d); d += b_par;
     float* d_pred = reinterpret_cast<float*>(d); d += b_par;
     long long* d_cnt = reinterpret_cast<long long*>(d); d += b_out;
     SQ_TRY(cudaMemcpyAsync(d_true, true_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
     SQ_TRY(cudaMemcpyAsync(d_pred, pred_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
-    rc = sq_iou_counts(d_true, d_pred, SQ_F32, batch, n, 1.0 / (double)(n - 1), 0.0, d_cnt, d_cnt + batch, d, b_scr, c->stream);
+    rc = sq_iou_counts(d_true, d_pred, SQ_F32, batch, n, 1.0 / (double)(n - 1), 0.0, d_cnt, d_cnt + batch, d_scr, b_scr, c->stream);
     if (rc) return rc;
     SQ_TRY(cudaMemcpyAsync(c->pin, d_cnt, sizeof(long long) * 2 * (size_t)batch, cudaMemcpyDeviceToHost, c->stream));
     SQ_TRY(cudaStreamSynchronize(c->stream));

@@ -37,6 +37,9 @@ def _get_scratch(device: torch.device, batch: int, n: int) -> torch.Tensor:
     buf = _scratch.get(key)
     if buf is None or buf.numel() < need:
         buf = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):      # zero the control block once; every call leaves it zero (include/sqloss.h)
+            _lib.check(_lib.lib().sq_scratch_init(ctypes.c_void_p(buf.data_ptr()), buf.numel(), _stream(device)),
+                       "sq_scratch_init")
         _scratch[key] = buf
     return buf
 

@@ -37,7 +37,7 @@ true, pred = true.to(dev), pred.to(dev)
 img = S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(true).unsqueeze(1).contiguous()
 row_off, col_off = nearest_offsets(256, 256, R, dev)
 loss = torch.empty((), dtype=torch.float64, device=dev); grad = torch.empty_like(pred)
-nb = h.sq_scratch_bytes(B, R); scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+nb = h.sq_scratch_bytes(B, R); scratch = torch.zeros(nb, dtype=torch.uint8, device=dev)
 P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
 for _ in range(5):
     rc = h.sq_implicit_loss(P(pred), 0, B, R, 1.0 / (R - 1), 1e-4, P(img), 256 * 256, P(row_off), P(col_off), 1.5, 260.0,

@@ -83,7 +83,7 @@ def main():
     for defs in (sys.argv[1:] or [""]):
         h, regs = build(defs)
         nb = h.sq_scratch_bytes(B, R + 1)
-        scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+        scratch = torch.zeros(nb, dtype=torch.uint8, device=dev)
         def imp(g):
             rc = h.sq_implicit_loss(P(pred), 0, B, R, 1.0 / (R - 1), 1e-4, P(img), 256 * 256, P(row_off), P(col_off), 1.5, 260.0,
                                     P(loss), None, P(g), None, P(scratch), nb, st)
