@@ -90,15 +90,41 @@ struct Grid {
     double step;    // spacing
     double z0;      // coordinate of index 0 (1e-4 with the zero fix-up, else 0)
     float inv_n;    // 1 / n
+    float stepf, z0f;
 };
-SQ_HD Grid make_grid(int n, double step, double z0) { Grid g; g.n = n; g.step = step; g.z0 = z0; g.inv_n = 1.0f / (float)n; return g; }
+SQ_HD Grid make_grid(int n, double step, double z0) {
+    Grid g; g.n = n; g.step = step; g.z0 = z0; g.inv_n = 1.0f / (float)n; g.stepf = (float)step; g.z0f = (float)z0; return g;
+}
 SQ_HD double grid_coord(const Grid& g, int i) { return i == 0 ? g.z0 : (double)i * g.step; }
+SQ_HD float grid_coord_f32(const Grid& g, int i) { return i == 0 ? g.z0f : (float)i * g.stepf; }
+
+// double <-> float conversions without the denormal fix-up code that -ftz=true attaches to a plain cast (a DSETP and a
+// predicated FMUL per conversion; the values converted here are never denormal)
+SQ_HD float d2f(double v) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("cvt.rn.f32.f64 %0, %1;" : "=f"(y) : "d"(v)); return y;
+#else
+    return (float)v;
+#endif
+}
+SQ_HD double f2d(float v) {
+#if defined(__CUDA_ARCH__)
+    double y; asm("cvt.f64.f32 %0, %1;" : "=d"(y) : "f"(v)); return y;
+#else
+    return (double)v;
+#endif
+}
 
 // ---------------------------------------------------------------- per-sample constants
+// `Sample` is what the column kernels keep per warp in shared memory; `SampleFull` (what prep writes to HBM) appends
+// the fields only finalize and the fp64 IoU tie-break read.
 struct Sample {
     // fp64 geometry: rows of M pre-divided by a_i, so s = Ms (g - t)
     double Ms[9];
     double t[3];
+    // fp32 copy of the affine map (gx, gy) -> s at plane index 0, for culling and cost estimates (column_base_f32)
+    float mf[6];              // Ms[i][0], Ms[i][1]
+    float of[3];              // -(Ms t)_i
     // fp32 constants of the point loop
     float dh[3], dl[3];       // Ms[i][2] * step, split hi/lo: s_i(c) = base_i + d_i * cf(c)
     float idh[3];             // 1 / dh (+-inf when the column runs parallel to a face of the SQ's box)
@@ -108,16 +134,18 @@ struct Sample {
     // ellipsoid that contains every level set of F (column_range): w (sx^2 + sy^2) + sz^2 <= qB1 * F
     float wd[3];              // w_i * dh_i,  w = (qw, qw, 1)
     float qw, qa, qia, qB1;   // 2^(e2-1), sum w_i dh_i^2, its reciprocal, 2^(1-e1)
-    // for the finalize step
+    float pad_;
+};
+struct SampleFull : Sample {
     double M[9];              // un-scaled rotation
     double a[3], e[2], q[4];
     float mask[8];            // clamp sub-gradient masks for a(3), e(2), t(3): 1 inside or on the boundary, else 0
 };
 
-SQ_HD void split2(double v, float& hi, float& lo) { hi = (float)v; lo = (float)(v - (double)hi); }
+SQ_HD void split2(double v, float& hi, float& lo) { hi = d2f(v); lo = d2f(v - f2d(hi)); }
 
 // p: 12 raw parameters [a1 a2 a3 e1 e2 t1 t2 t3 qx qy qz qw].  clamp per classes.py:129-136 (IoU: no clamp, :398).
-SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, Sample& S) {
+SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, SampleFull& S) {
     const double lo[8] = {0.05, 0.05, 0.05, 0.1, 0.1, 0.0, 0.0, 0.0};
     double v[8];
     for (int i = 0; i < 8; ++i) {
@@ -147,7 +175,10 @@ SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, Sample& S) {
         for (int j = 0; j < 3; ++j) S.Ms[3 * i + j] = S.M[3 * i + j] * ia;
         split2(S.Ms[3 * i + 2] * g.step, S.dh[i], S.dl[i]);
         S.idh[i] = 1.0f / S.dh[i];
+        S.mf[2 * i] = (float)S.Ms[3 * i]; S.mf[2 * i + 1] = (float)S.Ms[3 * i + 1];
+        S.of[i] = (float)-(S.Ms[3 * i] * S.t[0] + S.Ms[3 * i + 1] * S.t[1] + S.Ms[3 * i + 2] * S.t[2]);
     }
+    S.pad_ = 0.f;
     {
         // Power-mean inequality, for exponents 2/e >= 2:  F >= 2^(e1-1) (2^(e2-1) (sx^2 + sy^2) + sz^2); the factors
         // are 1 for e > 1 (unclamped IoU parameters).  Non-positive e: no bound (the reference yields inf/nan there).
@@ -173,7 +204,15 @@ SQ_HD void column_base(const Sample& S, const Grid& g, int ia, int ib, float* bh
     const double dx = grid_coord(g, ia) - S.t[0], dy = grid_coord(g, ib) - S.t[1], dz = -S.t[2];
     for (int i = 0; i < 3; ++i)
         split2(S.Ms[3 * i] * dx + S.Ms[3 * i + 1] * dy + S.Ms[3 * i + 2] * dz, bh[i], bl[i]);
-    if (dxy) { dxy[0] = (float)dx; dxy[1] = (float)dy; }      // column position relative to t (for the M gradient)
+    if (dxy) { dxy[0] = d2f(dx); dxy[1] = d2f(dy); }          // column position relative to t (for the M gradient)
+}
+
+// The same in plain fp32 (absolute error ~2e-6 for |s| <= 30): good enough to decide which planes can hold occupancy
+// (column_range has 1e-3 of slack in the bound and a plane of slack per side), and 6 FMAs instead of 40 instructions
+// of fp64 -- more than half of all warp column groups turn out empty and never need the exact base.
+SQ_HD void column_base_f32(const Sample& S, const Grid& g, int ia, int ib, float* b) {
+    const float gx = grid_coord_f32(g, ia), gy = grid_coord_f32(g, ib);
+    for (int i = 0; i < 3; ++i) b[i] = fmaf(S.mf[2 * i], gx, fmaf(S.mf[2 * i + 1], gy, S.of[i]));
 }
 
 // ---------------------------------------------------------------- forward at one point
@@ -294,7 +333,7 @@ SQ_HD void acc_zero(Acc& a) {
 //   grad wrt q    = sum_ij dM_ij/dq * grad M_ij,  M = mat(conj(q))
 // z_is_index: the z moment gm[i][2] holds sum gs_i * cf (grid index units, column kernels) instead of
 // sum gs_i * (z - t_z) (point-list kernel).
-SQ_HD void finalize_sample(const Sample& S, const Grid& g, const double* acc, double scale, bool z_is_index,
+SQ_HD void finalize_sample(const SampleFull& S, const Grid& g, const double* acc, double scale, bool z_is_index,
                            double* grad12) {
     const double* gs = acc; const double* gm = acc + 3; const double* wa = acc + 12; const double* ge = acc + 15;
     double gM[9];
@@ -424,7 +463,7 @@ struct ImplicitParams { float kl; float tl; float bound; };     // k log2(e), ta
 constexpr float kDeep = SQ_KDEEP;       // points behind 2^-kDeep of transmittance carry no gradient (S_c < n 2^-kDeep)
 
 struct ColGrad {       // two-moment accumulators of one column
-    float gs0[3], gs1[3], gz0[3], gz1[3], wa0[3], wa1[3], ge0[2], ge1[2];
+    float gs0[3], gs1[3], gz0[3], gz1[3], ge0[2], ge1[2];
 };
 
 // Returns the rendered depth.  1 - sum T / n cannot resolve depths below ~1e-7 in fp32, but the sign of
@@ -471,7 +510,6 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
                 cg.gs0[i] += b.gs[i];            cg.gs1[i] = fmaf(pp, b.gs[i], cg.gs1[i]);
                 const float gz = b.gs[i] * p.cf;
                 cg.gz0[i] += gz;                 cg.gz1[i] = fmaf(pp, gz, cg.gz1[i]);
-                cg.wa0[i] += b.wa[i];            cg.wa1[i] = fmaf(pp, b.wa[i], cg.wa1[i]);
             }
             for (int i = 0; i < 2; ++i) { cg.ge0[i] += b.ge[i]; cg.ge1[i] = fmaf(pp, b.ge[i], cg.ge1[i]); }
         }
@@ -499,7 +537,7 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
     st.psh = 0.f; st.seen = 0.f;
     ColGrad cg;
     if (BWD) {
-        for (int i = 0; i < 3; ++i) cg.gs0[i] = cg.gs1[i] = cg.gz0[i] = cg.gz1[i] = cg.wa0[i] = cg.wa1[i] = 0.f;
+        for (int i = 0; i < 3; ++i) cg.gs0[i] = cg.gs1[i] = cg.gz0[i] = cg.gz1[i] = 0.f;
         cg.ge0[0] = cg.ge0[1] = cg.ge1[0] = cg.ge1[1] = 0.f;
     }
     int c = c_hi;
@@ -527,7 +565,9 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
         for (int i = 0; i < 3; ++i) {
             colgrad11[i]     = fmaf(U, cg.gs0[i], -cg.gs1[i]);
             colgrad11[3 + i] = fmaf(U, cg.gz0[i], -cg.gz1[i]);
-            colgrad11[6 + i] = fmaf(U, cg.wa0[i], -cg.wa1[i]);
+            // the size gradient needs sum gs_i s_i, and s_i = base_i + d_i cf is affine along the column: no accumulator
+            colgrad11[6 + i] = fmaf(bh[i], colgrad11[i], fmaf(S.dh[i], colgrad11[3 + i],
+                               fmaf(bl[i], colgrad11[i], S.dl[i] * colgrad11[3 + i])));
         }
         colgrad11[9]  = fmaf(U, cg.ge0[0], -cg.ge1[0]);
         colgrad11[10] = fmaf(U, cg.ge0[1], -cg.ge1[1]);
@@ -588,7 +628,6 @@ SQ_HD void explicit_step(const Sample& St, const Sample& Sp, float kl, float cf,
             for (int i = 0; i < 3; ++i) {
                 gs[i] += b.gs[i];
                 gz[i] = fmaf(b.gs[i], cf, gz[i]);
-                acc.wa[i] += b.wa[i];
             }
             acc.ge[0] += b.ge[0];
             acc.ge[1] += b.ge[1];
@@ -619,6 +658,8 @@ SQ_HD float explicit_column(const Sample& St, const Sample& Sp, const Grid& g, f
             acc.gm[3 * i + 0] = fmaf(gs[i], dx, acc.gm[3 * i + 0]);
             acc.gm[3 * i + 1] = fmaf(gs[i], dy, acc.gm[3 * i + 1]);
             acc.gm[3 * i + 2] += gz[i];
+            // sum gs_i s_i with s_i = base_i + d_i cf (see implicit_column)
+            acc.wa[i] += fmaf(bhp[i], gs[i], fmaf(Sp.dh[i], gz[i], fmaf(blp[i], gs[i], Sp.dl[i] * gz[i])));
         }
     }
     return sq;
@@ -633,7 +674,7 @@ __host__ __device__ __noinline__
 #else
 inline
 #endif
-bool inside_exact(const Sample& S, const Grid& g, int ia, int ib, int ic) {
+bool inside_exact(const SampleFull& S, const Grid& g, int ia, int ib, int ic) {
     const double gx = grid_coord(g, ia), gy = grid_coord(g, ib), gz = grid_coord(g, ic);
     double s[3];
     for (int i = 0; i < 3; ++i) {
@@ -658,8 +699,9 @@ constexpr float kIoUMargin = 2e-4f;     // |log2 F| below which the fp32 decisio
 // beyond the margin, so it is outside without evaluating anything.
 constexpr float kIoUBound = 1.001f;
 
-SQ_HD void iou_column(const Sample& St, const Sample& Sp, const Grid& g, int ia, int ib,
-                      const float* bht, const float* blt, const float* bhp, const float* blp,
+// Ft / Fp: the full records (in HBM), read only for the fp64 tie-break
+SQ_HD void iou_column(const Sample& St, const Sample& Sp, const SampleFull* Ft, const SampleFull* Fp, const Grid& g,
+                      int ia, int ib, const float* bht, const float* blt, const float* bhp, const float* blp,
                       Range rt, Range rp, unsigned& inter, unsigned& uni) {
     const int c_hi = rt.hi > rp.hi ? rt.hi : rp.hi;
     const int c_lo = (rt.hi < rt.lo) ? rp.lo : (rp.hi < rp.lo) ? rt.lo : (rt.lo < rp.lo ? rt.lo : rp.lo);
@@ -672,14 +714,14 @@ SQ_HD void iou_column(const Sample& St, const Sample& Sp, const Grid& g, int ia,
                                        fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
                                        fmaf(cf, St.dh[2], bht[2]) + fmaf(cf, St.dl[2], blt[2]));
             it = yt <= 0.f;
-            if (!(fabsf(yt) > kIoUMargin)) it = inside_exact(St, g, ia, ib, c);      // also catches NaN
+            if (!(fabsf(yt) > kIoUMargin)) it = inside_exact(*Ft, g, ia, ib, c);     // also catches NaN
         }
         if (c >= rp.lo && c <= rp.hi) {
             const float yp = log2F(Sp, fmaf(cf, Sp.dh[0], bhp[0]) + fmaf(cf, Sp.dl[0], blp[0]),
                                        fmaf(cf, Sp.dh[1], bhp[1]) + fmaf(cf, Sp.dl[1], blp[1]),
                                        fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]));
             ip = yp <= 0.f;
-            if (!(fabsf(yp) > kIoUMargin)) ip = inside_exact(Sp, g, ia, ib, c);
+            if (!(fabsf(yp) > kIoUMargin)) ip = inside_exact(*Fp, g, ia, ib, c);
         }
         inter += (it && ip) ? 1u : 0u;
         uni += (it || ip) ? 1u : 0u;

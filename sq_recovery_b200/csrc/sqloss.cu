@@ -44,10 +44,10 @@ namespace {
 #define SQ_IMPF_CPT 1
 #endif
 #ifndef SQ_EXP_THREADS
-#define SQ_EXP_THREADS 256               // explicit fwd and fwd+bwd
+#define SQ_EXP_THREADS 128               // explicit fwd and fwd+bwd
 #endif
 #ifndef SQ_EXP_MINB
-#define SQ_EXP_MINB 2
+#define SQ_EXP_MINB 3
 #endif
 #ifndef SQ_EXP_CPT
 #define SQ_EXP_CPT 1
@@ -156,8 +156,8 @@ static_assert(sizeof(Control) == 256, "Control block is 256 bytes");
 
 struct Scratch {
     Control* ctl;
-    Sample* pred;          // [batch]
-    Sample* tru;           // [batch]
+    SampleFull* pred;      // [batch]
+    SampleFull* tru;       // [batch]
     float* partials;       // [batch * rows_per_sample][kAccN]
     double* per_sample;    // [batch]
     unsigned long long* counts;   // [batch][2] (IoU)
@@ -172,8 +172,8 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_ctl = take(sizeof(Control));          // always at offset 0
-    const size_t o_pred = take(sizeof(Sample) * (size_t)batch);
-    const size_t o_true = take(sizeof(Sample) * (size_t)batch);
+    const size_t o_pred = take(sizeof(SampleFull) * (size_t)batch);
+    const size_t o_true = take(sizeof(SampleFull) * (size_t)batch);
     // partial rows: one per warp item for the column kernels, one per 256 pixels for the point-list kernel
     size_t rows_ps = (size_t)L.rows_per_sample;
     const size_t lsq_rows = (size_t)(L.slots + kThreads - 1) / kThreads;
@@ -186,8 +186,8 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     const size_t o_queue = take(queued ? sizeof(int) * kClasses * cap : 0);
     if (s) {
         s->ctl = reinterpret_cast<Control*>(base + o_ctl);
-        s->pred = reinterpret_cast<Sample*>(base + o_pred);
-        s->tru = reinterpret_cast<Sample*>(base + o_true);
+        s->pred = reinterpret_cast<SampleFull*>(base + o_pred);
+        s->tru = reinterpret_cast<SampleFull*>(base + o_true);
         s->partials = reinterpret_cast<float*>(base + o_part);
         s->per_sample = reinterpret_cast<double*>(base + o_ps);
         s->counts = reinterpret_cast<unsigned long long*>(base + o_cnt);
@@ -198,8 +198,9 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
 }
 
 // ------------------------------------------------------------------------------------------------ prep / plan
-constexpr int kSampleWords = (int)(sizeof(Sample) / 4);
-static_assert(sizeof(Sample) % 4 == 0, "Sample must be word-copyable");
+constexpr int kSampleWords = (int)(sizeof(Sample) / 4);          // the part the column kernels keep per warp
+constexpr int kFullWords = (int)(sizeof(SampleFull) / 4);        // the record in HBM
+static_assert(sizeof(Sample) % 8 == 0 && sizeof(SampleFull) % 8 == 0, "Sample records must be word-copyable");
 
 __device__ __forceinline__ void load_params(const void* params, int dtype, int b, double* p) {
 #pragma unroll
@@ -211,8 +212,8 @@ __device__ __forceinline__ void load_params(const void* params, int dtype, int b
 // prep (point-list and field kernels): one warp per sample; lane 0 does the fp64 work into shared memory, the warp
 // copies the 328-byte record out with coalesced stores.
 __global__ void __launch_bounds__(128)
-prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample* out, Control* ctl) {
-    __shared__ Sample Ssh[4];
+prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, SampleFull* out, Control* ctl) {
+    __shared__ SampleFull Ssh[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + warp;
     if (blockIdx.x == 0 && threadIdx.x == 0 && ctl) { ctl->ticket = 0u; ctl->cursor = 0u; }
@@ -225,35 +226,49 @@ prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, Sample*
     __syncwarp();
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&Ssh[warp]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(out + b);
-    for (int w = lane; w < kSampleWords; w += 32) dst[w] = src[w];
+    for (int w = lane; w < kFullWords; w += 32) dst[w] = src[w];
 }
 
-// Estimated z planes a 32-column group of one sample walks: union of the culled ranges of five probe columns (the
-// corners and the middle of the warp's patch).  Only the ORDER in which work is handed out depends on this, never a
-// result.
+// Upper estimate of the z planes a 32-column group of one sample walks: the culling bounds of column_range() evaluated
+// once at the centre of the group's footprint, widened by how far s can move across the footprint (so a thin object
+// that slips between probe columns is never taken for empty).  Only the ORDER in which work is handed out depends on
+// this, never a result.
 __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, float bound, int group) {
-    int lo = g.n, hi = -1;
-    const int probes[5] = {0, 7, 12, 24, 31};
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const int lane = probes[q], slot = group * 32 + lane;
-        if (slot >= L.slots) continue;
-        int ia, ib;
-        if (L.patched) {
-            const int pw = L.n >> 3, pb = group / pw, pa = group - pb * pw;
-            ia = (pa << 3) + (lane & 7);
-            ib = (pb << 2) + (lane >> 3);
-        } else {
-            ib = slot / L.n;
-            ia = slot - ib * L.n;
-        }
-        float bh[3], bl[3];
-        column_base(S, g, ia, ib, bh, bl);
-        int c_lo, c_hi;
-        column_range(S, g, bound, bh, c_lo, c_hi);
-        if (c_hi >= c_lo) { lo = c_lo < lo ? c_lo : lo; hi = c_hi > hi ? c_hi : hi; }
+    float cx, cy, hx, hy;                                  // centre and half extent of the footprint, in grid steps
+    if (L.patched) {
+        const int pw = L.n >> 3, pb = group / pw, pa = group - pb * pw;
+        cx = (float)(pa << 3) + 3.5f; cy = (float)(pb << 2) + 1.5f; hx = 3.5f; hy = 1.5f;
+    } else {
+        const int slot = group * 32, ib = slot / L.n, ia = slot - ib * L.n;
+        if (ia + 31 < L.n) { cx = (float)ia + 15.5f; cy = (float)ib; hx = 15.5f; hy = 0.f; }
+        else { cx = 0.5f * (float)(L.n - 1); hx = cx; cy = (float)ib + 0.5f; hy = 0.5f; }      // wraps into the next row
     }
-    return hi >= lo ? hi - lo + 1 : 0;
+    const float gx = cx * g.stepf, gy = cy * g.stepf;
+    float lo = -1e30f, hi = 1e30f, he2 = 0.f, bc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        bc[i] = fmaf(S.mf[2 * i], gx, fmaf(S.mf[2 * i + 1], gy, S.of[i]));
+        const float hw = (fabsf(S.mf[2 * i]) * hx + fabsf(S.mf[2 * i + 1]) * hy) * g.stepf;
+        const float bi = bound + hw;
+        const float u = (bi - bc[i]) * S.idh[i], v = (-bi - bc[i]) * S.idh[i];
+        lo = fmaxf(lo, fminf(u, v));
+        hi = fminf(hi, fmaxf(u, v));
+        he2 = fmaf(i < 2 ? S.qw : 1.0f, hw * hw, he2);
+    }
+    {
+        const float r = sqrtf(bound * bound * 1.004f * S.qB1) + sqrtf(he2);
+        const float beta = fmaf(S.wd[0], bc[0], fmaf(S.wd[1], bc[1], S.wd[2] * bc[2]));
+        const float gamma = fmaf(S.qw, fmaf(bc[0], bc[0], bc[1] * bc[1]), fmaf(bc[2], bc[2], -r * r));
+        const float disc = fmaf(beta, beta, -S.qa * gamma);
+        const float sq = sqrtf(fmaxf(disc, 0.0f));
+        lo = fmaxf(lo, (-beta - sq) * S.qia);
+        hi = fminf(hi, disc > 0.0f ? (sq - beta) * S.qia : -1e30f);
+    }
+    const float nf = (float)g.n;
+    lo = fminf(fmaxf(lo - 1.0f, 0.0f), nf);
+    hi = fmaxf(fminf(hi + 1.0f, nf - 1.0f), -1.0f);
+    const int c_lo = (int)ceilf(lo), c_hi = (int)floorf(hi);
+    return c_hi >= c_lo ? c_hi - c_lo + 1 : 0;
 }
 
 // plan (column kernels): one block per sample.  Builds the Sample record(s) like prep, then estimates the cost of each
@@ -261,8 +276,8 @@ __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, flo
 template <int NS>
 __global__ void __launch_bounds__(kPlanThreads)
 plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Grid g, Layout L, float bound,
-            Sample* out_a, Sample* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap) {
-    __shared__ Sample Ssh[NS];
+            SampleFull* out_a, SampleFull* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap) {
+    __shared__ SampleFull Ssh[NS];
     __shared__ unsigned char cls[kPlanMaxItems];
     __shared__ unsigned int ccnt[kClasses], cbase[kClasses];
     const int b = blockIdx.x;
@@ -278,8 +293,8 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
         prep_sample(p, clamp != 0, g, Ssh[w]);
     }
     __syncthreads();
-    for (int w = threadIdx.x; w < NS * kSampleWords; w += kPlanThreads) {
-        const int which = w / kSampleWords, i = w - which * kSampleWords;
+    for (int w = threadIdx.x; w < NS * kFullWords; w += kPlanThreads) {
+        const int which = w / kFullWords, i = w - which * kFullWords;
         reinterpret_cast<uint32_t*>((which == 0 ? out_a : out_b) + b)[i] = reinterpret_cast<const uint32_t*>(&Ssh[which])[i];
     }
     if (!queue) return;
@@ -379,7 +394,7 @@ __device__ __forceinline__ void block_reduce_store(const Acc& a, float (*red)[kA
     }
 }
 
-__device__ __forceinline__ void load_sample(Sample* dst, const Sample* src) {       // whole block
+__device__ __forceinline__ void load_sample(Sample* dst, const SampleFull* src) {   // whole block
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
     for (int i = threadIdx.x; i < kSampleWords; i += blockDim.x) d[i] = s[i];
@@ -390,7 +405,7 @@ __device__ __forceinline__ void load_sample(Sample* dst, const Sample* src) {   
 constexpr int kSampleRegs = (kSampleWords + 31) / 32;
 struct SampleFetch {
     uint32_t w[kSampleRegs];
-    __device__ __forceinline__ void fetch(const Sample* src, int lane) {
+    __device__ __forceinline__ void fetch(const SampleFull* src, int lane) {
         const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
 #pragma unroll
         for (int j = 0; j < kSampleRegs; ++j) {
@@ -492,7 +507,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 
 template <bool BWD, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitParams P, int total_items,
+implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, ImplicitParams P, int total_items,
                 Control* __restrict__ ctl, const int* __restrict__ queue, int cap,
                 const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
@@ -532,14 +547,25 @@ implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitPa
                 const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
                 float tv = 0.f;                                // issued now, needed after the z walk
                 if (valid && target) tv = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
-                float bh[3], bl[3], cg[11], dxy[2];
-                column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
+                // which planes can hold occupancy: decided from the fp32 base; most warp column groups are empty and
+                // never need the exact (fp64) one
+                float b32[3];
+                column_base_f32(S, g, valid ? ia : 0, valid ? ib : 0, b32);
                 int c_lo, c_hi;
-                column_range(S, g, P.bound, bh, c_lo, c_hi);
+                column_range(S, g, P.bound, b32, c_lo, c_hi);
                 if (!valid) { c_lo = 0; c_hi = -1; }           // masked lanes do not widen the warp's range
                 warp_range(g.n, c_lo, c_hi);
+                if (c_hi < c_lo) {                             // warp-uniform: no occupancy anywhere, depth is exactly 0
+                    if (valid) {
+                        if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = 0.f;
+                        acc.loss += fabsf(tv);
+                    }
+                    continue;
+                }
+                float bh[3], bl[3], cg[11], dxy[2];
+                column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
                 float depth;
-#ifndef SQ_FIXHOIST
+#ifndef SQ_FIXHOIST      // measured: no gain once empty column groups leave early (profiles/tune_r01.txt)
                 depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
 #else
                 if (__any_sync(0xffffffffu, column_zero_possible(S, bh)))
@@ -576,7 +602,7 @@ implicit_kernel(const Sample* __restrict__ samples, Grid g, Layout L, ImplicitPa
 // ------------------------------------------------------------------------------------------------ ExplicitLoss
 template <bool BWD>
 __global__ void __launch_bounds__(SQ_EXP_THREADS, SQ_EXP_MINB)
-explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, float kl,
+explicit_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict__ pred, Grid g, Layout L, float kl,
                 float bound, int total_items, Control* __restrict__ ctl, const int* __restrict__ queue, int cap,
                 float* __restrict__ partials) {
     __shared__ Sample Tsh[SQ_EXP_THREADS / 32], Psh[SQ_EXP_THREADS / 32];
@@ -606,14 +632,17 @@ explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred,
                 const int ia = valid ? it.ia : 0, ib = valid ? it.ib : 0;
                 float bht[3], blt[3], bhp[3], blp[3];
                 float dxy[2];
-                column_base(St, g, ia, ib, bht, blt);
-                column_base(Sp, g, ia, ib, bhp, blp, dxy);
                 Range rt, rp;
+                column_base_f32(St, g, ia, ib, bht);           // fp32 bases decide the ranges (see implicit_kernel)
+                column_base_f32(Sp, g, ia, ib, bhp);
                 column_range(St, g, bound, bht, rt.lo, rt.hi);
                 column_range(Sp, g, bound, bhp, rp.lo, rp.hi);
                 if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }      // masked lanes do not widen the warp's range
                 warp_range(g.n, rt.lo, rt.hi);
                 warp_range(g.n, rp.lo, rp.hi);
+                if (rt.hi < rt.lo && rp.hi < rp.lo) continue;               // both occupancies 0 on the whole column
+                column_base(St, g, ia, ib, bht, blt);
+                column_base(Sp, g, ia, ib, bhp, blp, dxy);
                 Acc col;
                 acc_zero(col);
                 const float sq = explicit_column<BWD>(St, Sp, g, kl, bht, blt, bhp, blp, rt, rp, dxy[0], dxy[1], col);
@@ -638,7 +667,7 @@ explicit_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred,
 
 // ------------------------------------------------------------------------------------------------ IoU
 __global__ void __launch_bounds__(SQ_IOU_THREADS, SQ_IOU_MINB)
-iou_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid g, Layout L, int total_items,
+iou_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict__ pred, Grid g, Layout L, int total_items,
            Control* __restrict__ ctl, const int* __restrict__ queue, int cap, unsigned long long* __restrict__ counts) {
     __shared__ Sample Tsh[SQ_IOU_THREADS / 32], Psh[SQ_IOU_THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -664,16 +693,19 @@ iou_kernel(const Sample* __restrict__ tru, const Sample* __restrict__ pred, Grid
                 const bool valid = it.valid(L);
                 const int ia = valid ? it.ia : 0, ib = valid ? it.ib : 0;
                 float bht[3], blt[3], bhp[3], blp[3];
-                column_base(St, g, ia, ib, bht, blt);
-                column_base(Sp, g, ia, ib, bhp, blp);
                 Range rt, rp;
+                column_base_f32(St, g, ia, ib, bht);           // fp32 bases decide the ranges (see implicit_kernel)
+                column_base_f32(Sp, g, ia, ib, bhp);
                 column_range(St, g, kIoUBound, bht, rt.lo, rt.hi);
                 column_range(Sp, g, kIoUBound, bhp, rp.lo, rp.hi);
                 if (!valid) { rt.lo = rp.lo = 0; rt.hi = rp.hi = -1; }
                 warp_range(g.n, rt.lo, rt.hi);
                 warp_range(g.n, rp.lo, rp.hi);
+                if (rt.hi < rt.lo && rp.hi < rp.lo) continue;               // outside both: nothing to count
+                column_base(St, g, ia, ib, bht, blt);
+                column_base(Sp, g, ia, ib, bhp, blp);
                 unsigned i = 0, u = 0;
-                iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
+                iou_column(St, Sp, tru + b, pred + b, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
                 if (valid) { inter += i; uni += u; }
             }
             inter = __reduce_add_sync(0xffffffffu, inter);
@@ -697,7 +729,7 @@ __global__ void iou_export_kernel(const unsigned long long* counts, int batch, l
 // ------------------------------------------------------------------------------------------------ LeastSquares
 template <bool BWD>
 __global__ void __launch_bounds__(kThreads)
-lsq_kernel(const Sample* __restrict__ samples, int R, int items_per_sample,
+lsq_kernel(const SampleFull* __restrict__ samples, int R, int items_per_sample,
            const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
            const int* __restrict__ col_off, float* __restrict__ partials) {
     __shared__ Sample S;
@@ -726,7 +758,7 @@ enum { FIN_IMPLICIT = 0, FIN_EXPLICIT = 1, FIN_LSQ = 2 };
 // one warp per sample; the last block averages the batch
 template <int KIND>
 __global__ void __launch_bounds__(32)
-finalize_kernel(const Sample* __restrict__ samples, Grid g, int batch, int items_per_sample,
+finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int items_per_sample,
                 const float* __restrict__ partials, double loss_norm, double grad_scale,
                 int dtype, void* __restrict__ grad, double* __restrict__ per_sample,
                 double* __restrict__ per_sample_user, double* __restrict__ loss_out, unsigned int* ticket) {
@@ -754,7 +786,7 @@ finalize_kernel(const Sample* __restrict__ samples, Grid g, int batch, int items
     }
     __syncwarp();
     if (lane == 0) {
-        const Sample& S = samples[b];
+        const SampleFull& S = samples[b];
         double ls = acc[17] * loss_norm;
         double vol = 1.0;
         if (KIND == FIN_LSQ) { vol = S.a[0] * S.a[1] * S.a[2]; ls *= vol; }
@@ -788,7 +820,7 @@ finalize_kernel(const Sample* __restrict__ samples, Grid g, int batch, int items
 
 // ------------------------------------------------------------------------------------------------ field
 __global__ void __launch_bounds__(256)
-field_kernel(const Sample* __restrict__ samples, Grid g, int batch, int mode, float kl, float* __restrict__ out) {
+field_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int mode, float kl, float* __restrict__ out) {
     const size_t n = g.n, per = n * n * n;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= per * batch) return;
@@ -863,7 +895,7 @@ int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
     return need < fill ? need : fill;
 }
 
-int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid& g, Sample* out, Control* ctl,
+int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid& g, SampleFull* out, Control* ctl,
                 cudaStream_t st) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
     prep_kernel<<<(batch + 3) / 4, 128, 0, st>>>(params, dtype, batch, clamp ? 1 : 0, g, out, ctl);

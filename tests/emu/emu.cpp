@@ -27,7 +27,7 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
     double total = 0.0;
     for (int b = 0; b < B; ++b) {
         double p[12]; for (int i = 0; i < 12; ++i) p[i] = pred[12 * b + i];
-        Sample S; prep_sample(p, true, g, S);
+        SampleFull S; prep_sample(p, true, g, S);
         double accd[kAccN] = {0};
         for (int ib = 0; ib < n; ++ib) for (int ia = 0; ia < n; ++ia) {
             float bh[3], bl[3], cg[11];
@@ -66,7 +66,7 @@ int emu_explicit(const double* tru, const double* pred, int B, int n, double ste
     for (int b = 0; b < B; ++b) {
         double pt[12], pp[12];
         for (int i = 0; i < 12; ++i) { pt[i] = tru[12 * b + i]; pp[i] = pred[12 * b + i]; }
-        Sample St, Sp; prep_sample(pt, true, g, St); prep_sample(pp, true, g, Sp);
+        SampleFull St, Sp; prep_sample(pt, true, g, St); prep_sample(pp, true, g, Sp);
         double accd[kAccN] = {0};
         for (int ib = 0; ib < n; ++ib) for (int ia = 0; ia < n; ++ia) {
             float bht[3], blt[3], bhp[3], blp[3];
@@ -95,7 +95,7 @@ int emu_iou(const double* tru, const double* pred, int B, int n, double step, lo
     for (int b = 0; b < B; ++b) {
         double pt[12], pp[12];
         for (int i = 0; i < 12; ++i) { pt[i] = tru[12 * b + i]; pp[i] = pred[12 * b + i]; }
-        Sample St, Sp; prep_sample(pt, false, g, St); prep_sample(pp, false, g, Sp);
+        SampleFull St, Sp; prep_sample(pt, false, g, St); prep_sample(pp, false, g, Sp);
         long long I = 0, U = 0;
         for (int ib = 0; ib < n; ++ib) for (int ia = 0; ia < n; ++ia) {
             float bht[3], blt[3], bhp[3], blp[3];
@@ -105,7 +105,7 @@ int emu_iou(const double* tru, const double* pred, int B, int n, double step, lo
             Range rt, rp;
             column_range(St, g, kIoUBound, bht, rt.lo, rt.hi); warp_range(n, rt.lo, rt.hi);
             column_range(Sp, g, kIoUBound, bhp, rp.lo, rp.hi); warp_range(n, rp.lo, rp.hi);
-            iou_column(St, Sp, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
+            iou_column(St, Sp, &St, &Sp, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
             I += i; U += u;
         }
         inter[b] = I; uni[b] = U;
@@ -119,7 +119,7 @@ int emu_lsq(const double* pred, int B, const float* points, const int* offsets, 
     double total = 0.0;
     for (int b = 0; b < B; ++b) {
         double p[12]; for (int i = 0; i < 12; ++i) p[i] = pred[12 * b + i];
-        Sample S; prep_sample(p, true, g, S);
+        SampleFull S; prep_sample(p, true, g, S);
         double accd[kAccN] = {0};
         for (int j = offsets[b]; j < offsets[b + 1]; ++j) {
             Acc a; acc_zero(a);
