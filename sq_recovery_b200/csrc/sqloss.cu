@@ -61,6 +61,7 @@ namespace {
 #ifndef SQ_IOU_CPT
 #define SQ_IOU_CPT 1
 #endif
+#define SQ_MAX_CPT 4                     // upper limit of any *_CPT above (loops over column groups are unrolled to it)
 constexpr int kThreads = 256;            // block size of the small kernels (point list, field)
 constexpr int kWarps = kThreads / 32;
 
@@ -248,7 +249,9 @@ __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, flo
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         bc[i] = fmaf(S.mf[2 * i], gx, fmaf(S.mf[2 * i + 1], gy, S.of[i]));
-        const float hw = (fabsf(S.mf[2 * i]) * hx + fabsf(S.mf[2 * i + 1]) * hy) * g.stepf;
+        // + the 0 -> z0 substitution of grid index 0, + 1 % and 1e-4 for the fp32 evaluation here and in the kernels
+        const float hw = ((fabsf(S.mf[2 * i]) * hx + fabsf(S.mf[2 * i + 1]) * hy) * g.stepf
+                          + (fabsf(S.mf[2 * i]) + fabsf(S.mf[2 * i + 1])) * fabsf(g.z0f)) * 1.01f + 1e-4f;
         const float bi = bound + hw;
         const float u = (bi - bc[i]) * S.idh[i], v = (-bi - bc[i]) * S.idh[i];
         lo = fmaxf(lo, fminf(u, v));
@@ -276,7 +279,8 @@ __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, flo
 template <int NS>
 __global__ void __launch_bounds__(kPlanThreads)
 plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Grid g, Layout L, float bound,
-            SampleFull* out_a, SampleFull* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap) {
+            SampleFull* out_a, SampleFull* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap,
+            float* zero_rows) {
     __shared__ SampleFull Ssh[NS];
     __shared__ unsigned char cls[kPlanMaxItems];
     __shared__ unsigned int ccnt[kClasses], cbase[kClasses];
@@ -308,8 +312,13 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
 #pragma unroll
             for (int w = 0; w < NS; ++w) cost += group_planes(Ssh[w], g, L, bound, group);
         }
-        int c = kClasses - 1;                              // estimated empty
+        int c = kClasses - 1;                              // proven empty (group_planes is an upper bound)
         if (cost > 0) { c = 0; while (c < kClasses - 2 && (cost << (c + 1)) <= max_cost) ++c; }
+        else if (zero_rows) {                              // the column kernel will not touch this item
+            float* row = zero_rows + (size_t)(b * J + j) * kAccN;
+#pragma unroll
+            for (int i = 0; i < kAccN; ++i) row[i] = 0.f;
+        }
         cls[j] = (unsigned char)c;
         atomicAdd(&ccnt[c], 1u);
     }
@@ -342,24 +351,23 @@ __device__ __forceinline__ void acc_to_array(const Acc& a, float* v) {
     v[15] = a.ge[0]; v[16] = a.ge[1]; v[17] = a.loss;
 }
 
+__device__ __forceinline__ void array_to_acc(const float* v, Acc& a) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a.gs[i] = v[i]; a.wa[i] = v[12 + i]; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a.gm[i] = v[3 + i];
+    a.ge[0] = v[15]; a.ge[1] = v[16]; a.loss = v[17];
+}
+
 // per-thread Acc -> one row of kAccN floats per WARP, through the warp's own shared-memory tile: every lane writes
 // its 18 sums (5 vector stores), lane i < 18 adds up column i over the 32 lanes in a fixed order.  37 shared-memory
 // instructions and 32 adds per warp instead of the 90 shuffles + 90 adds of a butterfly per value.
 constexpr int kRedStride = 20;           // floats per lane in the tile (18 used; 80 bytes keeps float4 alignment)
 constexpr int kRedFloats = 32 * kRedStride;
 
-__device__ __forceinline__ void warp_reduce_store(const Acc& a, float* tile, float* row, bool nonzero) {
+// lane i < 18 adds up column i of the warp's tile over the 32 lanes (fixed order) and stores the partial row
+__device__ __forceinline__ void tile_reduce_store(const float* tile, float* row) {
     const int lane = threadIdx.x & 31;
-    if (!__any_sync(0xffffffffu, nonzero)) {          // e.g. image-border patches: no object, no loss, no gradient
-        if (lane < kAccN) row[lane] = 0.f;
-        return;
-    }
-    float v[kRedStride];
-    acc_to_array(a, v);
-    v[18] = v[19] = 0.f;
-    float4* mine = reinterpret_cast<float4*>(tile + lane * kRedStride);
-#pragma unroll
-    for (int q = 0; q < kRedStride / 4; ++q) mine[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     __syncwarp();
     if (lane < kAccN) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -373,6 +381,30 @@ __device__ __forceinline__ void warp_reduce_store(const Acc& a, float* tile, flo
         row[lane] = (s0 + s1) + (s2 + s3);
     }
     __syncwarp();
+}
+
+__device__ __forceinline__ void tile_put(float* tile, const float* v /*[kRedStride]*/) {
+    float4* mine = reinterpret_cast<float4*>(tile + (threadIdx.x & 31) * kRedStride);
+#pragma unroll
+    for (int q = 0; q < kRedStride / 4; ++q) mine[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void tile_get(const float* tile, float* v /*[kRedStride]*/) {
+    const float4* mine = reinterpret_cast<const float4*>(tile + (threadIdx.x & 31) * kRedStride);
+#pragma unroll
+    for (int q = 0; q < kRedStride / 4; ++q) { const float4 t = mine[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+}
+
+__device__ __forceinline__ void warp_reduce_store(const Acc& a, float* tile, float* row, bool nonzero) {
+    const int lane = threadIdx.x & 31;
+    if (!__any_sync(0xffffffffu, nonzero)) {          // e.g. image-border patches: no object, no loss, no gradient
+        if (lane < kAccN) row[lane] = 0.f;
+        return;
+    }
+    float v[kRedStride];
+    acc_to_array(a, v);
+    v[18] = v[19] = 0.f;
+    tile_put(tile, v);
+    tile_reduce_store(tile, row);
 }
 
 // per-thread Acc -> one row of kAccN floats per BLOCK (point-list kernel)
@@ -465,33 +497,56 @@ struct WorkMap {
 // would be kept from idle warps during the end-game; claimed later, the cursor -> queue -> Sample chain of L2 round
 // trips would not be hidden).  Deeper pipelines (claims 2-3 items ahead) were measured 25 % slower: they undo the
 // longest-first order while the items are still expensive.
+// Positions from `empty_from` on are the last cost class: items the plan kernel has PROVEN to have no occupancy on any
+// of their columns (its estimate is an upper bound).  Kernels either drop them (skip_empty) or handle them in bulk.
 struct WorkPipe {
     WorkMap wm;
     const int* queue; unsigned int* cursor;
-    int cap, total;
+    int cap, total, empty_from;
     int item, next;              // current / next work item (-1: none)
-    __device__ __forceinline__ void start(Control* ctl, const int* q, int cap_, int total_, int lane) {
-        queue = q; cursor = &ctl->cursor; cap = cap_; total = total_;
-        item = next = -1;
+    int item_pos, next_pos;      // their positions in the processing order
+    bool joined;                 // this warp has read the queue counters (retire() must be told)
+    __device__ __forceinline__ void start(Control* ctl, const int* q, int cap_, int total_, bool skip_empty, int lane) {
+        queue = q; cursor = &ctl->cursor; cap = cap_; total = total_; empty_from = total_;
+        item = next = -1; item_pos = next_pos = total_;
         const int p0 = first_position();
-        if (p0 >= total) return;
+        joined = p0 < total_;
+        if (!joined) return;
         wm.init(ctl, lane);
-        item = wm.item(queue, cap, p0, lane);
+        if (queue) empty_from = (int)__shfl_sync(0xffffffffu, wm.excl, kClasses - 1);
+        if (skip_empty) total = empty_from;
+        if (p0 < total) { item = wm.item(queue, cap, p0, lane); item_pos = p0; }
     }
     __device__ __forceinline__ bool claim(int lane) {
-        const int pos = next_position(cursor, lane);
-        next = pos < total ? wm.item(queue, cap, pos, lane) : -1;
-        return next >= 0;
+        next_pos = next_position(cursor, lane);
+        next = next_pos < total ? wm.item(queue, cap, next_pos, lane) : -1;
+        return next >= 0 && next_pos < empty_from;         // true: an item that needs its Sample
     }
-    __device__ __forceinline__ void rotate() { item = next; next = -1; }
+    __device__ __forceinline__ void rotate() { item = next; item_pos = next_pos; next = -1; }
+    __device__ __forceinline__ bool current_needs_work() const { return item >= 0 && item_pos < empty_from; }
+    // up to kBulk proven-empty items per cursor claim
+    __device__ __forceinline__ int claim_empty(int* items, int max_items, int lane) {
+        int base = 0;
+        if (lane == 0) base = (int)(atomicAdd(cursor, (unsigned int)max_items) + gridDim.x * (blockDim.x >> 5));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        int cnt = total - base;
+        cnt = cnt < 0 ? 0 : (cnt > max_items ? max_items : cnt);
+        int mine = -1;
+        if (lane < cnt) mine = __ldg(queue + (size_t)(kClasses - 1) * cap + (base - empty_from + lane));
+        for (int e = 0; e < max_items; ++e) items[e] = __shfl_sync(0xffffffffu, mine, e);
+        return cnt;
+    }
 };
+constexpr int kBulk = 4;
 
-// A warp leaving a column kernel reports how many items it processed; the one that completes the count puts the
-// control block back to its between-calls state (every warp that had work read qcount before it processed anything).
-__device__ __forceinline__ void retire(Control* ctl, unsigned int n_items, unsigned int total, int lane) {
-    if (lane == 0 && n_items) {
-        const unsigned int before = atomicAdd(&ctl->retired, n_items);
-        if (before + n_items == total) {
+// Every warp that read the queue counters reports when it leaves; the last of them puts the control block back to
+// its between-calls state.  (`joiners` = warps whose first position is below the item count.)
+__device__ __forceinline__ void retire(Control* ctl, bool joined, int total_items, int lane) {
+    if (lane == 0 && joined) {
+        const unsigned int warps = gridDim.x * (blockDim.x >> 5);
+        const unsigned int joiners = (unsigned int)total_items < warps ? (unsigned int)total_items : warps;
+        const unsigned int before = atomicAdd(&ctl->retired, 1u);
+        if (before + 1u == joiners) {
             ctl->retired = 0u;
 #pragma unroll
             for (int k = 0; k < kClasses; ++k) ctl->qcount[k] = 0u;
@@ -502,6 +557,7 @@ __device__ __forceinline__ void retire(Control* ctl, unsigned int n_items, unsig
 // ------------------------------------------------------------------------------------------------ ImplicitLoss
 #ifdef SQ_TIMELINE     // tools/timeline.py: per-warp start / end timestamps and item counts of the implicit kernel
 __device__ unsigned long long g_timeline[3 * 8192];
+__device__ unsigned int g_classes[kClasses];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
@@ -518,35 +574,54 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
     // Persistent warps pull work items from a global cursor: item cost varies a lot with the culled z range, and a
     // static assignment left the SMs idle at the tail.  The next item and its Sample are fetched while the current
     // item is processed.  No block-level barrier anywhere.
-    unsigned int n_items = 0;
 #ifdef SQ_TIMELINE
     const unsigned long long t_begin = gtime();
-    unsigned long long t_last_fetch = t_begin;
+    unsigned long long t_last_fetch = t_begin, n_items = 0;
+    if (BWD && blockIdx.x == 0 && threadIdx.x < kClasses) g_classes[threadIdx.x] = ctl->qcount[threadIdx.x];
 #endif
     WorkPipe wp;
-    wp.start(ctl, queue, cap, total_items, lane);
+    wp.start(ctl, queue, cap, total_items, false, lane);
     {
         SampleFetch pre;
-        if (wp.item >= 0) pre.fetch(samples + L.sample_of(wp.item), lane);
-        while (wp.item >= 0) {
+        if (wp.current_needs_work()) pre.fetch(samples + L.sample_of(wp.item), lane);
+        while (wp.current_needs_work()) {
 #ifdef SQ_TIMELINE
-            t_last_fetch = gtime();
+            t_last_fetch = gtime(); ++n_items;
 #endif
             int b, chunk;
             L.split(wp.item, b, chunk);
             pre.commit(&S, lane);
 
-            Acc acc;
-            acc_zero(acc);
+            // Per-thread sums of the item live in the warp's shared-memory tile (the layout the final reduction reads),
+            // not in 18 registers: they are touched once per non-empty column, the registers buy a fifth block per SM.
+            float loss_sum = 0.f;
+            bool folded = false;
             ColIter it;
             it.init(L, chunk, lane);
-            for (int k = 0; k < L.cpt; ++k, it.next(L)) {
+            // the item's target pixels: all loads issued up front (they miss to HBM; most column groups turn out empty
+            // and would otherwise do nothing but wait for their pixel)
+            float tvs[SQ_MAX_CPT];
+            {
+                ColIter pt = it;
+#pragma unroll
+                for (int k = 0; k < SQ_MAX_CPT; ++k) {
+                    tvs[k] = 0.f;
+                    if (target && k < L.cpt) {
+                        if (pt.valid(L)) tvs[k] = __ldg(target + (size_t)b * tstride + row_off[g.n - 1 - pt.ib] + col_off[pt.ia]);
+                        pt.next(L);
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int k = 0; k < L.cpt; ++k) {
                 if (k == L.cpt - 1 && wp.claim(lane)) pre.fetch(samples + L.sample_of(wp.next), lane);
                 const int ia = it.ia, ib = it.ib;
                 const bool valid = it.valid(L);
                 const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
-                float tv = 0.f;                                // issued now, needed after the z walk
-                if (valid && target) tv = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
+                float tv = tvs[0];                             // select, not an indexed load: tvs stays in registers
+#pragma unroll
+                for (int q = 1; q < SQ_MAX_CPT; ++q) tv = k == q ? tvs[q] : tv;
+                it.next(L);
                 // which planes can hold occupancy: decided from the fp32 base; most warp column groups are empty and
                 // never need the exact (fp64) one
                 float b32[3];
@@ -558,7 +633,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 if (c_hi < c_lo) {                             // warp-uniform: no occupancy anywhere, depth is exactly 0
                     if (valid) {
                         if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = 0.f;
-                        acc.loss += fabsf(tv);
+                        loss_sum += fabsf(tv);
                     }
                     continue;
                 }
@@ -577,24 +652,88 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
                     if (target) {
                         const float diff = depth - tv;
-                        acc.loss += fabsf(diff);
-                        if (BWD) {
-                            const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                            implicit_fold(acc, cg, w, dxy[0], dxy[1]);
+                        loss_sum += fabsf(diff);
+                        if (BWD && diff != 0.f) {
+                            float v[kRedStride];
+                            Acc acc;
+                            if (folded) { tile_get(tiles[warp], v); array_to_acc(v, acc); } else acc_zero(acc);
+                            implicit_fold(acc, cg, diff > 0.f ? 1.f : -1.f, dxy[0], dxy[1]);
+                            acc_to_array(acc, v);
+                            v[18] = v[19] = 0.f;
+                            tile_put(tiles[warp], v);
+                            folded = true;
                         }
                     }
                 }
             }
-            if (target) warp_reduce_store(acc, tiles[warp], partials + ((size_t)b * L.rows_per_sample + chunk) * kAccN, acc.loss != 0.f);   // zero loss => zero gradient
-            ++n_items;
+            if (target) {
+                float* row = partials + ((size_t)b * L.rows_per_sample + chunk) * kAccN;
+                if (!__any_sync(0xffffffffu, loss_sum != 0.f)) {          // zero loss => zero gradient
+                    if (lane < kAccN) row[lane] = 0.f;
+                } else {
+                    if (!folded) {
+                        float4* mine = reinterpret_cast<float4*>(tiles[warp] + lane * kRedStride);
+#pragma unroll
+                        for (int q = 0; q < kRedStride / 4; ++q) mine[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    tiles[warp][lane * kRedStride + kAccN - 1] = loss_sum;
+                    tile_reduce_store(tiles[warp], row);
+                }
+            }
             wp.rotate();
         }
     }
-    retire(ctl, n_items, (unsigned int)total_items, lane);
+    // Items proven empty by the plan kernel: depth is exactly 0 on every column, so the loss is sum |target| and there
+    // is no gradient.  No Sample, no geometry; kBulk items per cursor claim, all their pixel loads in flight together.
+    if (wp.item >= 0) {
+        int items[kBulk];
+        int cnt = 1;
+        items[0] = wp.item;
+#pragma unroll
+        for (int e = 1; e < kBulk; ++e) items[e] = -1;
+        while (cnt > 0) {
+#ifdef SQ_TIMELINE
+            t_last_fetch = gtime(); n_items += cnt;
+#endif
+            float sum[kBulk];
+            ColIter its[kBulk];
+            int bs[kBulk];
+#pragma unroll
+            for (int e = 0; e < kBulk; ++e) {
+                sum[e] = 0.f;
+                int chunk = 0;
+                bs[e] = 0;
+                if (e < cnt) L.split(items[e], bs[e], chunk);
+                its[e].init(L, chunk, lane);
+            }
+            for (int k = 0; k < L.cpt; ++k) {
+#pragma unroll
+                for (int e = 0; e < kBulk; ++e) {
+                    if (e < cnt && its[e].valid(L)) {
+                        const int row = g.n - 1 - its[e].ib, col = its[e].ia;
+                        if (target) sum[e] += fabsf(__ldg(target + (size_t)bs[e] * tstride + row_off[row] + col_off[col]));
+                        if (depth_out) depth_out[((size_t)bs[e] * g.n + row) * g.n + col] = 0.f;
+                    }
+                    its[e].next(L);
+                }
+            }
+            if (target) {
+#pragma unroll
+                for (int e = 0; e < kBulk; ++e) {
+                    if (e < cnt) {
+                        const float t = warp_sum(sum[e]);
+                        if (lane < kAccN) partials[(size_t)items[e] * kAccN + lane] = lane == kAccN - 1 ? t : 0.f;
+                    }
+                }
+            }
+            cnt = wp.claim_empty(items, kBulk, lane);
+        }
+    }
+    retire(ctl, wp.joined, total_items, lane);
 #ifdef SQ_TIMELINE
     if (BWD && lane == 0) {
         const int w = first_position();
-        if (w < 8192) { g_timeline[3 * w] = t_begin; g_timeline[3 * w + 1] = gtime(); g_timeline[3 * w + 2] = ((unsigned long long)n_items << 40) | (t_last_fetch - t_begin); }
+        if (w < 8192) { g_timeline[3 * w] = t_begin; g_timeline[3 * w + 1] = gtime(); g_timeline[3 * w + 2] = (n_items << 40) | (t_last_fetch - t_begin); }
     }
 #endif
 }
@@ -610,9 +749,8 @@ explicit_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& St = Tsh[warp];
     Sample& Sp = Psh[warp];
-    unsigned int n_items = 0;
     WorkPipe wp;
-    wp.start(ctl, queue, cap, total_items, lane);
+    wp.start(ctl, queue, cap, total_items, true, lane);      // proven-empty items are dropped (their rows: plan kernel)
     {
         SampleFetch pre_t, pre_p;
         if (wp.item >= 0) { pre_t.fetch(tru + L.sample_of(wp.item), lane); pre_p.fetch(pred + L.sample_of(wp.item), lane); }
@@ -658,11 +796,10 @@ explicit_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict
                 }
             }
             warp_reduce_store(acc, tiles[warp], partials + (size_t)item * kAccN, acc.loss != 0.f);
-            ++n_items;
             wp.rotate();
         }
     }
-    retire(ctl, n_items, (unsigned int)total_items, lane);
+    retire(ctl, wp.joined, total_items, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ IoU
@@ -673,9 +810,8 @@ iou_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict__ pr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& St = Tsh[warp];
     Sample& Sp = Psh[warp];
-    unsigned int n_items = 0;
     WorkPipe wp;
-    wp.start(ctl, queue, cap, total_items, lane);
+    wp.start(ctl, queue, cap, total_items, true, lane);      // proven-empty items are dropped (their rows: plan kernel)
     {
         SampleFetch pre_t, pre_p;
         if (wp.item >= 0) { pre_t.fetch(tru + L.sample_of(wp.item), lane); pre_p.fetch(pred + L.sample_of(wp.item), lane); }
@@ -714,11 +850,10 @@ iou_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict__ pr
                 atomicAdd(counts + 2 * b, (unsigned long long)inter);
                 atomicAdd(counts + 2 * b + 1, (unsigned long long)uni);
             }
-            ++n_items;
             wp.rotate();
         }
     }
-    retire(ctl, n_items, (unsigned int)total_items, lane);
+    retire(ctl, wp.joined, total_items, lane);
 }
 
 __global__ void iou_export_kernel(const unsigned long long* counts, int batch, long long* inter, long long* uni) {
@@ -904,15 +1039,16 @@ int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid
 
 // plan kernel of a column-kernel call: Samples, per-sample counters, cost-class queues
 int launch_plan(const void* params_a, const void* params_b, int dtype, int batch, bool clamp, const Grid& g,
-                const Layout& L, float bound, const Scratch& s, unsigned long long* counts, cudaStream_t st) {
+                const Layout& L, float bound, const Scratch& s, unsigned long long* counts, float* zero_rows,
+                cudaStream_t st) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
     int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
     if (params_b)
         plan_kernel<2><<<batch, kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, g, L, bound, s.tru, s.pred,
-                                                       s.ctl, counts, queue, s.queue_cap);
+                                                       s.ctl, counts, queue, s.queue_cap, zero_rows);
     else
         plan_kernel<1><<<batch, kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, g, L, bound, s.pred, nullptr,
-                                                       s.ctl, counts, queue, s.queue_cap);
+                                                       s.ctl, counts, queue, s.queue_cap, zero_rows);
     return (int)cudaGetLastError();
 }
 
@@ -932,6 +1068,9 @@ int sq_device_sm_count(int device, int* sm_count) {
 #ifdef SQ_TIMELINE
 int sq_debug_timeline(unsigned long long* host_out, int n) {
     return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * 3 * (size_t)n);
+}
+int sq_debug_classes(unsigned int* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_classes, sizeof(unsigned int) * kClasses);
 }
 #endif
 
@@ -962,8 +1101,8 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, grad_pred ? SQ_IMPB_CPT : SQ_IMPF_CPT);
-    const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, cull_bound(sharpness * kLog2e)};
-    rc = launch_plan(pred, nullptr, pred_dtype, batch, true, g, L, P.bound, s, nullptr, st);
+    const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, implicit_cull_bound(sharpness * kLog2e)};
+    rc = launch_plan(pred, nullptr, pred_dtype, batch, true, g, L, P.bound, s, nullptr, nullptr, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
@@ -1003,7 +1142,7 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, SQ_EXP_CPT);
     const float kl = sharpness * kLog2e, bound = cull_bound_bits(kl, 24.0f);
-    rc = launch_plan(true_params, pred, params_dtype, batch, true, g, L, bound, s, nullptr, st);
+    rc = launch_plan(true_params, pred, params_dtype, batch, true, g, L, bound, s, nullptr, s.partials, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
@@ -1033,7 +1172,7 @@ int sq_iou_counts(const void* true_params, const void* pred, int params_dtype, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, SQ_IOU_CPT);
-    rc = launch_plan(true_params, pred, params_dtype, batch, false, g, L, kIoUBound, s, s.counts, st);
+    rc = launch_plan(true_params, pred, params_dtype, batch, false, g, L, kIoUBound, s, s.counts, nullptr, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;

@@ -61,3 +61,8 @@ print(f"last item fetched at: p50 {np.median(last_fetch):.1f} max {last_fetch.ma
 print(f"items per warp: min {items.min()} p50 {np.median(items)} max {items.max()}")
 busy = (end - start).sum() / (len(buf) * end.max())
 print(f"warp-slot utilisation (sum of warp lifetimes / warps x span): {busy:.3f}")
+
+cls = np.zeros(8, dtype=np.uint32)
+h.sq_debug_classes.argtypes = [ctypes.c_void_p]
+if h.sq_debug_classes(cls.ctypes.data_as(ctypes.c_void_p)) == 0:
+    print("items per cost class (0 = longest ... 7 = certified empty):", cls.tolist())
