@@ -32,7 +32,7 @@ namespace {
 #define SQ_IMPB_MINB 4
 #endif
 #ifndef SQ_IMPB_CPT
-#define SQ_IMPB_CPT 2
+#define SQ_IMPB_CPT 1
 #endif
 #ifndef SQ_IMPF_THREADS
 #define SQ_IMPF_THREADS 256              // implicit fwd only (validation, depth rendering)
@@ -61,7 +61,6 @@ namespace {
 #ifndef SQ_IOU_CPT
 #define SQ_IOU_CPT 1
 #endif
-#define SQ_MAX_CPT 4                     // upper limit of any *_CPT above (loops over column groups are unrolled to it)
 constexpr int kThreads = 256;            // block size of the small kernels (point list, field)
 constexpr int kWarps = kThreads / 32;
 
@@ -139,7 +138,7 @@ struct ColIter {
 // kernel sorts them into kClasses cost classes, one queue per class.  Class k holds items whose estimated number of
 // z planes is in (max / 2^(k+1), max / 2^k]; the last class holds items estimated empty.
 constexpr int kClasses = 8;
-constexpr int kPlanThreads = 128;
+constexpr int kPlanThreads = 256;
 constexpr int kPlanMaxItems = 8192;      // items per sample the plan kernel can classify (more: index order)
 
 // First 256 bytes of every scratch buffer.  qcount and retired must be ZERO when a call starts: sq_scratch_init()
@@ -148,7 +147,7 @@ constexpr int kPlanMaxItems = 8192;      // items per sample the plan kernel can
 struct Control {
     unsigned int ticket;                 // samples finalized so far (the last one averages the batch)
     unsigned int cursor;                 // work-stealing cursor of the column kernel
-    unsigned int retired;                // items retired by warps that have left the column kernel
+    unsigned int retired;                // warps that have left the column kernel
     unsigned int pad0;
     unsigned int qcount[kClasses];       // items per cost class
     unsigned int pad1[64 - 4 - kClasses];
@@ -161,6 +160,7 @@ struct Scratch {
     SampleFull* tru;       // [batch]
     float* partials;       // [batch * rows_per_sample][kAccN]
     double* per_sample;    // [batch]
+    double* tv_sum;        // [batch] sum |target| over the sample's pixels (ImplicitLoss)
     unsigned long long* counts;   // [batch][2] (IoU)
     int* queue;            // [kClasses][queue_cap] item ids by cost class; nullptr: items are taken in index order
     int queue_cap;
@@ -181,6 +181,7 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     if (lsq_rows > rows_ps) rows_ps = lsq_rows;
     const size_t o_part = take(sizeof(float) * kAccN * rows_ps * (size_t)batch);
     const size_t o_ps = take(sizeof(double) * (size_t)batch);
+    const size_t o_tv = take(sizeof(double) * (size_t)batch);
     const size_t o_cnt = take(sizeof(unsigned long long) * 2 * (size_t)batch);
     const size_t cap = (size_t)L.rows_per_sample * (size_t)batch;
     const bool queued = L.rows_per_sample <= kPlanMaxItems && cap < (1u << 30);
@@ -191,6 +192,7 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
         s->tru = reinterpret_cast<SampleFull*>(base + o_true);
         s->partials = reinterpret_cast<float*>(base + o_part);
         s->per_sample = reinterpret_cast<double*>(base + o_ps);
+        s->tv_sum = reinterpret_cast<double*>(base + o_tv);
         s->counts = reinterpret_cast<unsigned long long*>(base + o_cnt);
         s->queue = queued ? reinterpret_cast<int*>(base + o_queue) : nullptr;
         s->queue_cap = (int)cap;
@@ -280,10 +282,12 @@ template <int NS>
 __global__ void __launch_bounds__(kPlanThreads)
 plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Grid g, Layout L, float bound,
             SampleFull* out_a, SampleFull* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap,
-            float* zero_rows) {
+            float* zero_rows, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
+            const int* __restrict__ col_off, double* tv_sum) {
     __shared__ SampleFull Ssh[NS];
     __shared__ unsigned char cls[kPlanMaxItems];
     __shared__ unsigned int ccnt[kClasses], cbase[kClasses];
+    __shared__ double tv_part[kPlanThreads / 32];
     const int b = blockIdx.x;
     if (threadIdx.x < kClasses) ccnt[threadIdx.x] = 0u;
     if (threadIdx.x == 64) {
@@ -296,7 +300,37 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
         load_params(w == 0 ? params_a : params_b, dtype, b, p);
         prep_sample(p, clamp != 0, g, Ssh[w]);
     }
+    // ImplicitLoss: sum |target| over the sample's n x n pixels, by the warps that are not busy with the fp64 prep (it
+    // hides behind it).  The column kernel then only adds |depth - t| - |t| for the columns it actually walks, so
+    // columns without occupancy need neither their pixel nor any other work.  Fixed order: bit-reproducible.
+    if (tv_sum) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (warp >= NS) {
+            const int t = threadIdx.x - 32 * NS, T = kPlanThreads - 32 * NS, npix = g.n * g.n;
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+            const float* img = target + (size_t)b * tstride;
+            int i = t;
+            for (; i + 3 * T < npix; i += 4 * T) {         // four independent loads in flight per thread
+                const int i1 = i + T, i2 = i + 2 * T, i3 = i + 3 * T;
+                const float v0 = __ldg(img + row_off[i / g.n] + col_off[i % g.n]);
+                const float v1 = __ldg(img + row_off[i1 / g.n] + col_off[i1 % g.n]);
+                const float v2 = __ldg(img + row_off[i2 / g.n] + col_off[i2 % g.n]);
+                const float v3 = __ldg(img + row_off[i3 / g.n] + col_off[i3 % g.n]);
+                acc0 += fabsf(v0); acc1 += fabsf(v1); acc2 += fabsf(v2); acc3 += fabsf(v3);
+            }
+            for (; i < npix; i += T) acc0 += fabsf(__ldg(img + row_off[i / g.n] + col_off[i % g.n]));
+            double d = (double)((acc0 + acc1) + (acc2 + acc3));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            if (lane == 0) tv_part[warp] = d;
+        }
+    }
     __syncthreads();
+    if (tv_sum && threadIdx.x == 0) {
+        double d = 0.0;
+        for (int w = NS; w < kPlanThreads / 32; ++w) d += tv_part[w];
+        tv_sum[b] = d;
+    }
     for (int w = threadIdx.x; w < NS * kFullWords; w += kPlanThreads) {
         const int which = w / kFullWords, i = w - which * kFullWords;
         reinterpret_cast<uint32_t*>((which == 0 ? out_a : out_b) + b)[i] = reinterpret_cast<const uint32_t*>(&Ssh[which])[i];
@@ -498,7 +532,7 @@ struct WorkMap {
 // trips would not be hidden).  Deeper pipelines (claims 2-3 items ahead) were measured 25 % slower: they undo the
 // longest-first order while the items are still expensive.
 // Positions from `empty_from` on are the last cost class: items the plan kernel has PROVEN to have no occupancy on any
-// of their columns (its estimate is an upper bound).  Kernels either drop them (skip_empty) or handle them in bulk.
+// of their columns (its estimate is an upper bound).  The kernels never touch them (skip_empty).
 struct WorkPipe {
     WorkMap wm;
     const int* queue; unsigned int* cursor;
@@ -524,20 +558,7 @@ struct WorkPipe {
     }
     __device__ __forceinline__ void rotate() { item = next; item_pos = next_pos; next = -1; }
     __device__ __forceinline__ bool current_needs_work() const { return item >= 0 && item_pos < empty_from; }
-    // up to kBulk proven-empty items per cursor claim
-    __device__ __forceinline__ int claim_empty(int* items, int max_items, int lane) {
-        int base = 0;
-        if (lane == 0) base = (int)(atomicAdd(cursor, (unsigned int)max_items) + gridDim.x * (blockDim.x >> 5));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        int cnt = total - base;
-        cnt = cnt < 0 ? 0 : (cnt > max_items ? max_items : cnt);
-        int mine = -1;
-        if (lane < cnt) mine = __ldg(queue + (size_t)(kClasses - 1) * cap + (base - empty_from + lane));
-        for (int e = 0; e < max_items; ++e) items[e] = __shfl_sync(0xffffffffu, mine, e);
-        return cnt;
-    }
 };
-constexpr int kBulk = 4;
 
 // Every warp that read the queue counters reports when it leaves; the last of them puts the control block back to
 // its between-calls state.  (`joiners` = warps whose first position is below the item count.)
@@ -561,7 +582,7 @@ __device__ unsigned int g_classes[kClasses];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
-template <bool BWD, int THREADS, int MINB>
+template <bool BWD, int THREADS, int MINB, int CPTMAX>      // CPTMAX: upper limit of L.cpt
 __global__ void __launch_bounds__(THREADS, MINB)
 implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, ImplicitParams P, int total_items,
                 Control* __restrict__ ctl, const int* __restrict__ queue, int cap,
@@ -571,20 +592,22 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
     __shared__ __align__(16) float tiles[THREADS / 32][kRedFloats];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& S = Ssh[warp];
-    // Persistent warps pull work items from a global cursor: item cost varies a lot with the culled z range, and a
-    // static assignment left the SMs idle at the tail.  The next item and its Sample are fetched while the current
-    // item is processed.  No block-level barrier anywhere.
+    // Persistent warps pull work items from a global cursor, most expensive first (plan kernel).  The next item and its
+    // Sample are fetched while the current item is processed.  No block-level barrier anywhere.
+    // Items the plan kernel has proven empty are never touched: depth is exactly 0 on all their columns (depth_out was
+    // cleared by the host), their loss sum |target| is part of the per-sample offset the plan kernel computed, their
+    // partial rows were zeroed there.  What this kernel accumulates as "loss" is |depth - t| - |t| per walked column.
 #ifdef SQ_TIMELINE
     const unsigned long long t_begin = gtime();
     unsigned long long t_last_fetch = t_begin, n_items = 0;
     if (BWD && blockIdx.x == 0 && threadIdx.x < kClasses) g_classes[threadIdx.x] = ctl->qcount[threadIdx.x];
 #endif
     WorkPipe wp;
-    wp.start(ctl, queue, cap, total_items, false, lane);
+    wp.start(ctl, queue, cap, total_items, true, lane);
     {
         SampleFetch pre;
-        if (wp.current_needs_work()) pre.fetch(samples + L.sample_of(wp.item), lane);
-        while (wp.current_needs_work()) {
+        if (wp.item >= 0) pre.fetch(samples + L.sample_of(wp.item), lane);
+        while (wp.item >= 0) {
 #ifdef SQ_TIMELINE
             t_last_fetch = gtime(); ++n_items;
 #endif
@@ -593,18 +616,17 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
             pre.commit(&S, lane);
 
             // Per-thread sums of the item live in the warp's shared-memory tile (the layout the final reduction reads),
-            // not in 18 registers: they are touched once per non-empty column, the registers buy a fifth block per SM.
+            // not in 18 registers: they are touched once per non-empty column.
             float loss_sum = 0.f;
             bool folded = false;
             ColIter it;
             it.init(L, chunk, lane);
-            // the item's target pixels: all loads issued up front (they miss to HBM; most column groups turn out empty
-            // and would otherwise do nothing but wait for their pixel)
-            float tvs[SQ_MAX_CPT];
+            // the item's target pixels: loads issued up front (they miss to HBM), used after the z walks
+            float tvs[CPTMAX];
             {
                 ColIter pt = it;
 #pragma unroll
-                for (int k = 0; k < SQ_MAX_CPT; ++k) {
+                for (int k = 0; k < CPTMAX; ++k) {
                     tvs[k] = 0.f;
                     if (target && k < L.cpt) {
                         if (pt.valid(L)) tvs[k] = __ldg(target + (size_t)b * tstride + row_off[g.n - 1 - pt.ib] + col_off[pt.ia]);
@@ -620,23 +642,17 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
                 float tv = tvs[0];                             // select, not an indexed load: tvs stays in registers
 #pragma unroll
-                for (int q = 1; q < SQ_MAX_CPT; ++q) tv = k == q ? tvs[q] : tv;
+                for (int q = 1; q < CPTMAX; ++q) tv = k == q ? tvs[q] : tv;
                 it.next(L);
-                // which planes can hold occupancy: decided from the fp32 base; most warp column groups are empty and
-                // never need the exact (fp64) one
+                // which planes can hold occupancy: decided from the fp32 base; the exact (fp64) one is formed only for
+                // groups that have some
                 float b32[3];
                 column_base_f32(S, g, valid ? ia : 0, valid ? ib : 0, b32);
                 int c_lo, c_hi;
                 column_range(S, g, P.bound, b32, c_lo, c_hi);
                 if (!valid) { c_lo = 0; c_hi = -1; }           // masked lanes do not widen the warp's range
                 warp_range(g.n, c_lo, c_hi);
-                if (c_hi < c_lo) {                             // warp-uniform: no occupancy anywhere, depth is exactly 0
-                    if (valid) {
-                        if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = 0.f;
-                        loss_sum += fabsf(tv);
-                    }
-                    continue;
-                }
+                if (c_hi < c_lo) continue;                     // warp-uniform: no occupancy anywhere, depth is exactly 0
                 float bh[3], bl[3], cg[11], dxy[2];
                 column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
                 float depth;
@@ -652,7 +668,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
                     if (target) {
                         const float diff = depth - tv;
-                        loss_sum += fabsf(diff);
+                        loss_sum += fabsf(diff) - fabsf(tv);
                         if (BWD && diff != 0.f) {
                             float v[kRedStride];
                             Acc acc;
@@ -668,7 +684,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
             }
             if (target) {
                 float* row = partials + ((size_t)b * L.rows_per_sample + chunk) * kAccN;
-                if (!__any_sync(0xffffffffu, loss_sum != 0.f)) {          // zero loss => zero gradient
+                if (!__any_sync(0xffffffffu, loss_sum != 0.f || folded)) {
                     if (lane < kAccN) row[lane] = 0.f;
                 } else {
                     if (!folded) {
@@ -681,52 +697,6 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 }
             }
             wp.rotate();
-        }
-    }
-    // Items proven empty by the plan kernel: depth is exactly 0 on every column, so the loss is sum |target| and there
-    // is no gradient.  No Sample, no geometry; kBulk items per cursor claim, all their pixel loads in flight together.
-    if (wp.item >= 0) {
-        int items[kBulk];
-        int cnt = 1;
-        items[0] = wp.item;
-#pragma unroll
-        for (int e = 1; e < kBulk; ++e) items[e] = -1;
-        while (cnt > 0) {
-#ifdef SQ_TIMELINE
-            t_last_fetch = gtime(); n_items += cnt;
-#endif
-            float sum[kBulk];
-            ColIter its[kBulk];
-            int bs[kBulk];
-#pragma unroll
-            for (int e = 0; e < kBulk; ++e) {
-                sum[e] = 0.f;
-                int chunk = 0;
-                bs[e] = 0;
-                if (e < cnt) L.split(items[e], bs[e], chunk);
-                its[e].init(L, chunk, lane);
-            }
-            for (int k = 0; k < L.cpt; ++k) {
-#pragma unroll
-                for (int e = 0; e < kBulk; ++e) {
-                    if (e < cnt && its[e].valid(L)) {
-                        const int row = g.n - 1 - its[e].ib, col = its[e].ia;
-                        if (target) sum[e] += fabsf(__ldg(target + (size_t)bs[e] * tstride + row_off[row] + col_off[col]));
-                        if (depth_out) depth_out[((size_t)bs[e] * g.n + row) * g.n + col] = 0.f;
-                    }
-                    its[e].next(L);
-                }
-            }
-            if (target) {
-#pragma unroll
-                for (int e = 0; e < kBulk; ++e) {
-                    if (e < cnt) {
-                        const float t = warp_sum(sum[e]);
-                        if (lane < kAccN) partials[(size_t)items[e] * kAccN + lane] = lane == kAccN - 1 ? t : 0.f;
-                    }
-                }
-            }
-            cnt = wp.claim_empty(items, kBulk, lane);
         }
     }
     retire(ctl, wp.joined, total_items, lane);
@@ -896,7 +866,8 @@ __global__ void __launch_bounds__(32)
 finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int items_per_sample,
                 const float* __restrict__ partials, double loss_norm, double grad_scale,
                 int dtype, void* __restrict__ grad, double* __restrict__ per_sample,
-                double* __restrict__ per_sample_user, double* __restrict__ loss_out, unsigned int* ticket) {
+                double* __restrict__ per_sample_user, double* __restrict__ loss_out, unsigned int* ticket,
+                const double* __restrict__ loss_offset) {
     const int b = blockIdx.x, lane = threadIdx.x;
     __shared__ double acc[kAccN];
     __shared__ double part[32][kAccN + 1];
@@ -922,7 +893,7 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
     __syncwarp();
     if (lane == 0) {
         const SampleFull& S = samples[b];
-        double ls = acc[17] * loss_norm;
+        double ls = (acc[17] + (loss_offset ? loss_offset[b] : 0.0)) * loss_norm;   // ImplicitLoss: + sum |target|
         double vol = 1.0;
         if (KIND == FIN_LSQ) { vol = S.a[0] * S.a[1] * S.a[2]; ls *= vol; }
         per_sample[b] = ls;
@@ -1038,17 +1009,23 @@ int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid
 }
 
 // plan kernel of a column-kernel call: Samples, per-sample counters, cost-class queues
+struct PlanTarget { const float* target; long long tstride; const int* row_off; const int* col_off; };
+
 int launch_plan(const void* params_a, const void* params_b, int dtype, int batch, bool clamp, const Grid& g,
                 const Layout& L, float bound, const Scratch& s, unsigned long long* counts, float* zero_rows,
-                cudaStream_t st) {
+                const PlanTarget* pt, cudaStream_t st) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
     int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
     if (params_b)
         plan_kernel<2><<<batch, kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, g, L, bound, s.tru, s.pred,
-                                                       s.ctl, counts, queue, s.queue_cap, zero_rows);
+                                                       s.ctl, counts, queue, s.queue_cap, zero_rows, nullptr, 0, nullptr, nullptr,
+                                                       nullptr);
     else
         plan_kernel<1><<<batch, kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, g, L, bound, s.pred, nullptr,
-                                                       s.ctl, counts, queue, s.queue_cap, zero_rows);
+                                                       s.ctl, counts, queue, s.queue_cap, zero_rows,
+                                                       pt ? pt->target : nullptr, pt ? pt->tstride : 0,
+                                                       pt ? pt->row_off : nullptr, pt ? pt->col_off : nullptr,
+                                                       pt ? s.tv_sum : nullptr);
     return (int)cudaGetLastError();
 }
 
@@ -1102,7 +1079,11 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, grad_pred ? SQ_IMPB_CPT : SQ_IMPF_CPT);
     const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, implicit_cull_bound(sharpness * kLog2e)};
-    rc = launch_plan(pred, nullptr, pred_dtype, batch, true, g, L, P.bound, s, nullptr, nullptr, st);
+    if (depth_out)      // the column kernel writes the depth only where a column group can hold occupancy
+        SQ_TRY(cudaMemsetAsync(depth_out, 0, sizeof(float) * (size_t)batch * n * n, st));
+    const PlanTarget pt{target, target_stride_b, row_off, col_off};
+    rc = launch_plan(pred, nullptr, pred_dtype, batch, true, g, L, P.bound, s, nullptr, target ? s.partials : nullptr,
+                     target ? &pt : nullptr, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
@@ -1110,12 +1091,12 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
         ColumnKernelTimer timer(st);
         if (grad_pred) {
             const int blocks = persistent_blocks(items, SQ_IMPB_THREADS / 32, SQ_IMPB_MINB);
-            implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB><<<blocks, SQ_IMPB_THREADS, 0, st>>>(
+            implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB, SQ_IMPB_CPT><<<blocks, SQ_IMPB_THREADS, 0, st>>>(
                 s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off, s.partials,
                 depth_out);
         } else {
             const int blocks = persistent_blocks(items, SQ_IMPF_THREADS / 32, SQ_IMPF_MINB);
-            implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB><<<blocks, SQ_IMPF_THREADS, 0, st>>>(
+            implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB, SQ_IMPF_CPT><<<blocks, SQ_IMPF_THREADS, 0, st>>>(
                 s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off, s.partials,
                 depth_out);
         }
@@ -1125,7 +1106,7 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
         const double nn = (double)n * n;
         finalize_kernel<FIN_IMPLICIT><<<batch, 32, 0, st>>>(
             s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn, -(double)sharpness * (double)tau / (nn * n * (double)batch),
-            pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket);
+            pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket, s.tv_sum);
         SQ_TRY(cudaGetLastError());
     }
     return 0;
@@ -1142,7 +1123,7 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, SQ_EXP_CPT);
     const float kl = sharpness * kLog2e, bound = cull_bound_bits(kl, 24.0f);
-    rc = launch_plan(true_params, pred, params_dtype, batch, true, g, L, bound, s, nullptr, s.partials, st);
+    rc = launch_plan(true_params, pred, params_dtype, batch, true, g, L, bound, s, nullptr, s.partials, nullptr, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
@@ -1157,7 +1138,7 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     finalize_kernel<FIN_EXPLICIT><<<batch, 32, 0, st>>>(
         s.pred, g, batch, L.rows_per_sample, s.partials, (double)mult / n3,
         2.0 * (double)sharpness * (double)mult / (n3 * (double)batch), params_dtype, grad_pred, s.per_sample,
-        per_sample, loss_out, &s.ctl->ticket);
+        per_sample, loss_out, &s.ctl->ticket, nullptr);
     SQ_TRY(cudaGetLastError());
     return 0;
 }
@@ -1172,7 +1153,7 @@ int sq_iou_counts(const void* true_params, const void* pred, int params_dtype, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, SQ_IOU_CPT);
-    rc = launch_plan(true_params, pred, params_dtype, batch, false, g, L, kIoUBound, s, s.counts, nullptr, st);
+    rc = launch_plan(true_params, pred, params_dtype, batch, false, g, L, kIoUBound, s, s.counts, nullptr, nullptr, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
@@ -1204,7 +1185,8 @@ int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_siz
     else lsq_kernel<false><<<batch * ips, kThreads, 0, st>>>(s.pred, R, ips, target, target_stride_b, row_off, col_off, s.partials);
     SQ_TRY(cudaGetLastError());
     finalize_kernel<FIN_LSQ><<<batch, 32, 0, st>>>(s.pred, g, batch, ips, s.partials, 1.0, 2.0 / (double)batch,
-                                                   pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket);
+                                                   pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket,
+                                                   nullptr);
     SQ_TRY(cudaGetLastError());
     return 0;
 }
