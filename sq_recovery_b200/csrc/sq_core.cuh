@@ -139,6 +139,7 @@ struct Sample {
 struct SampleFull : Sample {
     double M[9];              // un-scaled rotation
     double a[3], e[2], q[4];
+    double ia[3];             // 1 / a
     float mask[8];            // clamp sub-gradient masks for a(3), e(2), t(3): 1 inside or on the boundary, else 0
 };
 
@@ -172,6 +173,7 @@ SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, SampleFull& S
     S.M[6] = txz - twy;         S.M[7] = tyz + twx;         S.M[8] = 1.0 - (txx + tyy);
     for (int i = 0; i < 3; ++i) {
         const double ia = 1.0 / S.a[i];
+        S.ia[i] = ia;
         for (int j = 0; j < 3; ++j) S.Ms[3 * i + j] = S.M[3 * i + j] * ia;
         split2(S.Ms[3 * i + 2] * g.step, S.dh[i], S.dl[i]);
         S.idh[i] = 1.0f / S.dh[i];
@@ -338,12 +340,12 @@ SQ_HD void finalize_sample(const SampleFull& S, const Grid& g, const double* acc
     const double* gs = acc; const double* gm = acc + 3; const double* wa = acc + 12; const double* ge = acc + 15;
     double gM[9];
     for (int i = 0; i < 3; ++i) {
-        const double ia = 1.0 / S.a[i];
+        const double ia = S.ia[i];
         gM[3 * i + 0] = 2.0 * ia * gm[3 * i + 0];
         gM[3 * i + 1] = 2.0 * ia * gm[3 * i + 1];
         gM[3 * i + 2] = 2.0 * ia * (z_is_index ? g.step * gm[3 * i + 2] - S.t[2] * gs[i] : gm[3 * i + 2]);
     }
-    for (int i = 0; i < 3; ++i) grad12[i] = -2.0 * wa[i] / S.a[i] * S.mask[i] * scale;
+    for (int i = 0; i < 3; ++i) grad12[i] = -2.0 * wa[i] * S.ia[i] * S.mask[i] * scale;
     grad12[3] = kLn2 * ge[0] * S.mask[3] * scale;
     grad12[4] = kLn2 * ge[1] * S.mask[4] * scale;
     for (int j = 0; j < 3; ++j) {

@@ -138,7 +138,7 @@ struct ColIter {
 // kernel sorts them into kClasses cost classes, one queue per class.  Class k holds items whose estimated number of
 // z planes is in (max / 2^(k+1), max / 2^k]; the last class holds items estimated empty.
 constexpr int kClasses = 8;
-constexpr int kPlanThreads = 256;
+constexpr int kPlanThreads = 512;
 constexpr int kPlanMaxItems = 8192;      // items per sample the plan kernel can classify (more: index order)
 
 // First 256 bytes of every scratch buffer.  qcount and retired must be ZERO when a call starts: sq_scratch_init()
@@ -201,6 +201,10 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
 }
 
 // ------------------------------------------------------------------------------------------------ prep / plan
+#ifdef SQ_TIMELINE     // tools/timeline.py
+__device__ unsigned long long g_plan_ts[16];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 constexpr int kSampleWords = (int)(sizeof(Sample) / 4);          // the part the column kernels keep per warp
 constexpr int kFullWords = (int)(sizeof(SampleFull) / 4);        // the record in HBM
 static_assert(sizeof(Sample) % 8 == 0 && sizeof(SampleFull) % 8 == 0, "Sample records must be word-copyable");
@@ -289,6 +293,13 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
     __shared__ unsigned int ccnt[kClasses], cbase[kClasses];
     __shared__ double tv_part[kPlanThreads / 32];
     const int b = blockIdx.x;
+#ifdef SQ_TIMELINE
+    unsigned long long ts[6]; int nts = 0;
+#define SQ_STAMP() do { if (nts < 6) ts[nts++] = gtime(); } while (0)
+#else
+#define SQ_STAMP() do { } while (0)
+#endif
+    SQ_STAMP();
     if (threadIdx.x < kClasses) ccnt[threadIdx.x] = 0u;
     if (threadIdx.x == 64) {
         if (b == 0) { ctl->ticket = 0u; ctl->cursor = 0u; }
@@ -299,6 +310,7 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
         double p[12];
         load_params(w == 0 ? params_a : params_b, dtype, b, p);
         prep_sample(p, clamp != 0, g, Ssh[w]);
+        SQ_STAMP();
     }
     // ImplicitLoss: sum |target| over the sample's n x n pixels, by the warps that are not busy with the fp64 prep (it
     // hides behind it).  The column kernel then only adds |depth - t| - |t| for the columns it actually walks, so
@@ -310,22 +322,29 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
             const float* img = target + (size_t)b * tstride;
             int i = t;
-            for (; i + 3 * T < npix; i += 4 * T) {         // four independent loads in flight per thread
-                const int i1 = i + T, i2 = i + 2 * T, i3 = i + 3 * T;
-                const float v0 = __ldg(img + row_off[i / g.n] + col_off[i % g.n]);
-                const float v1 = __ldg(img + row_off[i1 / g.n] + col_off[i1 % g.n]);
-                const float v2 = __ldg(img + row_off[i2 / g.n] + col_off[i2 % g.n]);
-                const float v3 = __ldg(img + row_off[i3 / g.n] + col_off[i3 % g.n]);
-                acc0 += fabsf(v0); acc1 += fabsf(v1); acc2 += fabsf(v2); acc3 += fabsf(v3);
+            for (; i + 7 * T < npix; i += 8 * T) {         // eight independent loads in flight per thread (they miss to HBM)
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int iu = i + u * T; v[u] = __ldg(img + row_off[iu / g.n] + col_off[iu % g.n]); }
+                acc0 += fabsf(v[0]) + fabsf(v[4]); acc1 += fabsf(v[1]) + fabsf(v[5]);
+                acc2 += fabsf(v[2]) + fabsf(v[6]); acc3 += fabsf(v[3]) + fabsf(v[7]);
             }
-            for (; i < npix; i += T) acc0 += fabsf(__ldg(img + row_off[i / g.n] + col_off[i % g.n]));
+            {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int iu = i + u * T; v[u] = iu < npix ? __ldg(img + row_off[iu / g.n] + col_off[iu % g.n]) : 0.f; }
+                acc0 += fabsf(v[0]) + fabsf(v[4]); acc1 += fabsf(v[1]) + fabsf(v[5]);
+                acc2 += fabsf(v[2]) + fabsf(v[6]); acc3 += fabsf(v[3]) + fabsf(v[7]);
+            }
             double d = (double)((acc0 + acc1) + (acc2 + acc3));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
             if (lane == 0) tv_part[warp] = d;
+            SQ_STAMP();
         }
     }
     __syncthreads();
+    SQ_STAMP();
     if (tv_sum && threadIdx.x == 0) {
         double d = 0.0;
         for (int w = NS; w < kPlanThreads / 32; ++w) d += tv_part[w];
@@ -357,6 +376,7 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
         atomicAdd(&ccnt[c], 1u);
     }
     __syncthreads();
+    SQ_STAMP();
     if (threadIdx.x < kClasses) {
         const unsigned int c = ccnt[threadIdx.x];
         cbase[threadIdx.x] = c ? atomicAdd(&ctl->qcount[threadIdx.x], c) : 0u;
@@ -368,6 +388,14 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
         const unsigned int r = atomicAdd(&ccnt[c], 1u);
         queue[(size_t)c * cap + cbase[c] + r] = b * J + j;
     }
+#ifdef SQ_TIMELINE
+    SQ_STAMP();
+    if (b == 7 && (threadIdx.x == 0 || threadIdx.x == 100)) {
+        const int o = threadIdx.x == 0 ? 0 : 8;
+        for (int i = 0; i < nts; ++i) g_plan_ts[o + i] = ts[i];
+        g_plan_ts[o + 7] = nts;
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
@@ -557,7 +585,6 @@ struct WorkPipe {
         return next >= 0 && next_pos < empty_from;         // true: an item that needs its Sample
     }
     __device__ __forceinline__ void rotate() { item = next; item_pos = next_pos; next = -1; }
-    __device__ __forceinline__ bool current_needs_work() const { return item >= 0 && item_pos < empty_from; }
 };
 
 // Every warp that read the queue counters reports when it leaves; the last of them puts the control block back to
@@ -579,7 +606,6 @@ __device__ __forceinline__ void retire(Control* ctl, bool joined, int total_item
 #ifdef SQ_TIMELINE     // tools/timeline.py: per-warp start / end timestamps and item counts of the implicit kernel
 __device__ unsigned long long g_timeline[3 * 8192];
 __device__ unsigned int g_classes[kClasses];
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
 template <bool BWD, int THREADS, int MINB, int CPTMAX>      // CPTMAX: upper limit of L.cpt
@@ -860,38 +886,49 @@ lsq_kernel(const SampleFull* __restrict__ samples, int R, int items_per_sample,
 // ------------------------------------------------------------------------------------------------ finalize
 enum { FIN_IMPLICIT = 0, FIN_EXPLICIT = 1, FIN_LSQ = 2 };
 
-// one warp per sample; the last block averages the batch
+// One block of kFinThreads per sample: every thread sums the partial rows r = t, t + kFinThreads, ... in fp64 (all loads
+// independent: one L2 round trip), a fixed-order tree (shuffles inside a warp, then the warps in index order) gives the
+// 18 totals, thread 0 applies the Jacobians.  The last block to arrive averages the batch in index order.  Fixed order
+// everywhere: results are bit-reproducible run to run.
+constexpr int kFinThreads = 128;
+
 template <int KIND>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kFinThreads)
 finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int items_per_sample,
                 const float* __restrict__ partials, double loss_norm, double grad_scale,
                 int dtype, void* __restrict__ grad, double* __restrict__ per_sample,
                 double* __restrict__ per_sample_user, double* __restrict__ loss_out, unsigned int* ticket,
                 const double* __restrict__ loss_offset) {
-    const int b = blockIdx.x, lane = threadIdx.x;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __shared__ double wpart[kFinThreads / 32][kAccN];
     __shared__ double acc[kAccN];
-    __shared__ double part[32][kAccN + 1];
-    {   // lane l sums rows l, l+32, ... (independent loads in flight), then a fixed-order sum over the 32 lanes
+    __shared__ unsigned int last;
+    {
         double s[kAccN];
 #pragma unroll
         for (int i = 0; i < kAccN; ++i) s[i] = 0.0;
         const float* base = partials + (size_t)b * items_per_sample * kAccN;
-        for (int j = lane; j < items_per_sample; j += 32) {
-            const float* p = base + (size_t)j * kAccN;
+        for (int j = t; j < items_per_sample; j += kFinThreads) {
+            const float2* p = reinterpret_cast<const float2*>(base + (size_t)j * kAccN);     // rows are 72 bytes: 8-aligned
 #pragma unroll
-            for (int i = 0; i < kAccN; ++i) s[i] += (double)p[i];
+            for (int i = 0; i < kAccN / 2; ++i) { const float2 v = __ldcg(p + i); s[2 * i] += (double)v.x; s[2 * i + 1] += (double)v.y; }
         }
 #pragma unroll
-        for (int i = 0; i < kAccN; ++i) part[lane][i] = s[i];
-        __syncwarp();
-        if (lane < kAccN) {
-            double t = 0.0;
-            for (int l = 0; l < 32; ++l) t += part[l][lane];
-            acc[lane] = t;
+        for (int i = 0; i < kAccN; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+            if (lane == 0) wpart[warp][i] = s[i];
         }
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    if (t < kAccN) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kFinThreads / 32; ++w) v += wpart[w][t];
+        acc[t] = v;
+    }
+    __syncthreads();
+    if (t == 0) {
         const SampleFull& S = samples[b];
         double ls = (acc[17] + (loss_offset ? loss_offset[b] : 0.0)) * loss_norm;   // ImplicitLoss: + sum |target|
         double vol = 1.0;
@@ -902,22 +939,21 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
             double gr[12];
             finalize_sample(S, g, acc, grad_scale * vol, KIND != FIN_LSQ, gr);
             if (KIND == FIN_LSQ)
-                for (int i = 0; i < 3; ++i) gr[i] += S.mask[i] * (vol / S.a[i]) * acc[17] / (double)batch;
+                for (int i = 0; i < 3; ++i) gr[i] += S.mask[i] * (vol * S.ia[i]) * acc[17] / (double)batch;
             for (int i = 0; i < 12; ++i) {
                 if (dtype == SQ_F64) static_cast<double*>(grad)[12 * (size_t)b + i] = gr[i];
                 else static_cast<float*>(grad)[12 * (size_t)b + i] = (float)gr[i];
             }
         }
+        __threadfence();
+        last = atomicAdd(ticket, 1u);
     }
+    __syncthreads();
     // batch mean by the last block to arrive, in index order
-    __shared__ unsigned int last;
-    __syncwarp();
-    if (lane == 0) { __threadfence(); last = atomicAdd(ticket, 1u); }
-    __syncwarp();
-    if (last == (unsigned)batch - 1u) {
+    if (last == (unsigned)batch - 1u && warp == 0) {
         __threadfence();
         double s = 0.0;
-        for (int i = lane; i < batch; i += 32) s += *((volatile double*)(per_sample + i));
+        for (int i = lane; i < batch; i += 32) s += __ldcg(per_sample + i);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0 && loss_out) *loss_out = s / (double)batch;
@@ -1046,6 +1082,9 @@ int sq_device_sm_count(int device, int* sm_count) {
 int sq_debug_timeline(unsigned long long* host_out, int n) {
     return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * 3 * (size_t)n);
 }
+int sq_debug_plan(unsigned long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_plan_ts, sizeof(unsigned long long) * 16);
+}
 int sq_debug_classes(unsigned int* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, g_classes, sizeof(unsigned int) * kClasses);
 }
@@ -1104,7 +1143,7 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
     SQ_TRY(cudaGetLastError());
     if (target) {
         const double nn = (double)n * n;
-        finalize_kernel<FIN_IMPLICIT><<<batch, 32, 0, st>>>(
+        finalize_kernel<FIN_IMPLICIT><<<batch, kFinThreads, 0, st>>>(
             s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn, -(double)sharpness * (double)tau / (nn * n * (double)batch),
             pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket, s.tv_sum);
         SQ_TRY(cudaGetLastError());
@@ -1135,7 +1174,7 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     }
     SQ_TRY(cudaGetLastError());
     const double n3 = (double)n * n * n;
-    finalize_kernel<FIN_EXPLICIT><<<batch, 32, 0, st>>>(
+    finalize_kernel<FIN_EXPLICIT><<<batch, kFinThreads, 0, st>>>(
         s.pred, g, batch, L.rows_per_sample, s.partials, (double)mult / n3,
         2.0 * (double)sharpness * (double)mult / (n3 * (double)batch), params_dtype, grad_pred, s.per_sample,
         per_sample, loss_out, &s.ctl->ticket, nullptr);
@@ -1184,7 +1223,7 @@ int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_siz
     if (grad_pred) lsq_kernel<true><<<batch * ips, kThreads, 0, st>>>(s.pred, R, ips, target, target_stride_b, row_off, col_off, s.partials);
     else lsq_kernel<false><<<batch * ips, kThreads, 0, st>>>(s.pred, R, ips, target, target_stride_b, row_off, col_off, s.partials);
     SQ_TRY(cudaGetLastError());
-    finalize_kernel<FIN_LSQ><<<batch, 32, 0, st>>>(s.pred, g, batch, ips, s.partials, 1.0, 2.0 / (double)batch,
+    finalize_kernel<FIN_LSQ><<<batch, kFinThreads, 0, st>>>(s.pred, g, batch, ips, s.partials, 1.0, 2.0 / (double)batch,
                                                    pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket,
                                                    nullptr);
     SQ_TRY(cudaGetLastError());

@@ -66,3 +66,10 @@ cls = np.zeros(8, dtype=np.uint32)
 h.sq_debug_classes.argtypes = [ctypes.c_void_p]
 if h.sq_debug_classes(cls.ctypes.data_as(ctypes.c_void_p)) == 0:
     print("items per cost class (0 = longest ... 7 = certified empty):", cls.tolist())
+
+pl = np.zeros(16, dtype=np.uint64)
+h.sq_debug_plan.argtypes = [ctypes.c_void_p]
+if h.sq_debug_plan(pl.ctypes.data_as(ctypes.c_void_p)) == 0:
+    for o, who in ((0, "thread 0 (prep)"), (8, "thread 100 (pixel sum)")):
+        n = int(pl[o + 7]); t = (pl[o:o + n] - pl[o]).astype(np.int64) / 1e3
+        print(f"plan kernel block 7, {who}: stage stamps (us) {t.round(2).tolist()}")
