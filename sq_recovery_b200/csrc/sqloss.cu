@@ -662,7 +662,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
             }
 #pragma unroll 1
             for (int k = 0; k < L.cpt; ++k) {
+#ifdef SQ_EARLY_CLAIM
                 if (k == L.cpt - 1 && wp.claim(lane)) pre.fetch(samples + L.sample_of(wp.next), lane);
+#endif
                 const int ia = it.ia, ib = it.ib;
                 const bool valid = it.valid(L);
                 const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
@@ -678,17 +680,29 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 column_range(S, g, P.bound, b32, c_lo, c_hi);
                 if (!valid) { c_lo = 0; c_hi = -1; }           // masked lanes do not widen the warp's range
                 warp_range(g.n, c_lo, c_hi);
-                if (c_hi < c_lo) continue;                     // warp-uniform: no occupancy anywhere, depth is exactly 0
+                if (c_hi < c_lo) {                             // warp-uniform: no occupancy anywhere, depth is exactly 0
+#ifndef SQ_EARLY_CLAIM
+                    if (k == L.cpt - 1 && wp.claim(lane)) pre.fetch(samples + L.sample_of(wp.next), lane);
+#endif
+                    continue;
+                }
                 float bh[3], bl[3], cg[11], dxy[2];
                 column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
                 float depth;
-#ifndef SQ_FIXHOIST      // measured: no gain once empty column groups leave early (profiles/tune_r01.txt)
+#ifdef SQ_NO_FIXHOIST    // hoisting the exact-zero fix-up out of the walk: -3 % kernel time (profiles/tune_r01.txt)
                 depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
 #else
                 if (__any_sync(0xffffffffu, column_zero_possible(S, bh)))
                     depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
                 else
                     depth = implicit_column<BWD, false>(S, g, P, bh, bl, c_lo, c_hi, cg);
+#endif
+#ifndef SQ_EARLY_CLAIM
+                // Claim the next item only now, after the walk: the cursor -> queue -> Sample chain then stalls this warp
+                // for ~1300 cycles, but the kernel is bound by instruction dispatch and the other warps of the scheduler
+                // fill the gap; an item claimed at the start of a long walk, on the other hand, is work no idle warp can
+                // take -- during the end-game that was the tail of the kernel.
+                if (k == L.cpt - 1 && wp.claim(lane)) pre.fetch(samples + L.sample_of(wp.next), lane);
 #endif
                 if (valid) {
                     if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
@@ -756,7 +770,6 @@ explicit_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict
             L.split(item, b, chunk);
             pre_t.commit(&St, lane);
             pre_p.commit(&Sp, lane);
-            if (wp.claim(lane)) { pre_t.fetch(tru + L.sample_of(wp.next), lane); pre_p.fetch(pred + L.sample_of(wp.next), lane); }
             Acc acc;
             acc_zero(acc);
             ColIter it;
@@ -791,6 +804,8 @@ explicit_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict
                     }
                 }
             }
+            // claimed after the walk, not before it: see implicit_kernel
+            if (wp.claim(lane)) { pre_t.fetch(tru + L.sample_of(wp.next), lane); pre_p.fetch(pred + L.sample_of(wp.next), lane); }
             warp_reduce_store(acc, tiles[warp], partials + (size_t)item * kAccN, acc.loss != 0.f);
             wp.rotate();
         }
@@ -817,7 +832,6 @@ iou_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict__ pr
             L.split(item, b, chunk);
             pre_t.commit(&St, lane);
             pre_p.commit(&Sp, lane);
-            if (wp.claim(lane)) { pre_t.fetch(tru + L.sample_of(wp.next), lane); pre_p.fetch(pred + L.sample_of(wp.next), lane); }
             unsigned inter = 0, uni = 0;
             ColIter it;
             it.init(L, chunk, lane);
@@ -840,6 +854,7 @@ iou_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict__ pr
                 iou_column(St, Sp, tru + b, pred + b, g, ia, ib, bht, blt, bhp, blp, rt, rp, i, u);
                 if (valid) { inter += i; uni += u; }
             }
+            if (wp.claim(lane)) { pre_t.fetch(tru + L.sample_of(wp.next), lane); pre_p.fetch(pred + L.sample_of(wp.next), lane); }
             inter = __reduce_add_sync(0xffffffffu, inter);
             uni = __reduce_add_sync(0xffffffffu, uni);
             if (lane == 0 && (inter | uni)) {                 // integer atomics: order-independent, exact
