@@ -342,3 +342,98 @@ def test_host_entry_points(dev, S):
     i2, u2 = S.IoUAccuracy(R, dev).counts(true.to(dev), pred.to(dev))
     assert np.array_equal(i, i2.cpu().numpy()) and np.array_equal(u, u2.cpu().numpy())
     ctx.close()
+
+
+# ------------------------------------------------------------------ work queues, scratch contract, culling corner cases
+def _scratch_control_words(S, dev):
+    from sq_recovery_b200 import functional as Fn
+    torch.cuda.synchronize()
+    return [buf[:256].view(torch.int32).cpu() for key, buf in Fn._scratch.items() if key[0] == dev.index]
+
+
+def test_scratch_is_reusable_and_left_clean(dev, S):
+    """include/sqloss.h scratch contract: one buffer serves any sequence of calls (different losses, batch and grid
+    sizes) and every call leaves the queue counters of the control block zero again."""
+    rs = np.random.RandomState(5)
+    cases = [(7, 16), (33, 32), (2, 64), (64, 24), (1, 20)]
+    first = {}
+    for rep in range(2):
+        for B, R in cases:
+            true = O.random_params(B, 100 + B).to(dev)
+            pred = O.perturbed_params(O.random_params(B, 100 + B), 3).to(dev)
+            img = S.ImplicitLoss(64, dev, 1.5, 260).depth_projection(true).unsqueeze(1)
+            out = []
+            p = pred.clone().requires_grad_(True)
+            l = S.ImplicitLoss(R, dev, 1.5, 260)(img, p); l.backward(); out += [l.item(), p.grad.clone()]
+            p = pred.clone().requires_grad_(True)
+            l = S.ExplicitLoss(R, dev)(true, p); l.backward(); out += [l.item(), p.grad.clone()]
+            out += [t.clone() for t in S.IoUAccuracy(R, dev).counts(true, pred)]
+            p = pred.clone().requires_grad_(True)
+            l = S.LeastSquares(R, dev)(img, p); l.backward(); out += [l.item(), p.grad.clone()]
+            for w in _scratch_control_words(S, dev):
+                assert int(w[2]) == 0 and not w[4:12].any(), "queue counters not left clean"
+            if rep == 0:
+                first[(B, R)] = out
+            else:                                                       # same inputs, dirty-then-cleaned scratch: same bits
+                for a, b in zip(first[(B, R)], out):
+                    assert (a == b) if isinstance(a, float) else torch.equal(a, b)
+
+
+def test_objects_off_the_grid(dev, S):
+    """Samples whose superquadric lies (partly or entirely) outside the unit cube: the plan kernel proves most or all
+    work items empty; loss and gradients must still match the oracle (all-empty: loss = mean |target|, zero gradient)."""
+    B, R = 6, 32
+    pred = O.random_params(B, 11)
+    pred[0, 5:8] = torch.tensor([3.0, 0.5, 0.5])        # clamped to t = (1, .5, .5): half outside
+    pred[1, 5:8] = torch.tensor([-2.0, -2.0, -2.0])     # clamped to the corner (0, 0, 0)
+    pred[2, 0:3] = 0.05                                   # smallest allowed size
+    pred[3, 5:8] = torch.tensor([0.5, 0.5, 5.0])        # at the camera plane
+    true = O.random_params(B, 12)
+    img = S.ImplicitLoss(64, dev, 1.5, 260).depth_projection(true.to(dev)).unsqueeze(1)
+    oc = O.ImplicitLoss(R, "cpu", 1.5, 260)
+    po = pred.clone().requires_grad_(True)
+    ref = oc(img.cpu(), po); ref.backward()
+    l, g = run(S.ImplicitLoss(R, dev, 1.5, 260), img, pred, dev)
+    check(l, g, ref.item(), po.grad.double().numpy(), what="off-grid implicit", keep=unambiguous(oc, img.cpu(), pred))
+    pe = pred.clone().requires_grad_(True)
+    refe = O.ExplicitLoss(R, "cpu")(true, pe); refe.backward()
+    l, g = run(S.ExplicitLoss(R, dev), true, pred, dev)
+    check(l, g, refe.item(), pe.grad.double().numpy(), what="off-grid explicit")
+    i, u = S.IoUAccuracy(R, dev).counts(true.to(dev), pred.to(dev))
+    ri, ru = O.IoUAccuracy(R, "cpu").counts(true, pred)
+    assert torch.equal(i.cpu(), ri) and torch.equal(u.cpu(), ru)
+    # the loss assembled from the plan kernel's sum |target| and the column kernel's per-column differences equals the
+    # mean absolute difference to the kernel's own render (most columns of a tiny object are never walked)
+    tiny = pred[:2].clone().to(dev)
+    tiny[:, 0:3] = 0.05
+    crit = S.ImplicitLoss(R, dev, 1.5, 260)
+    blank = torch.full((2, 1, 64, 64), 0.25, device=dev)
+    d = crit.depth_projection(tiny)
+    assert d[:, :2, :].abs().max().item() == 0.0          # image border: proven empty, exactly 0
+    l = crit(blank, tiny)
+    expect = (0.25 - d.double()).abs().mean().item()
+    assert abs(l.item() - expect) <= 1e-6 * expect
+
+
+def test_render_256_and_index_order_path(dev, S):
+    """depth_projection at the data-generation size (R = 256) against the oracle, and a grid so large that a
+    sample has more work items than the plan kernel classifies (index-order hand-out, no queues), checked against a
+    render assembled from the full occupancy field (sq_field) with torch ops."""
+    p = O.random_params(2, 31)
+    d = S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(p.to(dev))
+    with torch.no_grad():
+        ref = O.ImplicitLoss(256, "cpu", 1.5, 260).depth_projection(p)
+    err = (d.double().cpu() - ref).abs()                 # fp32 kernel vs fp64: grazing pixels see k-amplified rounding
+    assert err.max().item() < 3e-5 and err.mean().item() < 3e-7, (err.max().item(), err.mean().item())
+    R = 520                                              # 520^2 / 32 = 8450 items per sample > 8192
+    crit = S.ImplicitLoss(R, dev, 1.0, 100)
+    q = O.random_params(1, 32).to(dev)
+    d = crit.depth_projection(q)
+    from sq_recovery_b200 import functional as Fn
+    occ = Fn.field(q, R, 1.0 / (R - 1), 1e-4, 1, 100.0)[0].double()             # (x, y, z) occupancy
+    cs = torch.cumsum(torch.flip(occ, dims=[2]), dim=2)
+    depth = 1.0 - torch.exp(-1.0 * cs).sum(dim=2) / R
+    img = depth.permute(1, 0).flip(0)                    # classes.py:279
+    assert (d[0].double() - img).abs().max().item() < 1e-5
+    for w in _scratch_control_words(S, dev):
+        assert int(w[2]) == 0 and not w[4:12].any()
