@@ -302,6 +302,17 @@ def run_gpu(args):
         issued = ncu["xu_warp_inst_per_launch"] * 32 if ncu else None
         achieved = issued / (kernel_ms * 1e-3) / 1e9 if issued else None
         dense_equiv = pts * MUFU_PER_POINT / (kernel_ms * 1e-3) / 1e9
+        # Dispatch model measured with csrc/peaks.cu on this GPU (profiles/peaks_r01.json, EX2_FFMA{4,6,8}): per
+        # scheduler a MUFU warp-instruction costs ~6 issue cycles and any other one ~0.9, and the XU itself 8 per MUFU:
+        # t >= max(8 Nm, 6 Nm + 0.9 No) / (4 schedulers x SMs x clock).  This is the bound the kernel actually runs into.
+        dispatch = None
+        if ncu and ncu.get("warp_inst_per_launch"):
+            nm, no = ncu["xu_warp_inst_per_launch"], ncu["warp_inst_per_launch"] - ncu["xu_warp_inst_per_launch"]
+            cyc = max(8.0 * nm, 6.0 * nm + 0.9 * no) / (4 * peak["sms"])
+            t_us = cyc / clock
+            dispatch = {"mufu_warp_inst": nm, "other_warp_inst": no, "bound_us": t_us, "kernel_us": kernel_ms * 1e3,
+                        "frac": t_us / (kernel_ms * 1e3),
+                        "model": "max(8 Nm, 6 Nm + 0.9 No) issue cycles per scheduler (profiles/peaks_r01.json EX2_FFMA*)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -322,9 +333,11 @@ def run_gpu(args):
                          "traffic": ncu["dram_bytes_per_launch"] if ncu else None,
                          "kernel_ms": kernel_ms,
                          "how": "achieved = MUFU-pipe thread-ops the kernel ISSUES per launch (profiles/"
-                                "implicit_kernel_ncu_summary.json) / live CUDA-event kernel time; the kernel culls grid "
-                                "points whose occupancy is exactly 0 and evaluates F with 8 MUFU ops instead of 10, so "
-                                "issued ops are far fewer than the reference algorithm's 16 per grid point",
+                                "implicit_kernel_ncu_summary.json) / live CUDA-event kernel time (events around the launch: "
+                                "includes ~5 us of launch latency); the kernel skips grid points whose occupancy is below "
+                                "2^-40 (box + ellipsoid bounds) and evaluates F with 8 MUFU ops instead of 10, so issued ops "
+                                "are far fewer than the reference algorithm's 16 per grid point",
+                         "dispatch_bound": dispatch,
                          "reference_algorithm_equivalent": {"mufu_per_point": MUFU_PER_POINT, "achieved": dense_equiv,
                                                             "frac": dense_equiv / peak_gops},
                          "peak_source": f"{peak['source']}: {peak['mufu_per_clk_sm']:.2f} MUFU/clk/SM x {peak['sms']} SMs x "

@@ -276,11 +276,33 @@ struct Bwd {
     float ge[2];      // W F H2,  W F eG H1
 };
 
+// Option SQ_MERGED_RCP: the five reciprocals (1 + t1, 1 + t2, sx, sy, sz) from ONE MUFU.RCP of their product plus 12 multiplications:
+// on B200 a MUFU warp instruction costs ~6 issue cycles and an FMUL ~0.9 (profiles/peaks_r01.json), and the kernels are
+// bound by instruction dispatch.  The product cannot leave fp32 range: 1 + t is in [1, 2], and of the three
+// coordinates of a gradient-carrying point (F ~ 1) at most two are small, each at least ~1e-15 when not exactly 0.
+// Measured: no gain for the implicit kernel, 2.5 % slower for the explicit one (longer dependent chain) -> off.
 template <bool FIX = true>
 SQ_HD void point_backward(const Fwd& f, float W, Bwd& b) {
     const float WF = W * f.F;
-    const float r1 = rcp(1.0f + f.t1), s1 = f.t1 * r1;
-    const float r2 = rcp(1.0f + f.t2), s2 = f.t2 * r2;
+    float sx = f.sx, sy = f.sy, sz = f.sz;
+    bool zx = false, zy = false, zz = false;
+    if (FIX) {          // exact zeros: the fix-up replaces s^2 by a constant, so no gradient reaches s or a through that term
+        zx = (sx == 0.0f); zy = (sy == 0.0f); zz = (sz == 0.0f);
+        sx = zx ? 1.0f : sx; sy = zy ? 1.0f : sy; sz = zz ? 1.0f : sz;
+    }
+#ifdef SQ_MERGED_RCP
+    const float p1 = 1.0f + f.t1, p2 = 1.0f + f.t2;
+    const float pa = p1 * p2, pb = sx * sy, pc = pb * sz;
+    const float inv = rcp(pa * pc);
+    const float ia = inv * pc, ic = inv * pa;              // 1 / (p1 p2), 1 / (sx sy sz)
+    const float r1 = ia * p2, r2 = ia * p1;
+    const float ib = ic * sz;                              // 1 / (sx sy)
+    const float isx = ib * sy, isy = ib * sx, isz = ic * pb;
+#else
+    const float r1 = rcp(1.0f + f.t1), r2 = rcp(1.0f + f.t2);
+    const float isx = rcp(sx), isy = rcp(sy), isz = rcp(sz);
+#endif
+    const float s1 = f.t1 * r1, s2 = f.t2 * r2;
     const bool a_big = f.d1 >= 0.0f, e_big = f.d2 >= 0.0f;
     const float aD = a_big ? r1 : s1, bD = a_big ? s1 : r1;
     const float eG = e_big ? r2 : s2, cG = e_big ? s2 : r2;
@@ -289,19 +311,17 @@ SQ_HD void point_backward(const Fwd& f, float W, Bwd& b) {
     b.ge[0] = WF * fmaf(s2, fabsf(f.d2), f.h2);
     b.ge[1] = wxy * fmaf(s1, fabsf(f.d1), f.h1);
     if (FIX) {
-        // exact zeros: the fix-up replaces s^2 by a constant, so no gradient reaches s or a through that term
-        const bool zx = (f.sx == 0.0f), zy = (f.sy == 0.0f), zz = (f.sz == 0.0f);
         b.wa[0] = zx ? 0.0f : wx;
         b.wa[1] = zy ? 0.0f : wy;
         b.wa[2] = zz ? 0.0f : wz;
-        b.gs[0] = zx ? 0.0f : wx * rcp(f.sx);
-        b.gs[1] = zy ? 0.0f : wy * rcp(f.sy);
-        b.gs[2] = zz ? 0.0f : wz * rcp(f.sz);
+        b.gs[0] = zx ? 0.0f : wx * isx;
+        b.gs[1] = zy ? 0.0f : wy * isy;
+        b.gs[2] = zz ? 0.0f : wz * isz;
     } else {            // the caller knows no coordinate of this column can be exactly 0 (column_zero_possible)
         b.wa[0] = wx; b.wa[1] = wy; b.wa[2] = wz;
-        b.gs[0] = wx * rcp(f.sx);
-        b.gs[1] = wy * rcp(f.sy);
-        b.gs[2] = wz * rcp(f.sz);
+        b.gs[0] = wx * isx;
+        b.gs[1] = wy * isy;
+        b.gs[2] = wz * isz;
     }
 }
 

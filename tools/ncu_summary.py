@@ -45,6 +45,7 @@ for r in launches:
 n = len(per)
 summary = {"source": rep, "launches": n,
            "xu_warp_inst_per_launch": sum(p["xu_warp_inst"] for p in per) / n,
+           "warp_inst_per_launch": sum(p["warp_inst_executed"] for p in per) / n,
            "dram_bytes_per_launch": sum(p["dram_bytes"] for p in per) / n,
            "duration_us_under_ncu": sum(p["duration_us"] for p in per) / n,
            "per_launch": per}
