@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Synthetic dataset generator on the GPU: random superquadrics rendered with the ImplicitLoss soft
+projection at 256 x 256, stored in the layout torch/classes.py:58-63 reads -- dataset "sq" of shape (N, 1, 256, 256)
+float32 -- with one label row per image in the format torch/helpers.py:188-218 (parse_csv) parses:
+
+    name,a1,a2,a3,e1,e2,t1,t2,t3,qx,qy,qz,qw        a and t scaled by 255 (parse_csv divides them by 255)
+
+It stands in for the reference's closed-source data/scanner + gen_rand_rot.py pipeline in benchmarks (scanner's hard
+projection is not byte-reproducible: no source).  Pixel scale: rendered depth is in [0, 1); `--scale 255` writes the
+0..255 range cv2.imread gives the reference (classes.py:82-88).
+
+    python harness/make_dataset.py --n 4096 --out /tmp/sq_synth [--scale 255] [--seed 0]
+
+Writes <out>.h5 when h5py is importable, else <out>.npy, plus <out>.csv.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def label_rows(params: np.ndarray, names):
+    """params (N, 12) in the loss's units ([a | e | t | q], a and t in [0, 1]) -> csv lines for parse_csv."""
+    rows = []
+    for name, p in zip(names, np.asarray(params, dtype=np.float64)):
+        v = np.concatenate([p[0:3] * 255.0, p[3:5], p[5:8] * 255.0, p[8:12]])
+        rows.append(name + "," + ",".join(repr(float(x)) for x in v))
+    return rows
+
+
+def parse_rows(lines):
+    """What torch/helpers.py:188-218 makes of such lines (restated here for the round-trip test)."""
+    out = []
+    for line in lines:
+        if line == "":
+            continue
+        s = line.split(",")
+        vals = [float(s[i]) / 255.0 if i in (1, 2, 3, 6, 7, 8) else float(s[i]) for i in range(1, 9)]
+        vals += [float(s[i]) for i in range(-4, 0)]
+        out.append(np.array(vals, dtype=np.float32))
+    return out
+
+
+def render(params: torch.Tensor, dev, size=256, tau=1.5, sharpness=260.0, chunk=256) -> torch.Tensor:
+    import sq_recovery_b200 as S
+    crit = S.ImplicitLoss(size, dev, tau, sharpness)
+    out = torch.empty((params.shape[0], 1, size, size), dtype=torch.float32, device=dev)
+    for i in range(0, params.shape[0], chunk):
+        out[i:i + chunk, 0] = crit.depth_projection(params[i:i + chunk].to(dev))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--out", default="/tmp/sq_synth")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--scale", type=float, default=1.0)
+    args = ap.parse_args()
+    from oracle import sq_oracle as O                       # randsq / randquat distributions (visu.py:55-56)
+    dev = torch.device("cuda:0")
+    params = O.random_params(args.n, args.seed)
+    render(params[:min(args.n, 256)], dev)                  # warm-up: workspace allocation, module load
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    images = render(params, dev) * args.scale
+    t1.record(); torch.cuda.synchronize()
+    names = [f"synth/{i:06d}.bmp" for i in range(args.n)]
+    with open(args.out + ".csv", "w") as f:
+        f.write("\n".join(label_rows(params.numpy(), names)) + "\n")
+    arr = images.cpu().numpy()
+    try:
+        import h5py
+        with h5py.File(args.out + ".h5", "w") as h:
+            h.create_dataset("sq", data=arr, dtype="f")
+        where = args.out + ".h5"
+    except ImportError:
+        np.save(args.out + ".npy", arr)
+        where = args.out + ".npy (h5py not installed)"
+    ms = t0.elapsed_time(t1)
+    print(f"{args.n} images {arr.shape} -> {where}; labels -> {args.out}.csv; render {ms:.1f} ms "
+          f"({args.n * 256 ** 3 / ms / 1e6:.1f} Gpoints/s), {100 * float((arr > 0).mean()):.1f}% non-zero pixels")
+
+
+if __name__ == "__main__":
+    main()

@@ -437,3 +437,29 @@ def test_render_256_and_index_order_path(dev, S):
     assert (d[0].double() - img).abs().max().item() < 1e-5
     for w in _scratch_control_words(S, dev):
         assert int(w[2]) == 0 and not w[4:12].any()
+
+
+# ------------------------------------------------------------------ harnesses
+def test_batched_descent_follows_the_oracle(dev, S):
+    """harness/optimize.py (visu.py:120-186 for many SQs at once): a few descent steps with the CUDA ExplicitLoss land
+    where the same steps with the fp64 oracle land."""
+    from harness import optimize
+    B, R, steps = 5, 32, 6
+    true = O.random_params(B, 41)
+    start = O.perturbed_params(O.random_params(B, 41), 4, sigma=0.05)
+    ref = start.clone().double()
+    optimize.descend(O.ExplicitLoss(R, "cpu"), true.double(), ref, steps)
+    got = start.clone().to(dev)
+    rec = []
+    optimize.descend(S.ExplicitLoss(R, dev), true.to(dev), got, steps, record=rec)
+    assert rec[-1].item() < rec[0].item()
+    np.testing.assert_allclose(got.cpu().double().numpy(), ref.numpy(), rtol=0, atol=2e-6)
+
+
+def test_dataset_generator(dev, S, tmp_path):
+    from harness import make_dataset
+    p = O.random_params(3, 51)
+    imgs = make_dataset.render(p, dev, size=256, chunk=2)
+    assert imgs.shape == (3, 1, 256, 256) and imgs.dtype == torch.float32
+    assert 0.0 <= imgs.min().item() and imgs.max().item() < 1.0 and 0.02 < (imgs > 0).float().mean().item() < 0.6
+    assert torch.equal(imgs[:, 0], S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(p.to(dev)))
