@@ -386,6 +386,9 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
     for (int j = threadIdx.x; j < J; j += kPlanThreads) {
         const int c = cls[j];
         const unsigned int r = atomicAdd(&ccnt[c], 1u);
+#ifdef SQ_DEBUG_BOUNDS
+        if (c < 0 || c >= kClasses || cbase[c] + r >= (unsigned int)cap || b * J + j >= cap) __trap();
+#endif
         queue[(size_t)c * cap + cbase[c] + r] = b * J + j;
     }
 #ifdef SQ_TIMELINE
@@ -550,6 +553,12 @@ struct WorkMap {
         const unsigned int m = __ballot_sync(0xffffffffu, lane < kClasses && (unsigned int)pos >= excl);
         const int c = 31 - __clz((int)m);                  // the highest class that starts at or before pos
         const unsigned int start = __shfl_sync(0xffffffffu, excl, c);
+#ifdef SQ_DEBUG_BOUNDS      // tools/sanitize_case.py --bounds (compute-sanitizer is not available on the GPU pool)
+        if (c < 0 || c >= kClasses || (unsigned int)pos - start >= (unsigned int)cap) __trap();
+        const int it = __ldg(queue + (size_t)c * cap + ((unsigned int)pos - start));
+        if (it < 0 || it >= cap) __trap();
+        return it;
+#endif
         return __ldg(queue + (size_t)c * cap + ((unsigned int)pos - start));
     }
 };

@@ -2,7 +2,16 @@
 import os
 import sys
 
+import subprocess
+
 import torch
+
+if "--bounds" in sys.argv:      # build a library with index traps and run this case on it (sets SQ_LIBSQLOSS)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = "/tmp/libsq_bounds.so"
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-ftz=true", "-std=c++17", "-shared",
+                           "-Xcompiler", "-fPIC", "-DSQ_DEBUG_BOUNDS", "-o", out, os.path.join(root, "sq_recovery_b200", "csrc", "sqloss.cu")])
+    os.environ["SQ_LIBSQLOSS"] = out
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import sq_oracle as O      # input distributions only
@@ -10,7 +19,7 @@ import sq_recovery_b200 as S
 from sq_recovery_b200.functional import HostContext
 
 dev = torch.device("cuda:0")
-for B, R in ((3, 8), (5, 24), (2, 33), (7, 16)):
+for B, R in ((3, 8), (5, 24), (2, 33), (7, 16), (300, 64), (1, 128)):
     true, pred = O.random_params(B, 1).to(dev), O.random_params(B, 2).to(dev)
     img = S.ImplicitLoss(4 * R, dev, 1.5, 260).depth_projection(true).unsqueeze(1)
     p = pred.clone().requires_grad_(True)
