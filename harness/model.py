@@ -18,9 +18,12 @@ class SQRegressor(nn.Module):
         self.trunk = trunk
         self.size, self.shape, self.position, self.rotation = (nn.Linear(width, k) for k in (3, 2, 3, 4))
 
-    def forward(self, depth_images: torch.Tensor) -> torch.Tensor:
-        """(B,1,H,W) -> (B,12) rows [a(3) | e(2) | t(3) | q(4)] like torch/train.py:88-89."""
+    def forward(self, depth_images: torch.Tensor, raw: bool = False) -> torch.Tensor:
+        """(B,1,H,W) -> (B,12) rows [a(3) | e(2) | t(3) | q(4)] like torch/train.py:88-89.  raw=True returns the head
+        outputs before sigmoid / normalisation, for ImplicitLoss.from_heads (the activations then run inside the loss)."""
         z = self.trunk(depth_images)
         q = self.rotation(z)
+        if raw:
+            return torch.cat([self.size(z), self.shape(z), self.position(z), q], dim=1)
         return torch.cat([torch.sigmoid(self.size(z)), torch.sigmoid(self.shape(z)), torch.sigmoid(self.position(z)),
                           q / q.norm(dim=-1, keepdim=True)], dim=1)

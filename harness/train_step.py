@@ -32,7 +32,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--render", type=int, default=64)
-    ap.add_argument("--loss", default="b200", choices=["b200", "oracle-cuda"])
+    ap.add_argument("--loss", default="b200", choices=["b200", "b200-heads", "oracle-cuda"],
+                    help="b200-heads: head activations fused into the loss kernels (ImplicitLoss.from_heads)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -49,7 +50,7 @@ def main():
     net = SQRegressor().to(dev)
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
-    if args.loss == "b200":
+    if args.loss in ("b200", "b200-heads"):
         crit = S.ImplicitLoss(args.render, dev, 1.5, 260)
     else:
         crit = O.ImplicitLoss(args.render, dev, 1.5, 260, form="loop")
@@ -57,8 +58,12 @@ def main():
 
     def step():
         opt.zero_grad(set_to_none=True)
-        pred = model(images)
-        loss = crit(images, pred)
+        if args.loss == "b200-heads":
+            pred = model(images, raw=True)
+            loss = crit.from_heads(images, pred)
+        else:
+            pred = model(images)
+            loss = crit(images, pred)
         loss.backward()
         opt.step()
         return loss, pred
@@ -75,12 +80,14 @@ def main():
     ev[1].record()
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / args.steps
+    if args.loss == "b200-heads":                          # raw head outputs -> parameters, for the timings / IoU below
+        pred = torch.cat([torch.sigmoid(pred[:, :8]), pred[:, 8:] / pred[:, 8:].norm(dim=1, keepdim=True)], dim=1)
     # loss share: time loss forward+backward alone on the same predictions
     p = pred.detach().requires_grad_(True)
     for _ in range(3):
         crit(images, p).backward()
     ev[2].record()
-    reps = 10 if args.loss == "b200" else 2
+    reps = 10 if args.loss.startswith("b200") else 2
     for _ in range(reps):
         crit(images, p).backward()
     ev[3].record()

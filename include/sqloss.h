@@ -67,6 +67,17 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
                      double* loss_out, double* per_sample, void* grad_pred, float* depth_out,
                      void* scratch, size_t scratch_bytes, sq_stream_t stream);
 
+/* The same with the network heads fused in: rows of raw_heads are the raw outputs of the four linear
+ * heads [size(3) | shape(2) | position(3) | rotation(4)]; the kernel applies sigmoid to the first eight and L2
+ * normalisation to the quaternion (torch/models.py:28,52,75,98), the torch.cat of torch/train.py:89 and the clamp, and
+ * returns d loss / d raw_heads in grad_raw -- replacing the ~14 small elementwise launches around the loss per step.
+ */
+int sq_implicit_loss_heads(const void* raw_heads, int dtype, int batch, int n, double step, double z0,
+                           const float* target, long long target_stride_b, const int* row_off, const int* col_off,
+                           float tau, float sharpness,
+                           double* loss_out, double* per_sample, void* grad_raw, float* depth_out,
+                           void* scratch, size_t scratch_bytes, sq_stream_t stream);
+
 /* ExplicitLoss.__call__ (torch/classes.py:138-201): mean_b( mult * mean_pts (o_true - o_pred)^2 ),
  * o = sigmoid(sharpness (1 - F)); the reference uses sharpness 5, mult 100 (:187, :198).
  *   grad_pred   [batch,12] d loss / d pred (params_dtype)              (NULL = forward only)

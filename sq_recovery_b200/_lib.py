@@ -21,6 +21,9 @@ _PROTOS = {
     "sq_implicit_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_longlong, c_void_p,
                                  c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
+    "sq_implicit_loss_heads": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_longlong, c_void_p,
+                                       c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]),
     "sq_explicit_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_float, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sq_iou_counts": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p,

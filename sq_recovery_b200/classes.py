@@ -97,6 +97,14 @@ class ImplicitLoss(_GridLoss):
         return Fn.ImplicitLossFn.apply(true, pred, self._n, self._step, self._z0, float(self.tau),
                                        float(self.sigmoid_sharpness))
 
+    def from_heads(self, true, raw_heads):
+        """The same loss taken straight from the RAW outputs of the four linear heads, (B, 12) =
+        [size(3) | shape(2) | position(3) | rotation(4)]: the sigmoids, the quaternion normalisation
+        (torch/models.py:28,52,75,98), the torch.cat of torch/train.py:89 and all their backward kernels run inside
+        the loss kernels.  Not in the reference; equals ``self(true, heads(raw_heads))``."""
+        return Fn.ImplicitLossFn.apply(true, raw_heads, self._n, self._step, self._z0, float(self.tau),
+                                       float(self.sigmoid_sharpness), True)
+
 
 class LeastSquares(_GridLoss):
     """Solina-Bajcsy energy on the points back-projected from the depth image (torch/classes.py:297-371)."""

@@ -140,10 +140,29 @@ struct SampleFull : Sample {
     double M[9];              // un-scaled rotation
     double a[3], e[2], q[4];
     double ia[3];             // 1 / a
+    // fused network heads (heads_forward): sigmoid outputs before the clamp, 1 / |raw quaternion|; heads = 0: not used
+    double hp[8], hrn;
+    int heads, pad2_;
     float mask[8];            // clamp sub-gradient masks for a(3), e(2), t(3): 1 inside or on the boundary, else 0
 };
 
 SQ_HD void split2(double v, float& hi, float& lo) { hi = d2f(v); lo = d2f(v - f2d(hi)); }
+
+// The network heads of torch/models.py (SizeHead :52, ShapeHead :75, PositionHead :98: sigmoid; RotationHead :28: L2
+// normalisation) and the torch.cat of train.py:89, applied to one row of raw head outputs [3 | 2 | 3 | 4].  The
+// reference runs them in fp32, so the sigmoid / normalised values are rounded to fp32 before the loss sees them.
+SQ_HD void heads_forward(const double* raw, double* p, double* hp, double& hrn) {
+    for (int i = 0; i < 8; ++i) { hp[i] = (double)(float)(1.0 / (1.0 + exp(-raw[i]))); p[i] = hp[i]; }
+    const double n2 = raw[8] * raw[8] + raw[9] * raw[9] + raw[10] * raw[10] + raw[11] * raw[11];
+    hrn = 1.0 / sqrt(n2);
+    for (int i = 8; i < 12; ++i) p[i] = (double)(float)(raw[i] * hrn);
+}
+// d loss / d raw from d loss / d params (gr, in place): sigmoid'(x) = p (1 - p); d (r / |r|) = (I - q q^T) / |r|
+SQ_HD void heads_backward(const double* hp, double hrn, const double* q, double* gr) {
+    for (int i = 0; i < 8; ++i) gr[i] *= hp[i] * (1.0 - hp[i]);
+    const double dot = q[0] * gr[8] + q[1] * gr[9] + q[2] * gr[10] + q[3] * gr[11];
+    for (int i = 0; i < 4; ++i) gr[8 + i] = (gr[8 + i] - q[i] * dot) * hrn;
+}
 
 // p: 12 raw parameters [a1 a2 a3 e1 e2 t1 t2 t3 qx qy qz qw].  clamp per classes.py:129-136 (IoU: no clamp, :398).
 SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, SampleFull& S) {
@@ -181,6 +200,8 @@ SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, SampleFull& S
         S.of[i] = (float)-(S.Ms[3 * i] * S.t[0] + S.Ms[3 * i + 1] * S.t[1] + S.Ms[3 * i + 2] * S.t[2]);
     }
     S.pad_ = 0.f;
+    S.heads = 0; S.pad2_ = 0; S.hrn = 1.0;
+    for (int i = 0; i < 8; ++i) S.hp[i] = 0.0;
     {
         // Power-mean inequality, for exponents 2/e >= 2:  F >= 2^(e1-1) (2^(e2-1) (sx^2 + sy^2) + sz^2); the factors
         // are 1 for e > 1 (unclamped IoU parameters).  Non-positive e: no bound (the reference yields inf/nan there).

@@ -284,7 +284,7 @@ __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, flo
 // of the sample's work items and appends the item to the queue of its cost class.  NS = SQs per item (2: true + pred).
 template <int NS>
 __global__ void __launch_bounds__(kPlanThreads)
-plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Grid g, Layout L, float bound,
+plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, int heads, Grid g, Layout L, float bound,
             SampleFull* out_a, SampleFull* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap,
             float* zero_rows, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
             const int* __restrict__ col_off, double* tv_sum) {
@@ -309,7 +309,18 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, Gr
         const int w = threadIdx.x >> 5;
         double p[12];
         load_params(w == 0 ? params_a : params_b, dtype, b, p);
-        prep_sample(p, clamp != 0, g, Ssh[w]);
+        if (heads) {                                       // rows are raw network-head outputs (sq_implicit_loss_heads)
+            double raw[12], hp[8], hrn;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) raw[i] = p[i];
+            heads_forward(raw, p, hp, hrn);
+            prep_sample(p, clamp != 0, g, Ssh[w]);
+            Ssh[w].heads = 1; Ssh[w].hrn = hrn;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Ssh[w].hp[i] = hp[i];
+        } else {
+            prep_sample(p, clamp != 0, g, Ssh[w]);
+        }
         SQ_STAMP();
     }
     // ImplicitLoss: sum |target| over the sample's n x n pixels, by the warps that are not busy with the fp64 prep (it
@@ -964,6 +975,7 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
             finalize_sample(S, g, acc, grad_scale * vol, KIND != FIN_LSQ, gr);
             if (KIND == FIN_LSQ)
                 for (int i = 0; i < 3; ++i) gr[i] += S.mask[i] * (vol * S.ia[i]) * acc[17] / (double)batch;
+            if (S.heads) heads_backward(S.hp, S.hrn, S.q, gr);
             for (int i = 0; i < 12; ++i) {
                 if (dtype == SQ_F64) static_cast<double*>(grad)[12 * (size_t)b + i] = gr[i];
                 else static_cast<float*>(grad)[12 * (size_t)b + i] = (float)gr[i];
@@ -1073,15 +1085,15 @@ struct PlanTarget { const float* target; long long tstride; const int* row_off; 
 
 int launch_plan(const void* params_a, const void* params_b, int dtype, int batch, bool clamp, const Grid& g,
                 const Layout& L, float bound, const Scratch& s, unsigned long long* counts, float* zero_rows,
-                const PlanTarget* pt, cudaStream_t st) {
+                const PlanTarget* pt, cudaStream_t st, bool heads = false) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
     int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
     if (params_b)
-        plan_kernel<2><<<batch, kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, g, L, bound, s.tru, s.pred,
+        plan_kernel<2><<<batch, kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, 0, g, L, bound, s.tru, s.pred,
                                                        s.ctl, counts, queue, s.queue_cap, zero_rows, nullptr, 0, nullptr, nullptr,
                                                        nullptr);
     else
-        plan_kernel<1><<<batch, kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, g, L, bound, s.pred, nullptr,
+        plan_kernel<1><<<batch, kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, heads ? 1 : 0, g, L, bound, s.pred, nullptr,
                                                        s.ctl, counts, queue, s.queue_cap, zero_rows,
                                                        pt ? pt->target : nullptr, pt ? pt->tstride : 0,
                                                        pt ? pt->row_off : nullptr, pt ? pt->col_off : nullptr,
@@ -1129,10 +1141,10 @@ int sq_scratch_init(void* scratch, size_t scratch_bytes, sq_stream_t stream) {
     return (int)cudaMemsetAsync(scratch, 0, sizeof(Control), static_cast<cudaStream_t>(stream));
 }
 
-int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double step, double z0,
-                     const float* target, long long target_stride_b, const int* row_off, const int* col_off,
-                     float tau, float sharpness, double* loss_out, double* per_sample, void* grad_pred,
-                     float* depth_out, void* scratch, size_t scratch_bytes, sq_stream_t stream) {
+static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n, double step, double z0,
+                              const float* target, long long target_stride_b, const int* row_off, const int* col_off,
+                              float tau, float sharpness, double* loss_out, double* per_sample, void* grad_pred,
+                              float* depth_out, void* scratch, size_t scratch_bytes, sq_stream_t stream, bool heads) {
     Scratch s;
     int rc = check_scratch(batch, n, scratch, scratch_bytes, &s);
     if (rc) return rc;
@@ -1146,7 +1158,7 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
         SQ_TRY(cudaMemsetAsync(depth_out, 0, sizeof(float) * (size_t)batch * n * n, st));
     const PlanTarget pt{target, target_stride_b, row_off, col_off};
     rc = launch_plan(pred, nullptr, pred_dtype, batch, true, g, L, P.bound, s, nullptr, target ? s.partials : nullptr,
-                     target ? &pt : nullptr, st);
+                     target ? &pt : nullptr, st, heads);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
@@ -1173,6 +1185,22 @@ int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double 
         SQ_TRY(cudaGetLastError());
     }
     return 0;
+}
+
+int sq_implicit_loss(const void* pred, int pred_dtype, int batch, int n, double step, double z0,
+                     const float* target, long long target_stride_b, const int* row_off, const int* col_off,
+                     float tau, float sharpness, double* loss_out, double* per_sample, void* grad_pred,
+                     float* depth_out, void* scratch, size_t scratch_bytes, sq_stream_t stream) {
+    return implicit_loss_impl(pred, pred_dtype, batch, n, step, z0, target, target_stride_b, row_off, col_off, tau, sharpness,
+                              loss_out, per_sample, grad_pred, depth_out, scratch, scratch_bytes, stream, false);
+}
+
+int sq_implicit_loss_heads(const void* raw_heads, int dtype, int batch, int n, double step, double z0,
+                           const float* target, long long target_stride_b, const int* row_off, const int* col_off,
+                           float tau, float sharpness, double* loss_out, double* per_sample, void* grad_raw,
+                           float* depth_out, void* scratch, size_t scratch_bytes, sq_stream_t stream) {
+    return implicit_loss_impl(raw_heads, dtype, batch, n, step, z0, target, target_stride_b, row_off, col_off, tau, sharpness,
+                              loss_out, per_sample, grad_raw, depth_out, scratch, scratch_bytes, stream, true);
 }
 
 int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype, int batch, int n, double step,

@@ -84,7 +84,9 @@ class ImplicitLossFn(torch.autograd.Function):
     """ImplicitLoss.__call__ (torch/classes.py:284-295) -> 0-dim fp64 loss; gradient reaches ``pred`` only."""
 
     @staticmethod
-    def forward(ctx, true, pred, n, step, z0, tau, sharpness):
+    def forward(ctx, true, pred, n, step, z0, tau, sharpness, heads=False):
+        # heads=True: `pred` holds the RAW outputs of the four network heads; sigmoid / quaternion normalisation, the
+        # torch.cat and their Jacobians run inside the kernels (sq_implicit_loss_heads, SURVEY 8f-3)
         _require_cuda(pred, "pred"); _require_cuda(true, "true")
         dev = pred.device
         img = _image(true)
@@ -97,11 +99,12 @@ class ImplicitLossFn(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float64, device=dev)
         grad = torch.empty_like(p) if want_grad else None
         scratch = _get_scratch(dev, B, n)
+        entry = _lib.lib().sq_implicit_loss_heads if heads else _lib.lib().sq_implicit_loss
         with torch.cuda.device(dev):
-            rc = _lib.lib().sq_implicit_loss(
+            rc = entry(
                 _ptr(p), tag, B, n, step, z0, _ptr(img), img.shape[2] * img.shape[3], _ptr(row_off), _ptr(col_off),
                 tau, sharpness, _ptr(loss), None, _ptr(grad), None, _ptr(scratch), scratch.numel(), _stream(dev))
-        _lib.check(rc, "sq_implicit_loss")
+        _lib.check(rc, "sq_implicit_loss_heads" if heads else "sq_implicit_loss")
         ctx.grad = grad
         ctx.pred_dtype = pred.dtype
         return loss
@@ -112,7 +115,7 @@ class ImplicitLossFn(torch.autograd.Function):
         g = None
         if ctx.grad is not None:
             g = (ctx.grad * go).to(ctx.pred_dtype)      # 0-dim fp64 `go` does not promote the result: one kernel
-        return None, g, None, None, None, None, None
+        return None, g, None, None, None, None, None, None
 
 
 class ExplicitLossFn(torch.autograd.Function):

@@ -463,3 +463,38 @@ def test_dataset_generator(dev, S, tmp_path):
     assert imgs.shape == (3, 1, 256, 256) and imgs.dtype == torch.float32
     assert 0.0 <= imgs.min().item() and imgs.max().item() < 1.0 and 0.02 < (imgs > 0).float().mean().item() < 0.6
     assert torch.equal(imgs[:, 0], S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(p.to(dev)))
+
+
+def test_fused_heads_match_torch_heads(dev, S):
+    """ImplicitLoss.from_heads(raw) == ImplicitLoss(heads(raw)) with the heads of torch/models.py.
+    At sharpness 260 the gradient is discontinuous in the parameters (sign(depth - target) per pixel), so the two paths
+    are compared on bit-identical parameters: the heads are evaluated here the way the kernel does (fp64, rounded to
+    fp32 like the reference's fp32 heads), the plain loss gives d loss / d params, and the head Jacobians are applied
+    in fp64.  The loss is also compared with torch's own fp32 heads."""
+    B, R = 12, 32
+    true = O.random_params(B, 61).to(dev)
+    img = S.ImplicitLoss(128, dev, 1.5, 260).depth_projection(true).unsqueeze(1)
+    g = torch.Generator().manual_seed(3)
+    p = O.perturbed_params(O.random_params(B, 61), 8).clamp(1e-3, 1 - 1e-3)
+    raw = torch.cat([torch.logit(p[:, :8]), p[:, 8:] * (0.5 + torch.rand(B, 1, generator=g))], dim=1)
+    crit = S.ImplicitLoss(R, dev, 1.5, 260)
+    r1 = raw.clone().to(dev).requires_grad_(True)
+    l1 = crit.from_heads(img, r1); l1.backward()
+    # the kernel's heads, restated
+    r64 = raw.double()
+    hp = torch.sigmoid(r64[:, :8]).float().double()
+    rn = r64[:, 8:].norm(dim=1, keepdim=True)
+    q = (r64[:, 8:] / rn).float().double()
+    pe = torch.cat([hp, q], dim=1).float().to(dev).requires_grad_(True)
+    l2 = crit(img, pe); l2.backward()
+    assert abs(l1.item() - l2.item()) <= 1e-9 * abs(l2.item())
+    gp = pe.grad.double().cpu()
+    expect = torch.cat([gp[:, :8] * hp * (1 - hp),
+                        (gp[:, 8:] - q * (q * gp[:, 8:]).sum(dim=1, keepdim=True)) / rn], dim=1)
+    torch.testing.assert_close(r1.grad.double().cpu(), expect, rtol=2e-6, atol=1e-10)
+    # and against torch's own fp32 heads (models.py:28,52,75,98 + train.py:89): same loss to fp32 head precision
+    r2 = raw.clone().to(dev)
+    q2 = r2[:, 8:]
+    pred = torch.cat([torch.sigmoid(r2[:, 0:3]), torch.sigmoid(r2[:, 3:5]), torch.sigmoid(r2[:, 5:8]),
+                      q2 / torch.norm(q2, 2, -1, keepdim=True)], dim=1)
+    assert abs(l1.item() - crit(img, pred).item()) <= 1e-5 * abs(l1.item())
