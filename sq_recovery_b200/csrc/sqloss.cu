@@ -709,7 +709,8 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 float bh[3], bl[3], cg[11], dxy[2];
                 column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
                 float depth;
-#ifdef SQ_NO_FIXHOIST    // hoisting the exact-zero fix-up out of the walk: -3 % kernel time (profiles/tune_r01.txt)
+#ifndef SQ_FIXHOIST      // hoisting the exact-zero fix-up out of the walk (two copies of the loop): measured 1 us
+                         // SLOWER per call once everything else was in place (profiles/tune_r01.txt) -> off
                 depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
 #else
                 if (__any_sync(0xffffffffu, column_zero_possible(S, bh)))
