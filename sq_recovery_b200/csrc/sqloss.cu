@@ -200,6 +200,21 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     return off;
 }
 
+// ------------------------------------------------------------------------------------------------ PDL
+// Programmatic dependent launch (-DSQ_PDL): the column kernel and the finalize kernel are launched with the
+// programmatic-stream-serialization attribute, so their blocks can become resident while the preceding kernel of the call
+// drains; pdl_wait() returns once that kernel has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() {
+#ifdef SQ_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#ifdef SQ_PDL
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ prep / plan
 #ifdef SQ_TIMELINE     // tools/timeline.py
 __device__ unsigned long long g_plan_ts[16];
@@ -643,6 +658,8 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
     // Items the plan kernel has proven empty are never touched: depth is exactly 0 on all their columns (depth_out was
     // cleared by the host), their loss sum |target| is part of the per-sample offset the plan kernel computed, their
     // partial rows were zeroed there.  What this kernel accumulates as "loss" is |depth - t| - |t| per walked column.
+    pdl_wait();                                           // the plan kernel's Samples, queues and counters
+    pdl_trigger();                                        // the finalize kernel may become resident (it waits for this grid)
 #ifdef SQ_TIMELINE
     const unsigned long long t_begin = gtime();
     unsigned long long t_last_fetch = t_begin, n_items = 0;
@@ -936,6 +953,7 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
                 double* __restrict__ per_sample_user, double* __restrict__ loss_out, unsigned int* ticket,
                 const double* __restrict__ loss_offset) {
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    pdl_wait();                                           // the column kernel's partial rows
     __shared__ double wpart[kFinThreads / 32][kAccN];
     __shared__ double acc[kAccN];
     __shared__ unsigned int last;
@@ -1058,6 +1076,18 @@ int check_scratch(int batch, int n, void* scratch, size_t bytes, Scratch* s) {
     return 0;
 }
 
+// kernel launch that may overlap the tail of the preceding kernel in the stream (the kernel must call pdl_wait())
+template <typename... KArgs, typename... Args>
+cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // blocks of a persistent column kernel: enough to fill every SM at the kernel's occupancy, no more than the work
 int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
     static int sms[64] = {0};
@@ -1163,26 +1193,32 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
+#ifdef SQ_PDL
+    const bool pdl = (t_ev_before == nullptr && t_ev_after == nullptr);   // an event record in between breaks the chain
+#else
+    const bool pdl = false;
+#endif
     {
         ColumnKernelTimer timer(st);
         if (grad_pred) {
             const int blocks = persistent_blocks(items, SQ_IMPB_THREADS / 32, SQ_IMPB_MINB);
-            implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB, SQ_IMPB_CPT><<<blocks, SQ_IMPB_THREADS, 0, st>>>(
-                s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off, s.partials,
-                depth_out);
+            SQ_TRY(launch_dependent(implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB, SQ_IMPB_CPT>, blocks, SQ_IMPB_THREADS, st, pdl,
+                                    s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off,
+                                    s.partials, depth_out));
         } else {
             const int blocks = persistent_blocks(items, SQ_IMPF_THREADS / 32, SQ_IMPF_MINB);
-            implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB, SQ_IMPF_CPT><<<blocks, SQ_IMPF_THREADS, 0, st>>>(
-                s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off, s.partials,
-                depth_out);
+            SQ_TRY(launch_dependent(implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB, SQ_IMPF_CPT>, blocks, SQ_IMPF_THREADS, st, pdl,
+                                    s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off,
+                                    s.partials, depth_out));
         }
     }
     SQ_TRY(cudaGetLastError());
     if (target) {
         const double nn = (double)n * n;
-        finalize_kernel<FIN_IMPLICIT><<<batch, kFinThreads, 0, st>>>(
-            s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn, -(double)sharpness * (double)tau / (nn * n * (double)batch),
-            pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket, s.tv_sum);
+        SQ_TRY(launch_dependent(finalize_kernel<FIN_IMPLICIT>, batch, kFinThreads, st, pdl,
+                                s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn,
+                                -(double)sharpness * (double)tau / (nn * n * (double)batch), pred_dtype, grad_pred, s.per_sample,
+                                per_sample, loss_out, &s.ctl->ticket, s.tv_sum));
         SQ_TRY(cudaGetLastError());
     }
     return 0;

@@ -104,6 +104,34 @@ def main():
             imp(grad)
         e1.record(); torch.cuda.synchronize()
         call_us = e0.elapsed_time(e1) / 400 * 1e3
+        # the same three kernels replayed from a CUDA graph (no launch gaps from the host)
+        graph_us = float("nan")
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                st_side = side.cuda_stream
+                def imp_side():
+                    rc = h.sq_implicit_loss(P(pred), 0, B, R, 1.0 / (R - 1), 1e-4, P(img), 256 * 256, P(row_off), P(col_off), 1.5, 260.0,
+                                            P(loss), None, P(grad), None, P(scratch), nb, st_side)
+                    assert rc == 0, rc
+                imp_side(); imp_side()
+                side.synchronize()
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side):
+                    rc = h.sq_implicit_loss(P(pred), 0, B, R, 1.0 / (R - 1), 1e-4, P(img), 256 * 256, P(row_off), P(col_off), 1.5, 260.0,
+                                            P(loss), None, P(grad), None, P(scratch), nb, torch.cuda.current_stream().cuda_stream)
+                    assert rc == 0, rc
+            torch.cuda.current_stream().wait_stream(side)
+            for _ in range(20):
+                gph.replay()
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(400):
+                gph.replay()
+            e1.record(); torch.cuda.synchronize()
+            graph_us = e0.elapsed_time(e1) / 400 * 1e3
+        except Exception as exc:      # keep the tool usable if capture fails for a variant
+            print("graph capture failed:", exc)
         t_ib = timed(h, lambda: imp(grad))
         chk = (loss.item(), grad.double().abs().sum().item())
         if ref is None:
@@ -112,7 +140,7 @@ def main():
         t_eb = timed(h, lambda: exp(grad))
         t_io = timed(h, iou)
         pts = B * R ** 3
-        print(f"{defs or 'default':40s} call {call_us:6.2f}us imp_bwd {t_ib[0]*1e3:7.1f}us ({pts/t_ib[0]/1e6:6.1f} Gpt/s) imp_fwd {t_if[0]*1e3:7.1f}us "
+        print(f"{defs or 'default':40s} call {call_us:6.2f}us graph {graph_us:6.2f}us imp_bwd {t_ib[0]*1e3:7.1f}us ({pts/t_ib[0]/1e6:6.1f} Gpt/s) imp_fwd {t_if[0]*1e3:7.1f}us "
               f"exp_bwd {t_eb[0]*1e3:7.1f}us iou {t_io[0]*1e3:7.1f}us  regs {regs}  same={abs(chk[0]-ref[0])<1e-9 and abs(chk[1]-ref[1])<1e-6*ref[1]}",
               flush=True)
 
