@@ -468,6 +468,41 @@ SQ_HD void column_range(const Sample& S, const Grid& g, float bound, const float
     c_hi = (int)floorf(hi);
 }
 
+// Upper bound on the z planes ANY column of a rectangular footprint (centre (cx, cy), half extents (hx, hy), in grid
+// steps) can need: the bounds of column_range() evaluated once at the centre, widened by how far s can move across the
+// footprint (so a thin object that slips between probe columns is never taken for empty).  0 is a PROOF that every
+// column of the footprint has an empty range -- the plan kernel relies on it to drop work items for good
+// (tests/test_emu_math.py checks the claim against the fp64 F).
+SQ_HD int footprint_planes(const Sample& S, const Grid& g, float bound, float cx, float cy, float hx, float hy) {
+    const float gx = cx * g.stepf, gy = cy * g.stepf;
+    float lo = -1e30f, hi = 1e30f, he2 = 0.f, bc[3];
+    for (int i = 0; i < 3; ++i) {
+        bc[i] = fmaf(S.mf[2 * i], gx, fmaf(S.mf[2 * i + 1], gy, S.of[i]));
+        // + the 0 -> z0 substitution of grid index 0, + 1 % and 1e-4 for the fp32 evaluation here and in the kernels
+        const float hw = ((fabsf(S.mf[2 * i]) * hx + fabsf(S.mf[2 * i + 1]) * hy) * g.stepf
+                          + (fabsf(S.mf[2 * i]) + fabsf(S.mf[2 * i + 1])) * fabsf(g.z0f)) * 1.01f + 1e-4f;
+        const float bi = bound + hw;
+        const float u = (bi - bc[i]) * S.idh[i], v = (-bi - bc[i]) * S.idh[i];
+        lo = fmaxf(lo, fminf(u, v));
+        hi = fminf(hi, fmaxf(u, v));
+        he2 = fmaf(i < 2 ? S.qw : 1.0f, hw * hw, he2);
+    }
+    {
+        const float r = sqrtf(bound * bound * 1.004f * S.qB1) + sqrtf(he2);
+        const float beta = fmaf(S.wd[0], bc[0], fmaf(S.wd[1], bc[1], S.wd[2] * bc[2]));
+        const float gamma = fmaf(S.qw, fmaf(bc[0], bc[0], bc[1] * bc[1]), fmaf(bc[2], bc[2], -r * r));
+        const float disc = fmaf(beta, beta, -S.qa * gamma);
+        const float sq = sqrtf(fmaxf(disc, 0.0f));
+        lo = fmaxf(lo, (-beta - sq) * S.qia);
+        hi = fminf(hi, disc > 0.0f ? (sq - beta) * S.qia : -1e30f);
+    }
+    const float nf = (float)g.n;
+    lo = fminf(fmaxf(lo - 1.0f, 0.0f), nf);
+    hi = fmaxf(fminf(hi + 1.0f, nf - 1.0f), -1.0f);
+    const int c_lo = (int)ceilf(lo), c_hi = (int)floorf(hi);
+    return c_hi >= c_lo ? c_hi - c_lo + 1 : 0;
+}
+
 #if defined(__CUDA_ARCH__)
 #define SQ_ANY(p) __any_sync(0xffffffffu, (p))
 #define SQ_WARP_MAX(v) __reduce_max_sync(0xffffffffu, (v))

@@ -265,34 +265,7 @@ __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, flo
         if (ia + 31 < L.n) { cx = (float)ia + 15.5f; cy = (float)ib; hx = 15.5f; hy = 0.f; }
         else { cx = 0.5f * (float)(L.n - 1); hx = cx; cy = (float)ib + 0.5f; hy = 0.5f; }      // wraps into the next row
     }
-    const float gx = cx * g.stepf, gy = cy * g.stepf;
-    float lo = -1e30f, hi = 1e30f, he2 = 0.f, bc[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        bc[i] = fmaf(S.mf[2 * i], gx, fmaf(S.mf[2 * i + 1], gy, S.of[i]));
-        // + the 0 -> z0 substitution of grid index 0, + 1 % and 1e-4 for the fp32 evaluation here and in the kernels
-        const float hw = ((fabsf(S.mf[2 * i]) * hx + fabsf(S.mf[2 * i + 1]) * hy) * g.stepf
-                          + (fabsf(S.mf[2 * i]) + fabsf(S.mf[2 * i + 1])) * fabsf(g.z0f)) * 1.01f + 1e-4f;
-        const float bi = bound + hw;
-        const float u = (bi - bc[i]) * S.idh[i], v = (-bi - bc[i]) * S.idh[i];
-        lo = fmaxf(lo, fminf(u, v));
-        hi = fminf(hi, fmaxf(u, v));
-        he2 = fmaf(i < 2 ? S.qw : 1.0f, hw * hw, he2);
-    }
-    {
-        const float r = sqrtf(bound * bound * 1.004f * S.qB1) + sqrtf(he2);
-        const float beta = fmaf(S.wd[0], bc[0], fmaf(S.wd[1], bc[1], S.wd[2] * bc[2]));
-        const float gamma = fmaf(S.qw, fmaf(bc[0], bc[0], bc[1] * bc[1]), fmaf(bc[2], bc[2], -r * r));
-        const float disc = fmaf(beta, beta, -S.qa * gamma);
-        const float sq = sqrtf(fmaxf(disc, 0.0f));
-        lo = fmaxf(lo, (-beta - sq) * S.qia);
-        hi = fminf(hi, disc > 0.0f ? (sq - beta) * S.qia : -1e30f);
-    }
-    const float nf = (float)g.n;
-    lo = fminf(fmaxf(lo - 1.0f, 0.0f), nf);
-    hi = fmaxf(fminf(hi + 1.0f, nf - 1.0f), -1.0f);
-    const int c_lo = (int)ceilf(lo), c_hi = (int)floorf(hi);
-    return c_hi >= c_lo ? c_hi - c_lo + 1 : 0;
+    return footprint_planes(S, g, bound, cx, cy, hx, hy);
 }
 
 // plan (column kernels): one block per sample.  Builds the Sample record(s) like prep, then estimates the cost of each

@@ -139,3 +139,48 @@ int emu_lsq(const double* pred, int B, const float* points, const int* offsets, 
 }
 
 }  // extern "C"
+
+extern "C" {
+
+// Culling claims of the column kernels, checked against the fp64 inside-outside function (TEST TOOL):
+//  * for every column, the planes OUTSIDE column_range() (computed from the fp32 base, as the kernels do) have F >= Fmin;
+//  * for every 8 x 4 patch the plan kernel would call proven empty (footprint_planes == 0), ALL planes of all its columns do.
+// Returns the number of violations; *patches_empty / *patches_total report how much the proof catches.
+long long emu_check_culling(const double* params, int B, int n, double step, double z0, int clamp, float bound,
+                            double Fmin, long long* patches_empty, long long* patches_total) {
+    Grid g = make_grid(n, step, z0);
+    long long bad = 0, pe = 0, ptot = 0;
+    for (int b = 0; b < B; ++b) {
+        double p[12]; for (int i = 0; i < 12; ++i) p[i] = params[12 * b + i];
+        SampleFull S; prep_sample(p, clamp != 0, g, S);
+        std::vector<char> inside((size_t)n * n * n);
+        for (int ia = 0; ia < n; ++ia) for (int ib = 0; ib < n; ++ib) for (int ic = 0; ic < n; ++ic) {
+            const double gx = grid_coord(g, ia), gy = grid_coord(g, ib), gz = grid_coord(g, ic);
+            double s[3];
+            for (int i = 0; i < 3; ++i)
+                s[i] = (S.M[3 * i] * (gx - S.t[0]) + S.M[3 * i + 1] * (gy - S.t[1]) + S.M[3 * i + 2] * (gz - S.t[2])) / S.a[i];
+            const double A = pow(s[0] * s[0], 1.0 / S.e[1]), Bv = pow(s[1] * s[1], 1.0 / S.e[1]), C = pow(s[2] * s[2], 1.0 / S.e[0]);
+            const double F = pow(pow(A + Bv, S.e[1] / S.e[0]) + C, S.e[0]);
+            inside[((size_t)ia * n + ib) * n + ic] = F < Fmin;
+        }
+        for (int ia = 0; ia < n; ++ia) for (int ib = 0; ib < n; ++ib) {
+            float b32[3]; column_base_f32(S, g, ia, ib, b32);
+            int c_lo, c_hi; column_range(S, g, bound, b32, c_lo, c_hi);
+            for (int ic = 0; ic < n; ++ic)
+                if (inside[((size_t)ia * n + ib) * n + ic] && (ic < c_lo || ic > c_hi)) ++bad;
+        }
+        if (n % 8 == 0)
+            for (int pa = 0; pa < n / 8; ++pa) for (int pb = 0; pb < n / 4; ++pb) {
+                ++ptot;
+                if (footprint_planes(S, g, bound, 8 * pa + 3.5f, 4 * pb + 1.5f, 3.5f, 1.5f) != 0) continue;
+                ++pe;
+                for (int ia = 8 * pa; ia < 8 * pa + 8; ++ia) for (int ib = 4 * pb; ib < 4 * pb + 4; ++ib)
+                    for (int ic = 0; ic < n; ++ic) if (inside[((size_t)ia * n + ib) * n + ic]) ++bad;
+            }
+    }
+    *patches_empty = pe; *patches_total = ptot;
+    return bad;
+}
+
+}  // extern "C"
+

@@ -75,3 +75,14 @@ def lsq(pred, points, offsets, want_grad=True):
     lib().emu_lsq(_ptr(pred, ctypes.c_double), B, _ptr(points, ctypes.c_float), _ptr(offsets, ctypes.c_int),
                   ctypes.byref(loss), _ptr(grad, ctypes.c_double))
     return loss.value, grad
+
+
+def check_culling(params, n, step, z0, clamp, bound, f_min):
+    """(violations, proven-empty patches, patches): see emu_check_culling in emu.cpp."""
+    params, B = _f64(params), len(params)
+    pe, pt = ctypes.c_longlong(), ctypes.c_longlong()
+    fn = lib().emu_check_culling
+    fn.restype = ctypes.c_longlong
+    bad = fn(_ptr(params, ctypes.c_double), B, n, ctypes.c_double(step), ctypes.c_double(z0), int(clamp),
+             ctypes.c_float(bound), ctypes.c_double(f_min), ctypes.byref(pe), ctypes.byref(pt))
+    return int(bad), int(pe.value), int(pt.value)

@@ -68,3 +68,33 @@ def test_emulated_fixture_least_squares(fixtures_golden):
     assert abs(l - g["lsq64_loss"]) <= 1e-4 * g["lsq64_loss"] and tol(gr, g["lsq64_grad"], 1e-3, 1e-5) <= 1.0
     i, u = E.iou(g["labels"], np.roll(g["labels"], 1, 0), 64, 1 / 63)
     assert (i == g["iou64_roll_inter"]).all() and (u == g["iou64_roll_union"]).all()
+
+
+@pytest.mark.parametrize("kind", ["implicit", "explicit", "iou"])
+def test_culling_never_drops_occupancy(kind):
+    """The column kernels skip grid points outside column_range() and whole work items the plan kernel proves empty.
+    Both claims are checked here against the fp64 inside-outside function on random, clamped-extreme and off-centre
+    superquadrics: a skipped point must have F >= 1 + bits / (k log2 e), i.e. occupancy below 2^-bits (DESIGN.md
+    "culling"; IoU: F > 1).  Host build of the same header the kernels compile."""
+    from oracle import sq_oracle as O
+    log2e = 1.4426950408889634
+    rs = np.random.RandomState(3)
+    p = O.random_params(24, 17).double().numpy()
+    p[0, 0:3] = 0.05; p[1, 0:3] = 1.0; p[2, 3:5] = 0.1; p[3, 3:5] = 1.0; p[4, 3:5] = [0.1, 1.0]; p[5, 3:5] = [1.0, 0.1]
+    p[6, 5:8] = [0.0, 0.0, 0.0]; p[7, 5:8] = [1.0, 1.0, 1.0]; p[8, 8:12] = [0, 0, 0, 1]; p[9, 8:12] = [0.5, 0.5, 0.5, 0.5]
+    p[10, 8:12] *= 1.7                                                  # non-unit quaternion
+    if kind == "iou":
+        p[11, 3:5] = [1.6, 1.3]; p[12, 5:8] = [1.4, -0.3, 0.5]; p[13, 0:3] = [0.02, 0.4, 1.5]     # no clamp for IoU
+        n, step, z0, clamp, bound, fmin = 32, 1 / 31, 0.0, 0, 1.001, 1.0 + 1e-12
+    elif kind == "implicit":
+        kl = 260 * log2e
+        n, step, z0, clamp = 32, 1 / 31, 1e-4, 1
+        bound, fmin = float(np.sqrt((1 + 40 / kl) * 1.002)), 1 + 40 / kl
+    else:
+        kl = 5 * log2e
+        n, step, z0, clamp = 24, 1 / 23, 1e-4, 1
+        bound, fmin = float(np.sqrt((1 + 24 / kl) * 1.002)), 1 + 24 / kl
+    bad, empty, total = E.check_culling(p, n, step, z0, clamp, bound, fmin)
+    assert bad == 0
+    if kind != "explicit":                                             # the proof is not vacuous: it catches a good part
+        assert empty > 0.2 * total, (empty, total)
