@@ -926,10 +926,13 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
                 double* __restrict__ per_sample_user, double* __restrict__ loss_out, unsigned int* ticket,
                 const double* __restrict__ loss_offset) {
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    pdl_wait();                                           // the column kernel's partial rows
+    __shared__ SampleFull S;
     __shared__ double wpart[kFinThreads / 32][kAccN];
     __shared__ double acc[kAccN];
-    __shared__ unsigned int last;
+    // the sample's record (written by the plan / prep kernel) into shared memory, while the partial rows are on their way
+    for (int w = t; w < kFullWords; w += kFinThreads)
+        reinterpret_cast<uint32_t*>(&S)[w] = __ldg(reinterpret_cast<const uint32_t*>(samples + b) + w);
+    pdl_wait();                                           // the column kernel's partial rows
     {
         double s[kAccN];
 #pragma unroll
@@ -955,36 +958,37 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
         acc[t] = v;
     }
     __syncthreads();
-    if (t == 0) {
-        const SampleFull& S = samples[b];
-        double ls = (acc[17] + (loss_offset ? loss_offset[b] : 0.0)) * loss_norm;   // ImplicitLoss: + sum |target|
-        double vol = 1.0;
-        if (KIND == FIN_LSQ) { vol = S.a[0] * S.a[1] * S.a[2]; ls *= vol; }
-        per_sample[b] = ls;
-        if (per_sample_user) per_sample_user[b] = ls;
-        if (grad) {
-            double gr[12];
-            finalize_sample(S, g, acc, grad_scale * vol, KIND != FIN_LSQ, gr);
-            if (KIND == FIN_LSQ)
-                for (int i = 0; i < 3; ++i) gr[i] += S.mask[i] * (vol * S.ia[i]) * acc[17] / (double)batch;
-            if (S.heads) heads_backward(S.hp, S.hrn, S.q, gr);
-            for (int i = 0; i < 12; ++i) {
-                if (dtype == SQ_F64) static_cast<double*>(grad)[12 * (size_t)b + i] = gr[i];
-                else static_cast<float*>(grad)[12 * (size_t)b + i] = (float)gr[i];
-            }
+    const double vol = KIND == FIN_LSQ ? S.a[0] * S.a[1] * S.a[2] : 1.0;
+    if (warp == 1) {
+        // Loss path, next to the gradient path of warp 0: per-sample loss, then the batch mean by the last block to
+        // arrive, in index order.
+        unsigned int last = 0u;
+        if (lane == 0) {
+            const double ls = (acc[17] + (loss_offset ? loss_offset[b] : 0.0)) * loss_norm * vol;   // ImplicitLoss: + sum |target|
+            per_sample[b] = ls;
+            if (per_sample_user) per_sample_user[b] = ls;
+            __threadfence();
+            last = atomicAdd(ticket, 1u);
         }
-        __threadfence();
-        last = atomicAdd(ticket, 1u);
-    }
-    __syncthreads();
-    // batch mean by the last block to arrive, in index order
-    if (last == (unsigned)batch - 1u && warp == 0) {
-        __threadfence();
-        double s = 0.0;
-        for (int i = lane; i < batch; i += 32) s += __ldcg(per_sample + i);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last == (unsigned)batch - 1u) {
+            __threadfence();
+            double s = 0.0;
+            for (int i = lane; i < batch; i += 32) s += __ldcg(per_sample + i);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && loss_out) *loss_out = s / (double)batch;
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && loss_out) *loss_out = s / (double)batch;
+        }
+    } else if (t == 0 && grad) {
+        double gr[12];
+        finalize_sample(S, g, acc, grad_scale * vol, KIND != FIN_LSQ, gr);
+        if (KIND == FIN_LSQ)
+            for (int i = 0; i < 3; ++i) gr[i] += S.mask[i] * (vol * S.ia[i]) * acc[17] / (double)batch;
+        if (S.heads) heads_backward(S.hp, S.hrn, S.q, gr);
+        for (int i = 0; i < 12; ++i) {
+            if (dtype == SQ_F64) static_cast<double*>(grad)[12 * (size_t)b + i] = gr[i];
+            else static_cast<float*>(grad)[12 * (size_t)b + i] = (float)gr[i];
+        }
     }
 }
 
@@ -1171,6 +1175,7 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
 #else
     const bool pdl = false;
 #endif
+#ifndef SQ_SKIP_COLUMN      // timing experiments only (tools/tune.py): leave out the column and / or finalize kernel
     {
         ColumnKernelTimer timer(st);
         if (grad_pred) {
@@ -1186,6 +1191,8 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
         }
     }
     SQ_TRY(cudaGetLastError());
+#endif
+#ifndef SQ_SKIP_FINALIZE
     if (target) {
         const double nn = (double)n * n;
         SQ_TRY(launch_dependent(finalize_kernel<FIN_IMPLICIT>, batch, kFinThreads, st, pdl,
@@ -1194,6 +1201,7 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
                                 per_sample, loss_out, &s.ctl->ticket, s.tv_sum));
         SQ_TRY(cudaGetLastError());
     }
+#endif
     return 0;
 }
 
