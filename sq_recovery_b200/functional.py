@@ -30,9 +30,30 @@ def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_need: Dict[Tuple[int, int], int] = {}
+
+
+class _on_device:
+    """torch.cuda.device(dev) only when dev is not already current (the context manager costs ~5 us per call)."""
+
+    def __init__(self, device: torch.device):
+        idx = device.index
+        self._ctx = None if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+
+
 def _get_scratch(device: torch.device, batch: int, n: int) -> torch.Tensor:
     """Per (device, stream) workspace, grown on demand and reused (stream-ordered, so reuse is safe)."""
-    need = _lib.lib().sq_scratch_bytes(batch, n)
+    need = _need.get((batch, n))
+    if need is None:
+        need = _need[(batch, n)] = _lib.lib().sq_scratch_bytes(batch, n)
     key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(device))
     buf = _scratch.get(key)
     if buf is None or buf.numel() < need:
@@ -100,7 +121,7 @@ class ImplicitLossFn(torch.autograd.Function):
         grad = torch.empty_like(p) if want_grad else None
         scratch = _get_scratch(dev, B, n)
         entry = _lib.lib().sq_implicit_loss_heads if heads else _lib.lib().sq_implicit_loss
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             rc = entry(
                 _ptr(p), tag, B, n, step, z0, _ptr(img), img.shape[2] * img.shape[3], _ptr(row_off), _ptr(col_off),
                 tau, sharpness, _ptr(loss), None, _ptr(grad), None, _ptr(scratch), scratch.numel(), _stream(dev))
@@ -140,7 +161,7 @@ class ExplicitLossFn(torch.autograd.Function):
         L = _lib.lib()
 
         def run(a, b, grad):
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 rc = L.sq_explicit_loss(_ptr(a), _ptr(b), tag, B, n, step, z0, sharpness, mult, _ptr(loss), None,
                                         _ptr(grad), _ptr(scratch), scratch.numel(), _stream(dev))
             _lib.check(rc, "sq_explicit_loss")
@@ -180,7 +201,7 @@ class LeastSquaresFn(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float64, device=dev)
         grad = torch.empty_like(p) if want_grad else None
         scratch = _get_scratch(dev, B, render_size)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             rc = _lib.lib().sq_least_squares(
                 _ptr(p), tag, B, render_size, _ptr(img), img.shape[2] * img.shape[3], _ptr(row_off), _ptr(col_off),
                 _ptr(loss), None, _ptr(grad), _ptr(scratch), scratch.numel(), _stream(dev))
@@ -211,7 +232,7 @@ def iou_counts(true: torch.Tensor, pred: torch.Tensor, n: int, step: float, z0: 
         raise ValueError("true and pred disagree on the batch size")
     out = torch.empty((2, B), dtype=torch.int64, device=dev)
     scratch = _get_scratch(dev, B, n)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = _lib.lib().sq_iou_counts(_ptr(t), _ptr(p), tag, B, n, step, z0, _ptr(out[0]), _ptr(out[1]),
                                       _ptr(scratch), scratch.numel(), _stream(dev))
     _lib.check(rc, "sq_iou_counts")
@@ -226,7 +247,7 @@ def depth_projection(pred: torch.Tensor, n: int, step: float, z0: float, tau: fl
     B = p.shape[0]
     out = torch.empty((B, n, n), dtype=torch.float32, device=dev)
     scratch = _get_scratch(dev, B, n)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = _lib.lib().sq_implicit_loss(_ptr(p), tag, B, n, step, z0, None, 0, None, None, tau, sharpness, None, None,
                                          None, _ptr(out), _ptr(scratch), scratch.numel(), _stream(dev))
     _lib.check(rc, "sq_implicit_loss(depth)")
@@ -241,7 +262,7 @@ def field(params: torch.Tensor, n: int, step: float, z0: float, mode: int, sharp
     B = p.shape[0]
     out = torch.empty((B, n, n, n), dtype=torch.float32, device=dev)
     scratch = _get_scratch(dev, B, n)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = _lib.lib().sq_field(_ptr(p), tag, B, n, step, z0, mode, sharpness, _ptr(out), _ptr(scratch),
                                  scratch.numel(), _stream(dev))
     _lib.check(rc, "sq_field")
