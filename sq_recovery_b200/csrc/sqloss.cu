@@ -44,10 +44,10 @@ namespace {
 #define SQ_IMPF_CPT 1
 #endif
 #ifndef SQ_EXP_THREADS
-#define SQ_EXP_THREADS 128               // explicit fwd and fwd+bwd
+#define SQ_EXP_THREADS 256               // explicit fwd and fwd+bwd
 #endif
 #ifndef SQ_EXP_MINB
-#define SQ_EXP_MINB 3
+#define SQ_EXP_MINB 2
 #endif
 #ifndef SQ_EXP_CPT
 #define SQ_EXP_CPT 1
