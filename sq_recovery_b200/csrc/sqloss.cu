@@ -1,14 +1,18 @@
 // libsqloss: CUDA kernels (sm_100a) and the C ABI declared in include/sqloss.h.
 //
-// Kernel plan: every loss is  prep -> column kernel -> finalize, all on the caller's stream.
-//   prep      one thread per parameter row: clamp, rotation, scaled rows, exponents, in fp64 -> Sample (scratch)
-//   column    one thread per grid column (x, y) walking the part of z that can hold occupancy (the rest is culled
-//             in closed form); grid points are generated from indices, nothing per-point touches HBM; warps are
-//             autonomous: private Sample copy in shared memory, per-thread sums -> warp shuffles -> one partial
-//             row per warp, no block barrier
-//   finalize  one warp per sample: fixed-order fp64 sum of the partial rows, Jacobians to the 12 parameters,
+// Kernel plan: every grid loss is  plan -> column kernel -> finalize, on the caller's stream.
+//   plan      one block per sample: clamp, rotation, scaled rows, exponents, culling constants in fp64 -> SampleFull
+//             (scratch); the sum of |target| over the sample's pixels (ImplicitLoss); an upper bound on the cost of every
+//             work item (32 grid columns) -> item appended to the queue of its cost class; items proven empty are
+//             dropped for good
+//   column    persistent warps take items most expensive class first; one thread per grid column (x, y) walking the
+//             part of z that can hold occupancy (the rest is accounted for in closed form); grid points are generated
+//             from indices, nothing per-point touches HBM; warps are autonomous: private Sample copy and sum tile in
+//             shared memory, one partial row per item, no block barrier
+//   finalize  one block per sample: fixed-order fp64 sum of the partial rows, Jacobians to the 12 parameters,
 //             per-sample loss; the last block to finish averages the batch (fixed order, so results are
 //             bit-reproducible run to run)
+// The point-list loss (LeastSquares) is  prep -> lsq_kernel -> finalize.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -136,7 +140,8 @@ struct ColIter {
 // ------------------------------------------------------------------------------------------------ scratch
 // Work items are handed to the persistent warps in order of estimated cost (longest first, empty last): the plan
 // kernel sorts them into kClasses cost classes, one queue per class.  Class k holds items whose estimated number of
-// z planes is in (max / 2^(k+1), max / 2^k]; the last class holds items estimated empty.
+// z planes is in (max / 2^(k+1), max / 2^k]; the last class holds items PROVEN empty (the estimate is an upper bound),
+// which the column kernels never touch.
 constexpr int kClasses = 8;
 constexpr int kPlanThreads = 512;
 constexpr int kPlanMaxItems = 8192;      // items per sample the plan kernel can classify (more: index order)
