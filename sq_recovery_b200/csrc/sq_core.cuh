@@ -792,31 +792,41 @@ constexpr float kIoUMargin = 2e-4f;     // |log2 F| below which the fp32 decisio
 constexpr float kIoUBound = 1.001f;
 
 // Ft / Fp: the full records (in HBM), read only for the fp64 tie-break
+SQ_HD float log2F_plane(const Sample& S, const float* bh, const float* bl, float cf) {
+    return log2F(S, fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]),
+                    fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]),
+                    fmaf(cf, S.dh[2], bh[2]) + fmaf(cf, S.dl[2], bl[2]));
+}
+
+// Two planes per iteration: up to four independent MUFU chains (two SQs x two planes) in flight per thread -- the
+// one-plane version spent most of its time waiting on the chain's own latency (ncu: XU pipe 37 % busy).
 SQ_HD void iou_column(const Sample& St, const Sample& Sp, const SampleFull* Ft, const SampleFull* Fp, const Grid& g,
                       int ia, int ib, const float* bht, const float* blt, const float* bhp, const float* blp,
                       Range rt, Range rp, unsigned& inter, unsigned& uni) {
     const int c_hi = rt.hi > rp.hi ? rt.hi : rp.hi;
     const int c_lo = (rt.hi < rt.lo) ? rp.lo : (rp.hi < rp.lo) ? rt.lo : (rt.lo < rp.lo ? rt.lo : rp.lo);
     float cfi = (float)c_hi;
-    for (int c = c_hi; c >= c_lo; --c, cfi -= 1.0f) {
-        const float cf = (c == 0) ? Sp.cf0 : cfi;
-        bool it = false, ip = false;
-        if (c >= rt.lo && c <= rt.hi) {
-            const float yt = log2F(St, fmaf(cf, St.dh[0], bht[0]) + fmaf(cf, St.dl[0], blt[0]),
-                                       fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
-                                       fmaf(cf, St.dh[2], bht[2]) + fmaf(cf, St.dl[2], blt[2]));
-            it = yt <= 0.f;
-            if (!(fabsf(yt) > kIoUMargin)) it = inside_exact(*Ft, g, ia, ib, c);     // also catches NaN
+    for (int c = c_hi; c >= c_lo; c -= 2, cfi -= 2.0f) {
+        const int c1 = c - 1;
+        const bool has1 = c1 >= c_lo;
+        const float cf0 = (c == 0) ? Sp.cf0 : cfi, cf1 = (c1 == 0) ? Sp.cf0 : cfi - 1.0f;
+        const bool t0 = c >= rt.lo && c <= rt.hi, t1 = has1 && c1 >= rt.lo && c1 <= rt.hi;       // warp-uniform
+        const bool p0 = c >= rp.lo && c <= rp.hi, p1 = has1 && c1 >= rp.lo && c1 <= rp.hi;
+        float yt0 = 1.f, yt1 = 1.f, yp0 = 1.f, yp1 = 1.f;                                       // log2 F > 0: outside
+        if (t0 || t1) { yt0 = log2F_plane(St, bht, blt, cf0); yt1 = log2F_plane(St, bht, blt, cf1); }
+        if (p0 || p1) { yp0 = log2F_plane(Sp, bhp, blp, cf0); yp1 = log2F_plane(Sp, bhp, blp, cf1); }
+        bool it0 = t0 && yt0 <= 0.f, it1 = t1 && yt1 <= 0.f, ip0 = p0 && yp0 <= 0.f, ip1 = p1 && yp1 <= 0.f;
+        // decisions too close to call in fp32 (also NaN) are re-taken in fp64, in the reference's operation order
+        const bool n_t0 = t0 && !(fabsf(yt0) > kIoUMargin), n_t1 = t1 && !(fabsf(yt1) > kIoUMargin);
+        const bool n_p0 = p0 && !(fabsf(yp0) > kIoUMargin), n_p1 = p1 && !(fabsf(yp1) > kIoUMargin);
+        if (n_t0 || n_t1 || n_p0 || n_p1) {
+            if (n_t0) it0 = inside_exact(*Ft, g, ia, ib, c);
+            if (n_t1) it1 = inside_exact(*Ft, g, ia, ib, c1);
+            if (n_p0) ip0 = inside_exact(*Fp, g, ia, ib, c);
+            if (n_p1) ip1 = inside_exact(*Fp, g, ia, ib, c1);
         }
-        if (c >= rp.lo && c <= rp.hi) {
-            const float yp = log2F(Sp, fmaf(cf, Sp.dh[0], bhp[0]) + fmaf(cf, Sp.dl[0], blp[0]),
-                                       fmaf(cf, Sp.dh[1], bhp[1]) + fmaf(cf, Sp.dl[1], blp[1]),
-                                       fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]));
-            ip = yp <= 0.f;
-            if (!(fabsf(yp) > kIoUMargin)) ip = inside_exact(*Fp, g, ia, ib, c);
-        }
-        inter += (it && ip) ? 1u : 0u;
-        uni += (it || ip) ? 1u : 0u;
+        inter += ((it0 && ip0) ? 1u : 0u) + ((it1 && ip1) ? 1u : 0u);
+        uni += ((it0 || ip0) ? 1u : 0u) + ((it1 || ip1) ? 1u : 0u);
     }
 }
 
