@@ -889,6 +889,8 @@ __global__ void iou_export_kernel(const unsigned long long* counts, int batch, l
 }
 
 // ------------------------------------------------------------------------------------------------ LeastSquares
+constexpr int kLsqPix = 4;               // pixels per thread of the point-list kernel
+
 template <bool BWD>
 __global__ void __launch_bounds__(kThreads)
 lsq_kernel(const SampleFull* __restrict__ samples, int R, int items_per_sample,
@@ -902,13 +904,25 @@ lsq_kernel(const SampleFull* __restrict__ samples, int R, int items_per_sample,
     __syncthreads();
     Acc acc;
     acc_zero(acc);
-    const int pix = chunk * kThreads + threadIdx.x;
-    if (pix < R * R) {
-        const int row = pix / R, col = pix - row * R;
-        const float v = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
-        if (v > 0.f) {                                     // classes.py:363-368 (fp32 arithmetic, like the reference)
+    // kLsqPix pixels per thread, all loads issued before the first is used (they come from HBM; the kernel is a point
+    // list read once, bound by memory latency x parallelism, not by arithmetic)
+    float v[kLsqPix];
+    int pixs[kLsqPix];
+#pragma unroll
+    for (int k = 0; k < kLsqPix; ++k) {
+        pixs[k] = (chunk * kLsqPix + k) * kThreads + threadIdx.x;
+        v[k] = 0.f;
+        if (pixs[k] < R * R) {
+            const int row = pixs[k] / R, col = pixs[k] - row * R;
+            v[k] = __ldg(target + (size_t)b * tstride + row_off[row] + col_off[col]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kLsqPix; ++k) {
+        if (v[k] > 0.f) {                                  // classes.py:363-368 (fp32 arithmetic, like the reference)
+            const int row = pixs[k] / R, col = pixs[k] - row * R;
             const float px = (float)col / (float)R, py = 1.0f - (float)row / (float)R;
-            acc.loss = lsq_point<BWD>(S, px, py, v, acc);
+            acc.loss += lsq_point<BWD>(S, px, py, v[k], acc);
         }
     }
     block_reduce_store(acc, red, partials + (size_t)item * kAccN);
@@ -1294,7 +1308,7 @@ int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_siz
     rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ctl, st);
     if (rc) return rc;
     const int R = render_size;
-    const int ips = (R * R + kThreads - 1) / kThreads;
+    const int ips = (R * R + kThreads * kLsqPix - 1) / (kThreads * kLsqPix);
     if (grad_pred) lsq_kernel<true><<<batch * ips, kThreads, 0, st>>>(s.pred, R, ips, target, target_stride_b, row_off, col_off, s.partials);
     else lsq_kernel<false><<<batch * ips, kThreads, 0, st>>>(s.pred, R, ips, target, target_stride_b, row_off, col_off, s.partials);
     SQ_TRY(cudaGetLastError());

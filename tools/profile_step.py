@@ -32,5 +32,7 @@ if "--all" in sys.argv:
     S.IoUAccuracy(R, dev)(true, pred)
     with torch.no_grad():
         crit(img, pred)
+    p = pred.detach().requires_grad_(True)
+    S.LeastSquares(R, dev)(img, p).backward()
 torch.cuda.synchronize()
 print("loss", loss.item())
