@@ -585,6 +585,9 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
     if (BWD) {
         const bool active = (fabsf(p.x) < kActive) && (st.csl > -kDeep);
         if (SQ_ANY(active)) {
+#if defined(SQ_BWD_HOOK) && defined(__CUDA_ARCH__)
+            SQ_BWD_HOOK(active);                // debug builds: statistics of how many lanes carry gradient
+#endif
             // do/dF = -k o (1-o) = -k eo o^2 ; the -k is applied in finalize
             const float W = active ? p.eo * p.o * p.o : 0.0f;
             Fwd fa = p.f;

@@ -20,6 +20,11 @@
 #include <new>
 
 #include "../../include/sqloss.h"
+#ifdef SQ_TIMELINE      // tools/timeline.py: [0] backward blocks executed (warp level), [1] lanes that carried gradient in them
+__device__ unsigned long long g_bwd_stats[2];
+#define SQ_BWD_HOOK(a) do { const unsigned m_ = __ballot_sync(0xffffffffu, (a)); if ((threadIdx.x & 31) == 0) { \
+    atomicAdd(&g_bwd_stats[0], 1ull); atomicAdd(&g_bwd_stats[1], (unsigned long long)__popc(m_)); } } while (0)
+#endif
 #include "sq_core.cuh"
 
 using namespace sq;
@@ -1144,6 +1149,9 @@ int sq_device_sm_count(int device, int* sm_count) {
 #ifdef SQ_TIMELINE
 int sq_debug_timeline(unsigned long long* host_out, int n) {
     return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * 3 * (size_t)n);
+}
+int sq_debug_bwd(unsigned long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_bwd_stats, sizeof(unsigned long long) * 2);
 }
 int sq_debug_plan(unsigned long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, g_plan_ts, sizeof(unsigned long long) * 16);

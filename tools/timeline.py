@@ -73,3 +73,8 @@ if h.sq_debug_plan(pl.ctypes.data_as(ctypes.c_void_p)) == 0:
     for o, who in ((0, "thread 0 (prep)"), (8, "thread 100 (pixel sum)")):
         n = int(pl[o + 7]); t = (pl[o:o + n] - pl[o]).astype(np.int64) / 1e3
         print(f"plan kernel block 7, {who}: stage stamps (us) {t.round(2).tolist()}")
+
+bw = np.zeros(2, dtype=np.uint64)
+h.sq_debug_bwd.argtypes = [ctypes.c_void_p]
+if h.sq_debug_bwd(bw.ctypes.data_as(ctypes.c_void_p)) == 0 and bw[0]:
+    print(f"backward blocks executed (all calls so far): {int(bw[0])} warp-steps, {bw[1] / bw[0]:.1f} of 32 lanes carrying gradient on average")
