@@ -172,6 +172,7 @@ struct Scratch {
     double* per_sample;    // [batch]
     double* tv_sum;        // [batch] sum |target| over the sample's pixels (ImplicitLoss)
     unsigned long long* counts;   // [batch][2] (IoU)
+    unsigned char* item_class;   // [batch * rows_per_sample] cost class of every item (kClasses - 1: proven empty, no row)
     int* queue;            // [kClasses][queue_cap] item ids by cost class; nullptr: items are taken in index order
     int queue_cap;
 };
@@ -196,6 +197,7 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     const size_t cap = (size_t)L.rows_per_sample * (size_t)batch;
     const bool queued = L.rows_per_sample <= kPlanMaxItems && cap < (1u << 30);
     const size_t o_queue = take(queued ? sizeof(int) * kClasses * cap : 0);
+    const size_t o_cls = take(queued ? cap : 0);
     if (s) {
         s->ctl = reinterpret_cast<Control*>(base + o_ctl);
         s->pred = reinterpret_cast<SampleFull*>(base + o_pred);
@@ -205,6 +207,7 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
         s->tv_sum = reinterpret_cast<double*>(base + o_tv);
         s->counts = reinterpret_cast<unsigned long long*>(base + o_cnt);
         s->queue = queued ? reinterpret_cast<int*>(base + o_queue) : nullptr;
+        s->item_class = queued ? reinterpret_cast<unsigned char*>(base + o_cls) : nullptr;
         s->queue_cap = (int)cap;
     }
     return off;
@@ -284,7 +287,7 @@ template <int NS>
 __global__ void __launch_bounds__(kPlanThreads)
 plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, int heads, Grid g, Layout L, float bound,
             SampleFull* out_a, SampleFull* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap,
-            float* zero_rows, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
+            unsigned char* item_class, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
             const int* __restrict__ col_off, double* tv_sum) {
     __shared__ SampleFull Ssh[NS];
     __shared__ unsigned char cls[kPlanMaxItems];
@@ -376,12 +379,8 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
         }
         int c = kClasses - 1;                              // proven empty (group_planes is an upper bound)
         if (cost > 0) { c = 0; while (c < kClasses - 2 && (cost << (c + 1)) <= max_cost) ++c; }
-        else if (zero_rows) {                              // the column kernel will not touch this item
-            float* row = zero_rows + (size_t)(b * J + j) * kAccN;
-#pragma unroll
-            for (int i = 0; i < kAccN; ++i) row[i] = 0.f;
-        }
         cls[j] = (unsigned char)c;
+        if (item_class) item_class[(size_t)b * J + j] = (unsigned char)c;      // finalize skips the rows of proven-empty items
         atomicAdd(&ccnt[c], 1u);
     }
     __syncthreads();
@@ -948,7 +947,7 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
                 const float* __restrict__ partials, double loss_norm, double grad_scale,
                 int dtype, void* __restrict__ grad, double* __restrict__ per_sample,
                 double* __restrict__ per_sample_user, double* __restrict__ loss_out, unsigned int* ticket,
-                const double* __restrict__ loss_offset) {
+                const double* __restrict__ loss_offset, const unsigned char* __restrict__ item_class) {
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     __shared__ SampleFull S;
     __shared__ double wpart[kFinThreads / 32][kAccN];
@@ -963,6 +962,8 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
         for (int i = 0; i < kAccN; ++i) s[i] = 0.0;
         const float* base = partials + (size_t)b * items_per_sample * kAccN;
         for (int j = t; j < items_per_sample; j += kFinThreads) {
+            // items the plan kernel proved empty were never processed: they have no row (and contribute nothing)
+            if (item_class && item_class[(size_t)b * items_per_sample + j] == kClasses - 1) continue;
             const float2* p = reinterpret_cast<const float2*>(base + (size_t)j * kAccN);     // rows are 72 bytes: 8-aligned
 #pragma unroll
             for (int i = 0; i < kAccN / 2; ++i) { const float2 v = __ldcg(p + i); s[2 * i] += (double)v.x; s[2 * i + 1] += (double)v.y; }
@@ -1116,17 +1117,17 @@ int launch_prep(const void* params, int dtype, int batch, bool clamp, const Grid
 struct PlanTarget { const float* target; long long tstride; const int* row_off; const int* col_off; };
 
 int launch_plan(const void* params_a, const void* params_b, int dtype, int batch, bool clamp, const Grid& g,
-                const Layout& L, float bound, const Scratch& s, unsigned long long* counts, float* zero_rows,
+                const Layout& L, float bound, const Scratch& s, unsigned long long* counts, unsigned char* item_class,
                 const PlanTarget* pt, cudaStream_t st, bool heads = false) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
     int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
     if (params_b)
         plan_kernel<2><<<batch, kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, 0, g, L, bound, s.tru, s.pred,
-                                                       s.ctl, counts, queue, s.queue_cap, zero_rows, nullptr, 0, nullptr, nullptr,
+                                                       s.ctl, counts, queue, s.queue_cap, queue ? item_class : nullptr, nullptr, 0, nullptr, nullptr,
                                                        nullptr);
     else
         plan_kernel<1><<<batch, kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, heads ? 1 : 0, g, L, bound, s.pred, nullptr,
-                                                       s.ctl, counts, queue, s.queue_cap, zero_rows,
+                                                       s.ctl, counts, queue, s.queue_cap, queue ? item_class : nullptr,
                                                        pt ? pt->target : nullptr, pt ? pt->tstride : 0,
                                                        pt ? pt->row_off : nullptr, pt ? pt->col_off : nullptr,
                                                        pt ? s.tv_sum : nullptr);
@@ -1191,8 +1192,11 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
     const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, implicit_cull_bound(sharpness * kLog2e)};
     if (depth_out)      // the column kernel writes the depth only where a column group can hold occupancy
         SQ_TRY(cudaMemsetAsync(depth_out, 0, sizeof(float) * (size_t)batch * n * n, st));
+#ifdef SQ_SKIP_COLUMN      // timing experiment: without the column kernel nobody restores the control block
+    SQ_TRY(cudaMemsetAsync(s.ctl, 0, sizeof(Control), st));
+#endif
     const PlanTarget pt{target, target_stride_b, row_off, col_off};
-    rc = launch_plan(pred, nullptr, pred_dtype, batch, true, g, L, P.bound, s, nullptr, target ? s.partials : nullptr,
+    rc = launch_plan(pred, nullptr, pred_dtype, batch, true, g, L, P.bound, s, nullptr, target ? s.item_class : nullptr,
                      target ? &pt : nullptr, st, heads);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
@@ -1225,7 +1229,7 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
         SQ_TRY(launch_dependent(finalize_kernel<FIN_IMPLICIT>, batch, kFinThreads, st, pdl,
                                 s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn,
                                 -(double)sharpness * (double)tau / (nn * n * (double)batch), pred_dtype, grad_pred, s.per_sample,
-                                per_sample, loss_out, &s.ctl->ticket, s.tv_sum));
+                                per_sample, loss_out, &s.ctl->ticket, s.tv_sum, queue ? s.item_class : nullptr));
         SQ_TRY(cudaGetLastError());
     }
 #endif
@@ -1259,7 +1263,7 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, SQ_EXP_CPT);
     const float kl = sharpness * kLog2e, bound = cull_bound_bits(kl, 24.0f);
-    rc = launch_plan(true_params, pred, params_dtype, batch, true, g, L, bound, s, nullptr, s.partials, nullptr, st);
+    rc = launch_plan(true_params, pred, params_dtype, batch, true, g, L, bound, s, nullptr, s.item_class, nullptr, st);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
@@ -1274,7 +1278,7 @@ int sq_explicit_loss(const void* true_params, const void* pred, int params_dtype
     finalize_kernel<FIN_EXPLICIT><<<batch, kFinThreads, 0, st>>>(
         s.pred, g, batch, L.rows_per_sample, s.partials, (double)mult / n3,
         2.0 * (double)sharpness * (double)mult / (n3 * (double)batch), params_dtype, grad_pred, s.per_sample,
-        per_sample, loss_out, &s.ctl->ticket, nullptr);
+        per_sample, loss_out, &s.ctl->ticket, nullptr, queue ? s.item_class : nullptr);
     SQ_TRY(cudaGetLastError());
     return 0;
 }
@@ -1322,7 +1326,7 @@ int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_siz
     SQ_TRY(cudaGetLastError());
     finalize_kernel<FIN_LSQ><<<batch, kFinThreads, 0, st>>>(s.pred, g, batch, ips, s.partials, 1.0, 2.0 / (double)batch,
                                                    pred_dtype, grad_pred, s.per_sample, per_sample, loss_out, &s.ctl->ticket,
-                                                   nullptr);
+                                                   nullptr, nullptr);
     SQ_TRY(cudaGetLastError());
     return 0;
 }
