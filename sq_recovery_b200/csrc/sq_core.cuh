@@ -24,6 +24,10 @@
 #define SQ_HD inline
 #endif
 
+#if !defined(__CUDACC__)
+struct float2 { float x, y; };          // host build (tests/emu): the type only appears in unused default arguments
+#endif
+
 namespace sq {
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -561,7 +565,26 @@ struct ColGrad {       // two-moment accumulators of one column
 // running state of one column walk
 struct ColState {
     float csl, cssum, tsum, psh, seen, T;
+    // SQ_BWD_COMPACT (device): this lane's column of the warp's queue of gradient-carrying points, entries queued, and
+    // whether a point had to be handled on the spot because the queue was full
+    float2* q;
+    int qn;
+    bool spilled;
 };
+
+// SQ_BWD_COMPACT.  The backward block runs for the whole warp as soon as ONE lane carries gradient, and the surface
+// crosses the 32 columns of a patch on different planes: 5.7 of 32 lanes do on average (tools/timeline.py).  So during
+// the walk a gradient-carrying lane only notes (plane, prefix of T) in a small shared-memory queue; after the walk --
+// when the column's suffix weight U and the sign of (depth - target) are known -- the queued points of all 32 columns
+// are dealt out evenly to the lanes, which redo the forward for their point and run the backward once, weighted,
+// straight into the item's sums.  A lane whose queue is full falls back to the on-the-spot two-moment path.
+#if !defined(SQ_NO_BWD_COMPACT) && !defined(SQ_BWD_COMPACT)
+#define SQ_BWD_COMPACT 1
+#endif
+#ifndef SQ_BWD_DEPTH
+#define SQ_BWD_DEPTH 16
+#endif
+constexpr int kBwdDepth = SQ_BWD_DEPTH;
 
 // geometry + forward chain + occupancy of one plane (independent of the scan state: two planes can be in flight)
 struct Plane { Fwd f; float x, eo, o, cf; };
@@ -588,20 +611,36 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
 #if defined(SQ_BWD_HOOK) && defined(__CUDA_ARCH__)
             SQ_BWD_HOOK(active);                // debug builds: statistics of how many lanes carry gradient
 #endif
-            // do/dF = -k o (1-o) = -k eo o^2 ; the -k is applied in finalize
-            const float W = active ? p.eo * p.o * p.o : 0.0f;
-            Fwd fa = p.f;
-            if (!active) fwd_neutral(fa);       // keep inactive lanes finite
-            Bwd b;
-            point_backward<FIX>(fa, W, b);
-            st.seen = active ? 1.0f : st.seen;
-            const float pp = st.psh;       // T in front of this point (since the first active one)
-            for (int i = 0; i < 3; ++i) {
-                cg.gs0[i] += b.gs[i];            cg.gs1[i] = fmaf(pp, b.gs[i], cg.gs1[i]);
-                const float gz = b.gs[i] * p.cf;
-                cg.gz0[i] += gz;                 cg.gz1[i] = fmaf(pp, gz, cg.gz1[i]);
+            bool now = active;                  // lanes whose point is handled on the spot
+#if defined(__CUDA_ARCH__) && defined(SQ_BWD_COMPACT)
+            if (st.q) {
+                const bool room = st.qn < kBwdDepth;
+                if (active && room) {
+                    st.q[st.qn * 32] = make_float2(p.cf, st.psh);      // plane, T in front of it since the first active point
+                    ++st.qn;
+                    st.seen = 1.0f;
+                }
+                now = active && !room;
+                st.spilled = st.spilled || now;
             }
-            for (int i = 0; i < 2; ++i) { cg.ge0[i] += b.ge[i]; cg.ge1[i] = fmaf(pp, b.ge[i], cg.ge1[i]); }
+            if (SQ_ANY(now))
+#endif
+            {
+                // do/dF = -k o (1-o) = -k eo o^2 ; the -k is applied in finalize
+                const float W = now ? p.eo * p.o * p.o : 0.0f;
+                Fwd fa = p.f;
+                if (!now) fwd_neutral(fa);          // keep the other lanes finite
+                Bwd b;
+                point_backward<FIX>(fa, W, b);
+                st.seen = now ? 1.0f : st.seen;
+                const float pp = st.psh;       // T in front of this point (since the first active one)
+                for (int i = 0; i < 3; ++i) {
+                    cg.gs0[i] += b.gs[i];            cg.gs1[i] = fmaf(pp, b.gs[i], cg.gs1[i]);
+                    const float gz = b.gs[i] * p.cf;
+                    cg.gz0[i] += gz;                 cg.gz1[i] = fmaf(pp, gz, cg.gz1[i]);
+                }
+                for (int i = 0; i < 2; ++i) { cg.ge0[i] += b.ge[i]; cg.ge1[i] = fmaf(pp, b.ge[i], cg.ge1[i]); }
+            }
         }
         st.psh = fmaf(st.seen, st.T, st.psh);
     }
@@ -616,10 +655,15 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
 #endif
 
 template <bool BWD, bool FIX = true>
+// bwd_q / U_out / qn_out / spilled_out: SQ_BWD_COMPACT only (see ColState); colgrad11 then holds only what was
+// handled on the spot.
 SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams& P,
-                            const float* bh, const float* bl, int c_lo, int c_hi, float* colgrad11) {
+                            const float* bh, const float* bl, int c_lo, int c_hi, float* colgrad11,
+                            float2* bwd_q = nullptr, float* U_out = nullptr, int* qn_out = nullptr,
+                            bool* spilled_out = nullptr) {
     // planes in front of the range: o = 0, cs = 0, T = 1 each
     ColState st;
+    st.q = bwd_q; st.qn = 0; st.spilled = false;
     st.csl = 0.f;                                     // -tau log2(e) cs
     st.T = 1.0f;                                      // 2^csl
     st.tsum = (float)(g.n - 1 - c_hi);
@@ -657,6 +701,7 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
     st.cssum = fmaf(nb, st.csl, st.cssum);
     if (BWD) {
         const float U = fmaf(nb * st.seen, st.T, st.psh);
+        if (U_out) { *U_out = U; *qn_out = st.qn; *spilled_out = st.spilled; }
         for (int i = 0; i < 3; ++i) {
             colgrad11[i]     = fmaf(U, cg.gs0[i], -cg.gs1[i]);
             colgrad11[3 + i] = fmaf(U, cg.gz0[i], -cg.gz1[i]);

@@ -22,6 +22,8 @@
 #include "../../include/sqloss.h"
 #ifdef SQ_TIMELINE      // tools/timeline.py: [0] backward blocks executed (warp level), [1] lanes that carried gradient in them
 __device__ unsigned long long g_bwd_stats[2];
+#endif
+#if defined(SQ_TIMELINE) && defined(SQ_BWD_STATS)      // the two atomics per block slow the kernel 3x: only when asked for
 #define SQ_BWD_HOOK(a) do { const unsigned m_ = __ballot_sync(0xffffffffu, (a)); if ((threadIdx.x & 31) == 0) { \
     atomicAdd(&g_bwd_stats[0], 1ull); atomicAdd(&g_bwd_stats[1], (unsigned long long)__popc(m_)); } } while (0)
 #endif
@@ -633,6 +635,12 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
     __shared__ Sample Ssh[THREADS / 32];
     __shared__ __align__(16) float tiles[THREADS / 32][kRedFloats];
+#ifdef SQ_BWD_COMPACT       // per warp: queued gradient-carrying points, per-column data for them, the deal-out list
+    constexpr int kQW = BWD ? THREADS / 32 : 1, kQN = BWD ? kBwdDepth * 32 : 1;
+    __shared__ float2 qent[kQW][kQN];
+    __shared__ float colinfo[kQW][BWD ? 10 * 32 : 1];
+    __shared__ unsigned short qmap[kQW][kQN];
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& S = Ssh[warp];
     // Persistent warps pull work items from a global cursor, most expensive first (plan kernel).  The next item and its
@@ -710,7 +718,13 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 float depth;
 #ifndef SQ_FIXHOIST      // hoisting the exact-zero fix-up out of the walk (two copies of the loop): measured 1 us
                          // SLOWER per call once everything else was in place (profiles/tune_r01.txt) -> off
+#ifdef SQ_BWD_COMPACT
+                float U = 0.f; int qn = 0; bool spilled = false;
+                depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg, BWD ? &qent[BWD ? warp : 0][lane] : nullptr,
+                                                   &U, &qn, &spilled);
+#else
                 depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
+#endif
 #else
                 if (__any_sync(0xffffffffu, column_zero_possible(S, bh)))
                     depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
@@ -723,6 +737,85 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 // fill the gap; an item claimed at the start of a long walk, on the other hand, is work no idle warp can
                 // take -- during the end-game that was the tail of the kernel.
                 if (k == L.cpt - 1 && wp.claim(lane)) pre.fetch(samples + L.sample_of(wp.next), lane);
+#endif
+#if defined(SQ_BWD_COMPACT)
+                if (BWD) {
+                    // sign of (depth - target) per column; 0 for masked lanes
+                    float wsg = 0.f;
+                    if (valid) {
+                        if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
+                        const float diff = depth - tv;
+                        loss_sum += fabsf(diff) - fabsf(tv);
+                        wsg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                    }
+                    if (wsg == 0.f) qn = 0;                    // its points carry no gradient after all
+                    int incl = qn;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t_; }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - qn;
+                    const bool any_spill = __any_sync(0xffffffffu, spilled && wsg != 0.f);
+                    if (total > 0 || any_spill) {
+                        Acc acc;
+                        float v[kRedStride];
+                        if (folded) { tile_get(tiles[warp], v); array_to_acc(v, acc); } else acc_zero(acc);
+                        if (spilled && wsg != 0.f) implicit_fold(acc, cg, wsg, dxy[0], dxy[1]);      // handled on the spot
+                        if (total > 0) {
+                            float* ci = colinfo[warp];
+                            ci[0 * 32 + lane] = bh[0]; ci[1 * 32 + lane] = bh[1]; ci[2 * 32 + lane] = bh[2];
+                            ci[3 * 32 + lane] = bl[0]; ci[4 * 32 + lane] = bl[1]; ci[5 * 32 + lane] = bl[2];
+                            ci[6 * 32 + lane] = U; ci[7 * 32 + lane] = wsg; ci[8 * 32 + lane] = dxy[0]; ci[9 * 32 + lane] = dxy[1];
+                            for (int e = 0; e < qn; ++e) qmap[warp][off + e] = (unsigned short)((lane << 8) | e);
+                            __syncwarp();
+                            // every lane gets a point per round; two rounds in flight (two independent MUFU chains)
+                            auto dealt = [&](int j, Bwd& bq, float& cfq, float& dx_, float& dy_) {
+                                const bool has = j < total;
+                                const int m_ = has ? qmap[warp][j] : 0, l_ = m_ >> 8, e_ = m_ & 255;
+                                float2 en = qent[warp][e_ * 32 + l_];
+                                if (!has) en = make_float2(1.0f, 0.0f);      // idle lane of the last round: never-written slot
+                                const float cbh[3] = {ci[0 * 32 + l_], ci[1 * 32 + l_], ci[2 * 32 + l_]};
+                                const float cbl[3] = {ci[3 * 32 + l_], ci[4 * 32 + l_], ci[5 * 32 + l_]};
+                                Plane pl;
+                                plane_forward<true>(S, P, cbh, cbl, en.x, pl);
+                                // weight: do/dF factor, suffix sum of T behind the point (U - prefix), sign of the column
+                                float W = pl.eo * pl.o * pl.o * (ci[6 * 32 + l_] - en.y) * ci[7 * 32 + l_];
+                                if (!has) { fwd_neutral(pl.f); W = 0.f; }
+                                point_backward<true>(pl.f, W, bq);
+                                cfq = en.x; dx_ = ci[8 * 32 + l_]; dy_ = ci[9 * 32 + l_];
+                            };
+                            auto add = [&](const Bwd& bq, float cfq, float dx_, float dy_) {
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) {
+                                    acc.gs[i] += bq.gs[i];
+                                    acc.gm[3 * i + 0] = fmaf(bq.gs[i], dx_, acc.gm[3 * i + 0]);
+                                    acc.gm[3 * i + 1] = fmaf(bq.gs[i], dy_, acc.gm[3 * i + 1]);
+                                    acc.gm[3 * i + 2] = fmaf(bq.gs[i], cfq, acc.gm[3 * i + 2]);
+                                    acc.wa[i] += bq.wa[i];
+                                }
+                                acc.ge[0] += bq.ge[0]; acc.ge[1] += bq.ge[1];
+                            };
+                            int j = lane;
+#ifndef SQ_DENSE_ILP1
+                            for (; j - lane + 32 < total; j += 64) {
+                                Bwd b0, b1; float c0, c1, x0, x1, y0, y1;
+                                dealt(j, b0, c0, x0, y0);
+                                dealt(j + 32, b1, c1, x1, y1);
+                                add(b0, c0, x0, y0);
+                                add(b1, c1, x1, y1);
+                            }
+#endif
+                            for (; j - lane < total; j += 32) {
+                                Bwd b0; float c0, x0, y0;
+                                dealt(j, b0, c0, x0, y0);
+                                add(b0, c0, x0, y0);
+                            }
+                            __syncwarp();
+                        }
+                        acc_to_array(acc, v);
+                        v[18] = v[19] = 0.f;
+                        tile_put(tiles[warp], v);
+                        folded = true;
+                    }
+                } else
 #endif
                 if (valid) {
                     if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;

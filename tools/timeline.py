@@ -1,7 +1,8 @@
 """Per-warp timeline of the implicit fwd+bwd kernel (debug build with -DSQ_TIMELINE): when each persistent warp
 started, fetched its last item and finished.  Shows how much of the kernel is end-game (warps idle, work left elsewhere).
 
-    python tools/timeline.py [extra -D defs]
+    python tools/timeline.py [extra -D defs]          (SQ_BWD_STATS: also count gradient-carrying lanes per backward
+                                                      block -- slows the kernel, the timeline is then not meaningful)
 """
 import ctypes
 import os
