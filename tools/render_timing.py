@@ -1,3 +1,4 @@
+"""Time ImplicitLoss(256).depth_projection on a batch of 256 (the data-generation path)."""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from oracle import sq_oracle as O
