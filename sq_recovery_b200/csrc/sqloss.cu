@@ -150,7 +150,10 @@ struct ColIter {
 // z planes is in (max / 2^(k+1), max / 2^k]; the last class holds items PROVEN empty (the estimate is an upper bound),
 // which the column kernels never touch.
 constexpr int kClasses = 8;
-constexpr int kPlanThreads = 512;
+#ifndef SQ_PLAN_THREADS
+#define SQ_PLAN_THREADS 512
+#endif
+constexpr int kPlanThreads = SQ_PLAN_THREADS;
 constexpr int kPlanMaxItems = 8192;      // items per sample the plan kernel can classify (more: index order)
 
 // First 256 bytes of every scratch buffer.  qcount and retired must be ZERO when a call starts: sq_scratch_init()
@@ -1032,7 +1035,10 @@ enum { FIN_IMPLICIT = 0, FIN_EXPLICIT = 1, FIN_LSQ = 2 };
 // independent: one L2 round trip), a fixed-order tree (shuffles inside a warp, then the warps in index order) gives the
 // 18 totals, thread 0 applies the Jacobians.  The last block to arrive averages the batch in index order.  Fixed order
 // everywhere: results are bit-reproducible run to run.
-constexpr int kFinThreads = 128;
+#ifndef SQ_FIN_THREADS
+#define SQ_FIN_THREADS 128
+#endif
+constexpr int kFinThreads = SQ_FIN_THREADS;
 
 template <int KIND>
 __global__ void __launch_bounds__(kFinThreads)
