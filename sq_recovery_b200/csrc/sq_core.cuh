@@ -599,6 +599,72 @@ SQ_HD void plane_forward(const Sample& S, const ImplicitParams& P, const float* 
     p.o = occupancy(p.f.F, P.kl, p.x, p.eo);
 }
 
+// SQ_F32X2: 0 = off, 1 = forward-only kernels (default), 2 = also the fwd+bwd kernel.  Measured (profiles/tune_r01.txt):
+// forward-only kernel -3.7 %; fwd+bwd kernel no gain (the register pairing costs as many moves as the packing saves).
+#ifndef SQ_F32X2
+#define SQ_F32X2 1
+#endif
+#if defined(__CUDA_ARCH__) && SQ_F32X2
+// Packed fp32 (Blackwell fma/add/sub/mul.f32x2: two operations per issue slot).  The two planes in flight execute the same
+// sequence on different data, and the kernel is bound by issue slots, so their non-MUFU arithmetic is done pairwise.
+struct F2 { float x, y; };
+__device__ __forceinline__ F2 f2(float a, float b) { F2 r; r.x = a; r.y = b; return r; }
+#define SQ_F2_OP3(name, op) \
+    __device__ __forceinline__ F2 name(F2 a, F2 b, F2 c) { F2 r; \
+        asm("{\n .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n " op " rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd;\n}" \
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y)); return r; }
+#define SQ_F2_OP2(name, op) \
+    __device__ __forceinline__ F2 name(F2 a, F2 b) { F2 r; \
+        asm("{\n .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n " op " rd, ra, rb;\n mov.b64 {%0, %1}, rd;\n}" \
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y)); return r; }
+SQ_F2_OP3(fma2, "fma.rn.ftz.f32x2")
+SQ_F2_OP2(add2, "add.rn.ftz.f32x2")
+SQ_F2_OP2(sub2, "sub.rn.ftz.f32x2")
+SQ_F2_OP2(mul2, "mul.rn.ftz.f32x2")
+
+// plane_forward() for two planes at once
+template <bool FIX>
+__device__ __forceinline__ void plane_forward2(const Sample& S, const ImplicitParams& P, const float* bh, const float* bl,
+                                               float cfa, float cfb, Plane& pa, Plane& pb) {
+    pa.cf = cfa; pb.cf = cfb;
+    const F2 cf = f2(cfa, cfb);
+    F2 s[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        s[i] = add2(fma2(cf, f2(S.dh[i], S.dh[i]), f2(bh[i], bh[i])), fma2(cf, f2(S.dl[i], S.dl[i]), f2(bl[i], bl[i])));
+    pa.f.sx = s[0].x; pa.f.sy = s[1].x; pa.f.sz = s[2].x;
+    pb.f.sx = s[0].y; pb.f.sy = s[1].y; pb.f.sz = s[2].y;
+    F2 m[3] = {s[0], s[1], s[2]};
+    if (FIX) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { m[i].x = (m[i].x == 0.0f) ? kAbsFix : m[i].x; m[i].y = (m[i].y == 0.0f) ? kAbsFix : m[i].y; }
+    }
+    const F2 pxy = f2(S.pxy, S.pxy), one = f2(1.0f, 1.0f);
+    const F2 lA = mul2(pxy, f2(lg2_abs(m[0].x), lg2_abs(m[0].y)));
+    const F2 lB = mul2(pxy, f2(lg2_abs(m[1].x), lg2_abs(m[1].y)));
+    const F2 lC = mul2(f2(S.pz, S.pz), f2(lg2_abs(m[2].x), lg2_abs(m[2].y)));
+    const F2 d1 = sub2(lA, lB);
+    const F2 t1 = f2(ex2_neg_abs(d1.x), ex2_neg_abs(d1.y));
+    const F2 u1 = add2(t1, one);
+    const F2 h1 = f2(lg2(u1.x), lg2(u1.y));
+    const F2 lE = mul2(f2(S.e21, S.e21), add2(f2(fmaxf(lA.x, lB.x), fmaxf(lA.y, lB.y)), h1));
+    const F2 d2 = sub2(lE, lC);
+    const F2 t2 = f2(ex2_neg_abs(d2.x), ex2_neg_abs(d2.y));
+    const F2 u2 = add2(t2, one);
+    const F2 h2 = f2(lg2(u2.x), lg2(u2.y));
+    const F2 lG = add2(f2(fmaxf(lE.x, lC.x), fmaxf(lE.y, lC.y)), h2);
+    const F2 yy = mul2(f2(S.e1, S.e1), lG);
+    const F2 F = f2(ex2(yy.x), ex2(yy.y));
+    const F2 xx = fma2(F, f2(P.kl, P.kl), f2(-P.kl, -P.kl));
+    const F2 eo = f2(ex2(xx.x), ex2(xx.y));
+    const F2 v = add2(eo, one);
+    pa.f.d1 = d1.x; pa.f.t1 = t1.x; pa.f.h1 = h1.x; pa.f.d2 = d2.x; pa.f.t2 = t2.x; pa.f.h2 = h2.x; pa.f.lG = lG.x; pa.f.F = F.x;
+    pb.f.d1 = d1.y; pb.f.t1 = t1.y; pb.f.h1 = h1.y; pb.f.d2 = d2.y; pb.f.t2 = t2.y; pb.f.h2 = h2.y; pb.f.lG = lG.y; pb.f.F = F.y;
+    pa.x = xx.x; pa.eo = eo.x; pa.o = rcp(v.x);
+    pb.x = xx.y; pb.eo = eo.y; pb.o = rcp(v.y);
+}
+#endif
+
 // scan step of one plane: transmittance, suffix-sum bookkeeping and (for gradient-carrying warps) the backward
 template <bool BWD, bool FIX>
 SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, ColGrad& cg) {
@@ -679,11 +745,18 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
 #if SQ_IMP_ILP >= 2
     for (; c - (SQ_IMP_ILP - 1) >= c_lo; c -= SQ_IMP_ILP, cfi -= (float)SQ_IMP_ILP) {
         Plane p[SQ_IMP_ILP];
+#if defined(__CUDA_ARCH__) && SQ_F32X2 && SQ_IMP_ILP == 2
+        if (SQ_F32X2 >= 2 || !BWD) {
+            plane_forward2<FIX>(S, P, bh, bl, cfi, (c - 1 == 0) ? S.cf0 : cfi - 1.0f, p[0], p[1]);
+        } else
+#endif
+        {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < SQ_IMP_ILP; ++j)
-            plane_forward<FIX>(S, P, bh, bl, (j > 0 && c - j == 0) ? S.cf0 : cfi - (float)j, p[j]);
+            for (int j = 0; j < SQ_IMP_ILP; ++j)
+                plane_forward<FIX>(S, P, bh, bl, (j > 0 && c - j == 0) ? S.cf0 : cfi - (float)j, p[j]);
+        }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
