@@ -153,7 +153,7 @@ def ncu_summary():
 # ----------------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch.distributed as dist
-    from oracle import sq_oracle as O                       # input distributions only (randsq / randquat)
+    from sq_recovery_b200 import inputs as O                # seeded randsq / randquat workloads
     import sq_recovery_b200 as S
     from sq_recovery_b200 import _lib
     from sq_recovery_b200.functional import HostContext

@@ -62,7 +62,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--scale", type=float, default=1.0)
     args = ap.parse_args()
-    from oracle import sq_oracle as O                       # randsq / randquat distributions (visu.py:55-56)
+    from sq_recovery_b200 import inputs as O          # seeded randsq / randquat workloads
     dev = torch.device("cuda:0")
     params = O.random_params(args.n, args.seed)
     render(params[:min(args.n, 256)], dev)                  # warm-up: workspace allocation, module load

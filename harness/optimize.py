@@ -27,7 +27,7 @@ LR = 0.001                                                  # visu.py:120
 
 def descend(crit, true, pred, steps, lr=LR, record=None):
     """`steps` updates of visu.py:176-186 for every row of `pred` (modified in place); returns the last batch-mean loss.
-    `crit(true, pred)` is any of the loss classes (this package's or the oracle's); true = targets of that loss."""
+    `crit(true, pred)` is any of the loss classes (or anything with their call signature); true = targets of that loss."""
     B = pred.shape[0]
     loss = None
     for _ in range(steps):
@@ -53,7 +53,7 @@ def main():
     args = ap.parse_args()
     import sq_recovery_b200 as S
     from sq_recovery_b200 import distributed as D
-    from oracle import sq_oracle as O                       # input distributions only
+    from sq_recovery_b200 import inputs as O          # seeded randsq / randquat workloads
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)

@@ -33,7 +33,7 @@ def main():
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from oracle import sq_oracle as O                      # input distributions only
+    from sq_recovery_b200 import inputs as O          # seeded randsq / randquat workloads
     b0, b1 = D.shard_range(args.pairs, rank, world)
     true = O.random_params(args.pairs, 0)[b0:b1].to(dev)
     pred = O.random_params(args.pairs, 1)[b0:b1].to(dev)

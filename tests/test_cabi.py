@@ -56,12 +56,17 @@ def test_no_cpu_fallback():
         S.ImplicitLoss(64, torch.device("cpu"), 1.5, 260)
     with pytest.raises(RuntimeError):
         S.ExplicitLoss(32, "cpu")
-    # nothing under the product package imports, includes or executes anything under oracle/
-    pkg = os.path.join(ROOT, "sq_recovery_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
-                assert not re.search(r"#include\s+[\"<][^\">]*oracle", text), f
-                assert "tests/emu" not in text or f == "sq_core.cuh", f     # the host build is a test tool only
+    # nothing under the product package, the harnesses or the tools imports, includes or executes anything under
+    # oracle/ (test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU reference leg may)
+    for sub in ("sq_recovery_b200", "harness", "tools", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                    assert not re.search(r"#include\s+[\"<][^\">]*oracle", text), f
+                    assert "tests/emu" not in text or f == "sq_core.cuh", f     # the host build is a test tool only
+    # bench.py: the oracle / the shipped reference only inside the CPU reference leg
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    gpu_arm = bench.split("def run_gpu(")[1].split("\ndef main(")[0]
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", gpu_arm, flags=re.M)

@@ -1,6 +1,6 @@
 """One-off parity check of ImplicitLoss fwd+bwd at large grids (R = 128, 96) against the fp64 oracle (slow on the CPU)."""
-import sys, torch, numpy as np, time
-sys.path.insert(0, '/root/repo')
+import os, sys, torch, numpy as np, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import sq_oracle as O
 import sq_recovery_b200 as S
 dev = torch.device('cuda:0')

@@ -1,8 +1,8 @@
 """Run the implicit loss + backward six times on the same inputs and report whether the results are bit-identical, then
 compare with the oracle.  Used with SQ_LIBSQLOSS=<variant .so> to check experimental builds (e.g. -DSQ_BWD_DEPTH=2, which
 forces the on-the-spot fallback of the compacted backward)."""
-import sys, torch
-sys.path.insert(0, '/root/repo')
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import sq_oracle as O
 import sq_recovery_b200 as S
 dev = torch.device('cuda:0')

@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import sq_oracle as O      # input distributions only
+from sq_recovery_b200 import inputs as O      # seeded randsq / randquat workloads
 import sq_recovery_b200 as S
 
 B, R = 256, 64

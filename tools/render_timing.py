@@ -1,7 +1,7 @@
 """Time ImplicitLoss(256).depth_projection on a batch of 256 (the data-generation path)."""
 import sys, torch
 sys.path.insert(0, '/root/repo')
-from oracle import sq_oracle as O
+from sq_recovery_b200 import inputs as O      # seeded randsq / randquat workloads
 import sq_recovery_b200 as S
 dev = torch.device('cuda:0')
 crit = S.ImplicitLoss(256, dev, 1.5, 260)

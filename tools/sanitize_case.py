@@ -14,7 +14,7 @@ if "--bounds" in sys.argv:      # build a library with index traps and run this 
     os.environ["SQ_LIBSQLOSS"] = out
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import sq_oracle as O      # input distributions only
+from sq_recovery_b200 import inputs as O      # seeded randsq / randquat workloads
 import sq_recovery_b200 as S
 from sq_recovery_b200.functional import HostContext
 

@@ -14,7 +14,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import sq_oracle as O
+from sq_recovery_b200 import inputs as O      # seeded randsq / randquat workloads
 from sq_recovery_b200 import _lib as L0
 import sq_recovery_b200 as S
 from sq_recovery_b200.functional import nearest_offsets

@@ -16,7 +16,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import sq_oracle as O          # input distributions only
+from sq_recovery_b200 import inputs as O      # seeded randsq / randquat workloads
 from sq_recovery_b200 import _lib as L0     # prototypes
 
 B, R = int(os.environ.get("SQ_B", 256)), 64
