@@ -200,7 +200,7 @@ def run_gpu(args):
             gph = torch.cuda.CUDAGraph()
             img, pred = sets[k]
             p = pred.detach().requires_grad_(True)
-            with torch.cuda.graph(gph):
+            with torch.cuda.graph(gph, stream=side):
                 loss_k = crit(img, p)
                 loss_k.backward()
             graphs.append((gph, loss_k, p))
@@ -209,7 +209,7 @@ def run_gpu(args):
         # leave the GPU idle between steps.  Same kernels, same work per step.
         quad = torch.cuda.CUDAGraph()
         quad_out = []
-        with torch.cuda.graph(quad):
+        with torch.cuda.graph(quad, stream=side):
             for k in range(4):
                 img, pred = sets[k]
                 p = pred.detach().requires_grad_(True)

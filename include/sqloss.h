@@ -102,6 +102,23 @@ int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_siz
                      double* loss_out, double* per_sample, void* grad_pred,
                      void* scratch, size_t scratch_bytes, sq_stream_t stream);
 
+/* LeastSquares.energy_function (torch/classes.py:318-356) on an explicit point list -- the stored-point-cloud variant.
+ *   points      compacted structure of arrays, fp32: row 0 = x, row 1 = y, row 2 = z of the points of ALL samples back
+ *               to back; rows are `stride` floats apart; stride is a multiple of 4 and >= the total point count rounded
+ *               up to a multiple of 4, and `points` is 16-byte aligned (the kernel reads four points per 16-byte load)
+ *   offsets     [batch+1] int64: sample b owns points [offsets[b], offsets[b+1])
+ *   max_points  the largest offsets[b+1] - offsets[b] (host value: it sizes the launch)
+ *   per_sample  [batch] fp64 energies sum_pts (sqrt(a1 a2 a3) (F - 1))^2      (may be NULL)
+ *   loss_out    [1] fp64 their mean over the batch (:371)                      (may be NULL)
+ *   grad_pred   [batch,12] d per_sample[b] / d pred[b]                         (NULL = forward only)
+ * Scratch: sq_points_scratch_bytes(batch, max_points).
+ */
+size_t sq_points_scratch_bytes(int batch, long long max_points);
+int sq_least_squares_points(const void* pred, int pred_dtype, int batch, const float* points, long long stride,
+                            const long long* offsets, long long max_points,
+                            double* loss_out, double* per_sample, void* grad_pred,
+                            void* scratch, size_t scratch_bytes, sq_stream_t stream);
+
 /* ExplicitLoss.occupancy / IoUAccuracy.ins_outs (torch/classes.py:138-189, 394-426): the full field [batch,n,n,n]
  * (index order [x][y][z], fp32).  mode 0: F without clamp/fix-up (ins_outs); mode 1: sigmoid(sharpness (1-F))
  * with clamp and fix-up (occupancy).  A convenience for callers that want the grid itself.

@@ -32,6 +32,17 @@ def _preprocess_sq(p: torch.Tensor) -> torch.Tensor:
     return torch.cat([a.clamp(0.05, 1), e.clamp(0.1, 1), t.clamp(0, 1), q], dim=-1)
 
 
+def _no_history(p: torch.Tensor, what: str) -> None:
+    """The grid-returning conveniences are forward-only here (the reference returns fp64 grids WITH autograd history,
+    torch/classes.py:138-189, 232-282, 394-426).  Differentiating through them would silently yield no gradient, so a
+    tensor that asks for one is refused instead."""
+    if torch.is_grad_enabled() and isinstance(p, torch.Tensor) and p.requires_grad:
+        raise RuntimeError(
+            f"sq_recovery_b200: {what}() is forward-only (fp32 grid, no autograd history); it was given a tensor that "
+            "requires grad.  Call it under torch.no_grad() / on p.detach(), or differentiate through the loss call "
+            "(loss(true, pred).backward()), which is fused.")
+
+
 class _GridLoss:
     """Shared bookkeeping: the reference stores these attributes on every loss object."""
 
@@ -74,10 +85,11 @@ class ExplicitLoss(_GridLoss):
 
     def occupancy(self, p):
         """(B, n, n, n) sigmoid(5 (1 - F)) (classes.py:138-189), fp32, no autograd."""
+        _no_history(p, "occupancy")
         return Fn.field(p, self._n, self._step, self._z0, 1, 5.0)
 
     def __call__(self, true, pred):
-        return Fn.ExplicitLossFn.apply(true, pred, self._n, self._step, self._z0, 5.0, 100.0)
+        return Fn.ExplicitLossFn.apply(true, pred, self._n, self._step, self._z0, 5.0, 100.0, torch.is_grad_enabled())
 
 
 class ImplicitLoss(_GridLoss):
@@ -91,11 +103,12 @@ class ImplicitLoss(_GridLoss):
 
     def depth_projection(self, p):
         """(B, R, R) depth render in image orientation (classes.py:232-282), fp32, no autograd."""
+        _no_history(p, "depth_projection")
         return Fn.depth_projection(p, self._n, self._step, self._z0, float(self.tau), float(self.sigmoid_sharpness))
 
     def __call__(self, true, pred):
         return Fn.ImplicitLossFn.apply(true, pred, self._n, self._step, self._z0, float(self.tau),
-                                       float(self.sigmoid_sharpness))
+                                       float(self.sigmoid_sharpness), False, torch.is_grad_enabled())
 
     def from_heads(self, true, raw_heads):
         """The same loss taken straight from the RAW outputs of the four linear heads, (B, 12) =
@@ -103,7 +116,7 @@ class ImplicitLoss(_GridLoss):
         (torch/models.py:28,52,75,98), the torch.cat of torch/train.py:89 and all their backward kernels run inside
         the loss kernels.  Not in the reference; equals ``self(true, heads(raw_heads))``."""
         return Fn.ImplicitLossFn.apply(true, raw_heads, self._n, self._step, self._z0, float(self.tau),
-                                       float(self.sigmoid_sharpness), True)
+                                       float(self.sigmoid_sharpness), True, torch.is_grad_enabled())
 
 
 class LeastSquares(_GridLoss):
@@ -116,8 +129,14 @@ class LeastSquares(_GridLoss):
     def xyz(self):
         raise AttributeError("LeastSquares has no grid (torch/classes.py:303-308)")
 
+    def energy_function(self, batch_points, params):
+        """Per-sample energies (B,) of explicit point lists (classes.py:318-356): ``batch_points[i]`` is a (3, m_i) tensor
+        of (x, y, z) rows, ``params`` (B, 12).  The lists are packed into one compacted structure-of-arrays buffer and
+        read with float4 loads by ``sq_least_squares_points``; gradient reaches ``params``."""
+        return Fn.lsq_energy(batch_points, params)
+
     def __call__(self, true, pred):
-        return Fn.LeastSquaresFn.apply(true, pred, int(self.render_size))
+        return Fn.LeastSquaresFn.apply(true, pred, int(self.render_size), torch.is_grad_enabled())
 
 
 class IoUAccuracy(_GridLoss):
@@ -130,6 +149,7 @@ class IoUAccuracy(_GridLoss):
 
     def ins_outs(self, p):
         """(B, R, R, R) inside-outside values F (classes.py:394-426), fp32, no autograd."""
+        _no_history(p, "ins_outs")
         return Fn.field(p, self._n, self._step, 0.0, 0)
 
     def counts(self, true, pred):

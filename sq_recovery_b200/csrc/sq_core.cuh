@@ -507,6 +507,18 @@ SQ_HD int footprint_planes(const Sample& S, const Grid& g, float bound, float cx
     return c_hi >= c_lo ? c_hi - c_lo + 1 : 0;
 }
 
+// Footprint (centre and half extents, in grid steps) of the 32-slot column group `group` in the x-fastest layout used
+// when n is not a multiple of 8: slots [32 group, 32 group + 31] of the n*n columns, slot = ib * n + ia.  For n < 32 a
+// group spans up to ceil(32 / n) + 1 rows, so the row span is computed, not assumed.
+SQ_HD void xfast_group_footprint(int n, int group, float& cx, float& cy, float& hx, float& hy) {
+    const int first = group * 32;
+    int last = first + 31;
+    if (last > n * n - 1) last = n * n - 1;
+    const int ib0 = first / n, ia0 = first - ib0 * n, ib1 = last / n, ia1 = last - ib1 * n;
+    if (ib1 == ib0) { cx = 0.5f * (float)(ia0 + ia1); hx = 0.5f * (float)(ia1 - ia0); cy = (float)ib0; hy = 0.f; }
+    else { cx = 0.5f * (float)(n - 1); hx = cx; cy = 0.5f * (float)(ib0 + ib1); hy = 0.5f * (float)(ib1 - ib0); }
+}
+
 #if defined(__CUDA_ARCH__)
 #define SQ_ANY(p) __any_sync(0xffffffffu, (p))
 #define SQ_WARP_MAX(v) __reduce_max_sync(0xffffffffu, (v))

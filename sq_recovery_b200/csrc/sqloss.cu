@@ -279,9 +279,7 @@ __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, flo
         const int pw = L.n >> 3, pb = group / pw, pa = group - pb * pw;
         cx = (float)(pa << 3) + 3.5f; cy = (float)(pb << 2) + 1.5f; hx = 3.5f; hy = 1.5f;
     } else {
-        const int slot = group * 32, ib = slot / L.n, ia = slot - ib * L.n;
-        if (ia + 31 < L.n) { cx = (float)ia + 15.5f; cy = (float)ib; hx = 15.5f; hy = 0.f; }
-        else { cx = 0.5f * (float)(L.n - 1); hx = cx; cy = (float)ib + 0.5f; hy = 0.5f; }      // wraps into the next row
+        xfast_group_footprint(L.n, group, cx, cy, hx, hy);
     }
     return footprint_planes(S, g, bound, cx, cy, hx, hy);
 }
@@ -1028,6 +1026,38 @@ lsq_kernel(const SampleFull* __restrict__ samples, int R, int items_per_sample,
     block_reduce_store(acc, red, partials + (size_t)item * kAccN);
 }
 
+// LeastSquares.energy_function on an explicit, compacted point list (classes.py:318-356): structure of arrays x[], y[],
+// z[] (rows of `points`, `stride` floats apart) holding the lists of all samples back to back, sample b owning
+// [offsets[b], offsets[b+1]).  One block per (sample, chunk of kThreads * 4 points); a thread reads four consecutive
+// points of each coordinate row with one 16-byte load.  The chunk grid is aligned to multiples of four points of the
+// WHOLE buffer (rows are 16-byte aligned and padded to a multiple of four), points outside the sample's range are masked.
+// 12 bytes per point from HBM, read once.
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads)
+lsq_points_kernel(const SampleFull* __restrict__ samples, int chunks_per_sample, const float* __restrict__ points,
+                  long long stride, const long long* __restrict__ offsets, float* __restrict__ partials) {
+    __shared__ Sample S;
+    __shared__ float red[kWarps][kAccN];
+    const int item = blockIdx.x;
+    const int b = item / chunks_per_sample, chunk = item - b * chunks_per_sample;
+    load_sample(&S, samples + b);
+    __syncthreads();
+    Acc acc;
+    acc_zero(acc);
+    const long long lo = offsets[b], hi = offsets[b + 1];
+    const long long base = (lo & ~3LL) + ((long long)chunk * kThreads + threadIdx.x) * 4;
+    if (base < hi) {
+        const float4 x4 = __ldg(reinterpret_cast<const float4*>(points + base));
+        const float4 y4 = __ldg(reinterpret_cast<const float4*>(points + stride + base));
+        const float4 z4 = __ldg(reinterpret_cast<const float4*>(points + 2 * stride + base));
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (base + k >= lo && base + k < hi) acc.loss += lsq_point<BWD>(S, xs[k], ys[k], zs[k], acc);
+    }
+    block_reduce_store(acc, red, partials + (size_t)item * kAccN);
+}
+
 // ------------------------------------------------------------------------------------------------ finalize
 enum { FIN_IMPLICIT = 0, FIN_EXPLICIT = 1, FIN_LSQ = 2 };
 
@@ -1107,7 +1137,7 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
         double gr[12];
         finalize_sample(S, g, acc, grad_scale * vol, KIND != FIN_LSQ, gr);
         if (KIND == FIN_LSQ)
-            for (int i = 0; i < 3; ++i) gr[i] += S.mask[i] * (vol * S.ia[i]) * acc[17] / (double)batch;
+            for (int i = 0; i < 3; ++i) gr[i] += S.mask[i] * (vol * S.ia[i]) * acc[17] * (0.5 * grad_scale);   // d (a1 a2 a3) / d a_i
         if (S.heads) heads_backward(S.hp, S.hrn, S.q, gr);
         for (int i = 0; i < 12; ++i) {
             if (dtype == SQ_F64) static_cast<double*>(grad)[12 * (size_t)b + i] = gr[i];
@@ -1428,6 +1458,41 @@ int sq_least_squares(const void* pred, int pred_dtype, int batch, int render_siz
                                                    nullptr, nullptr);
     SQ_TRY(cudaGetLastError());
     return 0;
+}
+
+int sq_least_squares_points(const void* pred, int pred_dtype, int batch, const float* points, long long stride,
+                            const long long* offsets, long long max_points, double* loss_out, double* per_sample,
+                            void* grad_pred, void* scratch, size_t scratch_bytes, sq_stream_t stream) {
+    if (!points || !offsets || max_points < 0 || stride < 0 || (stride & 3)) return (int)cudaErrorInvalidValue;
+    // scratch rows: one per chunk of kThreads * 4 points; sq_scratch_bytes(batch, n) provides for n * n points per sample
+    const long long chunks64 = (max_points + 3 + kThreads * 4 - 1) / (kThreads * 4);
+    const int chunks = chunks64 > 0 ? (int)chunks64 : 1;
+    int n = 1;
+    while ((long long)n * n < (long long)chunks * kThreads) ++n;
+    Scratch s;
+    int rc = check_scratch(batch, n, scratch, scratch_bytes, &s);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Grid g = make_grid(2, 1.0, 0.0);
+    rc = launch_prep(pred, pred_dtype, batch, true, g, s.pred, s.ctl, st);
+    if (rc) return rc;
+    if (grad_pred) lsq_points_kernel<true><<<batch * chunks, kThreads, 0, st>>>(s.pred, chunks, points, stride, offsets, s.partials);
+    else lsq_points_kernel<false><<<batch * chunks, kThreads, 0, st>>>(s.pred, chunks, points, stride, offsets, s.partials);
+    SQ_TRY(cudaGetLastError());
+    // per-sample energies: the gradient is d per_sample[b] / d pred[b] (no 1 / batch)
+    finalize_kernel<FIN_LSQ><<<batch, kFinThreads, 0, st>>>(s.pred, g, batch, chunks, s.partials, 1.0, 2.0, pred_dtype, grad_pred,
+                                                   s.per_sample, per_sample, loss_out, &s.ctl->ticket, nullptr, nullptr);
+    SQ_TRY(cudaGetLastError());
+    return 0;
+}
+
+size_t sq_points_scratch_bytes(int batch, long long max_points) {
+    if (batch <= 0 || max_points < 0) return 0;
+    const long long chunks64 = (max_points + 3 + kThreads * 4 - 1) / (kThreads * 4);
+    const int chunks = chunks64 > 0 ? (int)chunks64 : 1;
+    int n = 1;
+    while ((long long)n * n < (long long)chunks * kThreads) ++n;
+    return scratch_layout(batch, n, nullptr, nullptr);
 }
 
 int sq_field(const void* params, int params_dtype, int batch, int n, double step, double z0, int mode,

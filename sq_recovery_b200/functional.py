@@ -49,20 +49,38 @@ class _on_device:
             self._ctx.__exit__(*exc)
 
 
-def _get_scratch(device: torch.device, batch: int, n: int) -> torch.Tensor:
+def _get_scratch(device: torch.device, batch: int, n: int, need: Optional[int] = None) -> torch.Tensor:
     """Per (device, stream) workspace, grown on demand and reused (stream-ordered, so reuse is safe)."""
-    need = _need.get((batch, n))
     if need is None:
-        need = _need[(batch, n)] = _lib.lib().sq_scratch_bytes(batch, n)
+        need = _need.get((batch, n))
+        if need is None:
+            need = _need[(batch, n)] = _lib.lib().sq_scratch_bytes(batch, n)
     key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(device))
     buf = _scratch.get(key)
     if buf is None or buf.numel() < need:
+        if torch.cuda.is_current_stream_capturing():
+            # Allocated here, the buffer would come from the graph's private pool and its one-time zeroing would be a node
+            # of THIS graph only: another graph captured on the same stream and replayed first would start the kernels on
+            # uninitialised queue counters.  So the workspace of a capture stream must exist before the capture starts.
+            raise RuntimeError(
+                "sq_recovery_b200: no workspace for this stream yet (or it is too small for this batch / grid size) and "
+                "the stream is being captured into a CUDA graph.  Run the same call once eagerly on the capture stream "
+                "first -- `s = torch.cuda.Stream(); with torch.cuda.stream(s): loss_fn(true, pred)` -- and capture with "
+                "`torch.cuda.graph(g, stream=s)`, or call sq_recovery_b200.functional.prepare_stream(device, batch, n, s).")
         buf = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
         with torch.cuda.device(device):      # zero the control block once; every call leaves it zero (include/sqloss.h)
             _lib.check(_lib.lib().sq_scratch_init(ctypes.c_void_p(buf.data_ptr()), buf.numel(), _stream(device)),
                        "sq_scratch_init")
         _scratch[key] = buf
     return buf
+
+
+def prepare_stream(device, batch: int, n: int, stream: "torch.cuda.Stream") -> None:
+    """Create (and zero the control block of) the workspace `stream` will use for calls with up to this batch and grid
+    size.  Needed only before capturing a CUDA graph on a stream that has not run the call eagerly."""
+    device = torch.device(device)
+    with torch.cuda.stream(stream):
+        _get_scratch(device, batch, n)
 
 
 def _params(p: torch.Tensor) -> Tuple[torch.Tensor, int]:
@@ -105,7 +123,7 @@ class ImplicitLossFn(torch.autograd.Function):
     """ImplicitLoss.__call__ (torch/classes.py:284-295) -> 0-dim fp64 loss; gradient reaches ``pred`` only."""
 
     @staticmethod
-    def forward(ctx, true, pred, n, step, z0, tau, sharpness, heads=False):
+    def forward(ctx, true, pred, n, step, z0, tau, sharpness, heads=False, grad_mode=True):
         # heads=True: `pred` holds the RAW outputs of the four network heads; sigmoid / quaternion normalisation, the
         # torch.cat and their Jacobians run inside the kernels (sq_implicit_loss_heads, SURVEY 8f-3)
         _require_cuda(pred, "pred"); _require_cuda(true, "true")
@@ -116,7 +134,9 @@ class ImplicitLossFn(torch.autograd.Function):
         if img.shape[0] != B:
             raise ValueError("true and pred disagree on the batch size")
         row_off, col_off = nearest_offsets(img.shape[2], img.shape[3], n, dev)
-        want_grad = ctx.needs_input_grad[1]
+        # needs_input_grad follows pred.requires_grad whatever the grad mode: under torch.no_grad() (validation,
+        # train.py:135) the forward-only kernel runs
+        want_grad = grad_mode and ctx.needs_input_grad[1]
         loss = torch.empty((), dtype=torch.float64, device=dev)
         grad = torch.empty_like(p) if want_grad else None
         scratch = _get_scratch(dev, B, n)
@@ -136,7 +156,7 @@ class ImplicitLossFn(torch.autograd.Function):
         g = None
         if ctx.grad is not None:
             g = (ctx.grad * go).to(ctx.pred_dtype)      # 0-dim fp64 `go` does not promote the result: one kernel
-        return None, g, None, None, None, None, None, None
+        return None, g, None, None, None, None, None, None, None
 
 
 class ExplicitLossFn(torch.autograd.Function):
@@ -144,7 +164,7 @@ class ExplicitLossFn(torch.autograd.Function):
     ``true`` (no reference caller asks for one) is the same kernel with the roles swapped."""
 
     @staticmethod
-    def forward(ctx, true, pred, n, step, z0, sharpness, mult):
+    def forward(ctx, true, pred, n, step, z0, sharpness, mult, grad_mode=True):
         _require_cuda(pred, "pred"); _require_cuda(true, "true")
         dev = pred.device
         if true.dtype == torch.float64 or pred.dtype == torch.float64:
@@ -167,10 +187,10 @@ class ExplicitLossFn(torch.autograd.Function):
             _lib.check(rc, "sq_explicit_loss")
 
         ctx.grad_true = ctx.grad_pred = None
-        if ctx.needs_input_grad[0]:
+        if grad_mode and ctx.needs_input_grad[0]:
             ctx.grad_true = torch.empty_like(t)
             run(p, t, ctx.grad_true)
-        ctx.grad_pred = torch.empty_like(p) if ctx.needs_input_grad[1] else None
+        ctx.grad_pred = torch.empty_like(p) if (grad_mode and ctx.needs_input_grad[1]) else None
         run(t, p, ctx.grad_pred)
         ctx.dtypes = (true.dtype, pred.dtype)
         return loss
@@ -183,21 +203,23 @@ class ExplicitLossFn(torch.autograd.Function):
             gt = (ctx.grad_true * go).to(ctx.dtypes[0])
         if ctx.grad_pred is not None:
             gp = (ctx.grad_pred * go).to(ctx.dtypes[1])
-        return gt, gp, None, None, None, None, None
+        return gt, gp, None, None, None, None, None, None
 
 
 class LeastSquaresFn(torch.autograd.Function):
     """LeastSquares.__call__ (torch/classes.py:358-371) -> 0-dim loss in fp32 like the reference (``:319``)."""
 
     @staticmethod
-    def forward(ctx, true, pred, render_size):
+    def forward(ctx, true, pred, render_size, grad_mode=True):
         _require_cuda(pred, "pred"); _require_cuda(true, "true")
         dev = pred.device
         img = _image(true)
         p, tag = _params(pred)
         B = p.shape[0]
+        if img.shape[0] != B:
+            raise ValueError("true and pred disagree on the batch size")
         row_off, col_off = nearest_offsets(img.shape[2], img.shape[3], render_size, dev)
-        want_grad = ctx.needs_input_grad[1]
+        want_grad = grad_mode and ctx.needs_input_grad[1]
         loss = torch.empty((), dtype=torch.float64, device=dev)
         grad = torch.empty_like(p) if want_grad else None
         scratch = _get_scratch(dev, B, render_size)
@@ -216,7 +238,63 @@ class LeastSquaresFn(torch.autograd.Function):
         g = None
         if ctx.grad is not None:
             g = (ctx.grad * go).to(ctx.pred_dtype)
-        return None, g, None
+        return None, g, None, None
+
+
+class LsqEnergyFn(torch.autograd.Function):
+    """LeastSquares.energy_function (torch/classes.py:318-356) on a packed point list -> (B,) energies."""
+
+    @staticmethod
+    def forward(ctx, params, packed, offsets, max_points, grad_mode=True):
+        _require_cuda(params, "params")
+        dev = params.device
+        p, tag = _params(params)
+        B = p.shape[0]
+        want_grad = grad_mode and ctx.needs_input_grad[0]
+        per = torch.empty(B, dtype=torch.float64, device=dev)
+        grad = torch.empty_like(p) if want_grad else None
+        L = _lib.lib()
+        scratch = _get_scratch(dev, B, 0, need=L.sq_points_scratch_bytes(B, max_points))
+        with _on_device(dev):
+            rc = L.sq_least_squares_points(_ptr(p), tag, B, _ptr(packed), packed.shape[1], _ptr(offsets), max_points, None,
+                                           _ptr(per), _ptr(grad), _ptr(scratch), scratch.numel(), _stream(dev))
+        _lib.check(rc, "sq_least_squares_points")
+        ctx.grad = grad
+        ctx.pred_dtype = params.dtype
+        return per.to(params.dtype if params.dtype.is_floating_point else torch.float32)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        g = None
+        if ctx.grad is not None:
+            g = (ctx.grad * go.reshape(-1, 1).to(ctx.grad.dtype)).to(ctx.pred_dtype)
+        return g, None, None, None, None
+
+
+def pack_points(batch_points, device):
+    """List of (3, m_i) tensors -> ((3, stride) fp32 structure-of-arrays buffer, int64 offsets [B+1] on the device, max m_i).
+    The sizes are host metadata (tensor shapes): no device synchronisation."""
+    counts = []
+    for pts in batch_points:
+        if pts.dim() != 2 or pts.shape[0] != 3:
+            raise ValueError(f"expected point lists of shape (3, m), got {tuple(pts.shape)}")
+        counts.append(int(pts.shape[1]))
+    total = sum(counts)
+    stride = max(4, (total + 3) // 4 * 4)
+    packed = torch.zeros((3, stride), dtype=torch.float32, device=device)
+    if total:
+        packed[:, :total].copy_(torch.cat([pts.detach().to(device=device, dtype=torch.float32) for pts in batch_points], dim=1))
+    offsets = torch.tensor(np.concatenate(([0], np.cumsum(counts))), dtype=torch.int64).to(device)
+    return packed, offsets, max(counts) if counts else 0
+
+
+def lsq_energy(batch_points, params: torch.Tensor) -> torch.Tensor:
+    if len(batch_points) != params.shape[0]:
+        raise ValueError("one point list per parameter row is required")
+    _require_cuda(params, "params")
+    packed, offsets, max_points = pack_points(batch_points, params.device)
+    return LsqEnergyFn.apply(params, packed, offsets, max_points, torch.is_grad_enabled())
 
 
 def iou_counts(true: torch.Tensor, pred: torch.Tensor, n: int, step: float, z0: float = 0.0):

@@ -169,6 +169,18 @@ long long emu_check_culling(const double* params, int B, int n, double step, dou
             for (int ic = 0; ic < n; ++ic)
                 if (inside[((size_t)ia * n + ib) * n + ic] && (ic < c_lo || ic > c_hi)) ++bad;
         }
+        if (n % 8 != 0)      // x-fastest layout: 32-slot groups that wrap over several rows when n < 32
+            for (int group = 0; group * 32 < n * n; ++group) {
+                ++ptot;
+                float cx, cy, hx, hy;
+                xfast_group_footprint(n, group, cx, cy, hx, hy);
+                if (footprint_planes(S, g, bound, cx, cy, hx, hy) != 0) continue;
+                ++pe;
+                for (int slot = group * 32; slot < group * 32 + 32 && slot < n * n; ++slot) {
+                    const int ib = slot / n, ia = slot - ib * n;
+                    for (int ic = 0; ic < n; ++ic) if (inside[((size_t)ia * n + ib) * n + ic]) ++bad;
+                }
+            }
         if (n % 8 == 0)
             for (int pa = 0; pa < n / 8; ++pa) for (int pb = 0; pb < n / 4; ++pb) {
                 ++ptot;

@@ -98,3 +98,23 @@ def test_culling_never_drops_occupancy(kind):
     assert bad == 0
     if kind != "explicit":                                             # the proof is not vacuous: it catches a good part
         assert empty > 0.2 * total, (empty, total)
+
+
+@pytest.mark.parametrize("n", [9, 12, 17, 20, 33])
+@pytest.mark.parametrize("kind", ["implicit", "iou"])
+def test_proven_empty_groups_in_the_x_fastest_layout(kind, n):
+    """Grids whose size is not a multiple of 8 hand out 32 consecutive columns of the x-fastest order per work item; for
+    n < 32 such a group wraps over several rows.  The plan kernel's "proven empty" must hold for every column of the
+    group's real footprint (round-1 advisor finding: the footprint assumed two rows)."""
+    from oracle import sq_oracle as O
+    log2e = 1.4426950408889634
+    rs = np.random.RandomState(n)
+    p = O.random_params(400, 300 + n).double().numpy()
+    p[:, 0:3] = rs.uniform(0.05, 0.5, (400, 3))
+    p[:, 5:8] = rs.uniform(0.1, 0.9, (400, 3))
+    if kind == "iou":
+        bad, empty, total = E.check_culling(p, n, 1 / (n - 1), 0.0, 0, 1.001, 1.0 + 1e-12)
+    else:
+        kl = 260 * log2e
+        bad, empty, total = E.check_culling(p, n, 1 / (n - 1), 1e-4, 1, float(np.sqrt((1 + 40 / kl) * 1.002)), 1 + 40 / kl)
+    assert bad == 0 and total > 0
