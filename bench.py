@@ -42,19 +42,36 @@ def workload_config(n_gpus):
                         f"{R}^3 grid, depth maps {H}x{W} (BASELINE config 2)",
             "points_per_step_per_gpu": B * R ** 3, "batch_per_gpu": B, "render_size": R,
             "l2": "inputs rotate over 4 independent batches (4 x 67 MB of depth maps > 126 MB L2)",
+            "reference_arm_sample": REFERENCE_SAMPLE,
             "parallelism": f"{n_gpus} x independent batch shards, no data-path collective"}
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
+REFERENCE_SAMPLE = (f"the reference arm and cpu_baseline run a B={CPU_SAMPLE_B} slice of this workload per step on the host cores "
+                    f"({CPU_SAMPLE_B * R ** 3} points), scaled per point")
+
+
 def cpu_reference(steps, warmup):
-    """The oracle port (loop form = the reference's per-sample op sequence, torch fp64) on all host cores."""
+    """The reference's own ImplicitLoss (UNMODIFIED torch/classes.py staged under oracle/_ref by oracle/build_ref.py;
+    the oracle port's loop form when that is absent) on all host cores, fwd+bwd, on a B=8 slice of the workload.
+    This is the one place bench.py executes anything under oracle/ (the checker timed as the CPU baseline)."""
+    from oracle import ref_import
     from oracle import sq_oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    cpu = torch.device("cpu")
     true = O.random_params(CPU_SAMPLE_B, 0)
     pred = O.perturbed_params(true, 5)
-    img = torch.rand(CPU_SAMPLE_B, 1, H, W, generator=torch.Generator().manual_seed(0))
-    crit = O.ImplicitLoss(R, "cpu", TAU, SHARP, form="loop")
+    if ref_import.available() or ref_import.staged():
+        rc, _ = ref_import.load()
+        crit, kind = rc.ImplicitLoss(R, cpu, TAU, SHARP), "reference"
+        what = f"UNMODIFIED reference torch/classes.py ImplicitLoss({R}, cpu, {TAU}, {SHARP:g}) (oracle/_ref)"
+    else:
+        crit, kind = O.ImplicitLoss(R, "cpu", TAU, SHARP, form="loop"), "port"
+        what = "oracle/sq_oracle.py loop form (the reference's per-sample op sequence; oracle/_ref not staged)"
+    with torch.no_grad():   # depth maps: the reference's own render of the true parameters at R, blown up to H x W so that
+        small = crit.depth_projection(true).float()          # the nearest resize inside the loss returns it unchanged
+    img = small.repeat_interleave(H // R, dim=1).repeat_interleave(W // R, dim=2).unsqueeze(1).contiguous()
     times = []
     for i in range(warmup + steps):
         p = pred.clone().requires_grad_(True)
@@ -65,18 +82,23 @@ def cpu_reference(steps, warmup):
         if i >= warmup:
             times.append(dt)
     pts = CPU_SAMPLE_B * R ** 3
-    best = float(np.min(times))     # best step: the most favourable reading for the CPU on a shared host
-    return {"value": pts / best / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"B={CPU_SAMPLE_B} slice of the workload ({pts} points per step), best of {steps} steps after {warmup} "
-                      f"warm-up ({best * 1e3:.1f} ms; mean {np.mean(times) * 1e3:.1f} ms), oracle/sq_oracle.py loop form "
-                      f"(the reference's per-sample op sequence, torch fp64, {threads} threads)"}, best
+    mean = float(np.mean(times))
+    cpu_name = ""
+    try:
+        cpu_name = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        pass
+    return {"value": pts / mean / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"B={CPU_SAMPLE_B} slice of the workload ({pts} points per step), {steps} timed steps after {warmup} warm-up: "
+                      f"mean {mean * 1e3:.1f} ms, best {np.min(times) * 1e3:.1f} ms per fwd+bwd; {what}; torch fp64, "
+                      f"{threads} threads on {os.cpu_count()} host cores ({cpu_name})"}, mean
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     cb, mean = cpu_reference(steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak",

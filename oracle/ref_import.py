@@ -1,8 +1,8 @@
 """Import the UNMODIFIED reference loss classes from /root/reference (dev container only).
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  ``/root/reference`` does not exist on the GPU
-box, so this module is used only by ``oracle/make_goldens.py`` and by CPU tests that skip when
-the tree is absent.  ``torch/classes.py`` imports three packages that are not installed here
+box; there the verbatim copies staged by ``oracle/build_ref.py`` under ``oracle/_ref/`` are imported
+instead (``bench.py --impl reference``, ``cpu_baseline`` and one ``-m gpu`` test).  ``torch/classes.py`` imports three packages that are not installed here
 (``h5py`` :3, ``torchsummary`` :12, ``matplotlib`` :15 and ``helpers.py:5-7``); none is touched
 by the loss classes, so empty stand-in modules satisfy the imports.
 """
@@ -14,10 +14,17 @@ import types
 import warnings
 
 REFERENCE_ROOT = os.environ.get("SQ_REFERENCE_ROOT", "/root/reference")
+STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # oracle/build_ref.py: travels to the GPU box
 
 
 def available() -> bool:
+    """The full reference tree (dev container): classes AND data/example_imgs."""
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "torch", "classes.py"))
+
+
+def staged() -> bool:
+    """The verbatim copies under oracle/_ref/ (GPU box)."""
+    return os.path.isfile(os.path.join(STAGED, "torch", "classes.py"))
 
 
 def _stub(name: str, **attrs):
@@ -34,9 +41,14 @@ def _stub(name: str, **attrs):
 
 
 def load():
-    """Return the reference ``classes`` and ``quaternion`` modules (imported by bare name, as the reference does)."""
-    if not available():
-        raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT}")
+    """Return the reference ``classes`` and ``quaternion`` modules (imported by bare name, as the reference does): from
+    /root/reference when the tree is mounted, else from the staged copies."""
+    if available():
+        tdir = os.path.join(REFERENCE_ROOT, "torch")
+    elif staged():
+        tdir = os.path.join(STAGED, "torch")
+    else:
+        raise FileNotFoundError(f"reference not found under {REFERENCE_ROOT} nor staged under {STAGED}")
     _stub("h5py")
     _stub("torchsummary", summary=lambda *a, **k: None)
     mpl = _stub("matplotlib")
@@ -45,7 +57,6 @@ def load():
         setattr(mpl, sub, m)
     lines = _stub("matplotlib.lines", Line2D=object)
     mpl.lines = lines
-    tdir = os.path.join(REFERENCE_ROOT, "torch")
     if tdir not in sys.path:
         sys.path.insert(0, tdir)
     with warnings.catch_warnings():

@@ -682,3 +682,40 @@ def test_config2_whole_batch_against_oracle(dev, S):
     keep = np.concatenate(keep)
     assert keep.sum() >= B - 8
     check(l, gr, ref_loss, np.concatenate(ref_grad), what="config 2 whole batch", keep=keep)
+
+
+def test_against_the_live_reference(dev, S):
+    """The UNMODIFIED reference classes (staged under oracle/_ref by oracle/build_ref.py; /root/reference itself in the dev
+    container) run on the CPU next to the CUDA path on the same inputs: all four classes, R = 16 and 32."""
+    from oracle import ref_import
+    if not (ref_import.available() or ref_import.staged()):
+        pytest.skip("reference not staged under oracle/_ref (python -m oracle.build_ref in the dev container)")
+    rc, rq = ref_import.load()
+    cpu = torch.device("cpu")
+    for R, B, seed in ((16, 6, 201), (32, 4, 202)):
+        true = O.random_params(B, seed)
+        for pred in (O.random_params(B, seed + 50), O.perturbed_params(true, seed)):
+            with torch.no_grad():
+                img = rc.ImplicitLoss(2 * R, cpu, 1.5, 260).depth_projection(true).float().unsqueeze(1)
+            oc = O.ImplicitLoss(R, "cpu", 1.5, 260)
+            for args in ((1.5, 260), (1, 100)):
+                p = pred.clone().requires_grad_(True)
+                ref = rc.ImplicitLoss(R, cpu, *args)(img, p); ref.backward()
+                l, gr = run(S.ImplicitLoss(R, dev, *args), img, pred, dev)
+                check(l, gr, ref.item(), p.grad.double().numpy(), what=f"reference implicit{args} R={R}",
+                      keep=unambiguous(O.ImplicitLoss(R, "cpu", *args), img, pred))
+            p = pred.clone().requires_grad_(True)
+            ref = rc.ExplicitLoss(R, cpu)(true, p); ref.backward()
+            l, gr = run(S.ExplicitLoss(R, dev), true, pred, dev)
+            check(l, gr, ref.item(), p.grad.double().numpy(), what=f"reference explicit R={R}")
+            ref = rc.IoUAccuracy(R, cpu)(true, pred).item()
+            assert abs(S.IoUAccuracy(R, dev)(true.to(dev), pred.to(dev)).item() - ref) < 1e-7
+            per = rc.IoUAccuracy(R, cpu, reduce=False)(true, pred)
+            np.testing.assert_allclose(S.IoUAccuracy(R, dev, reduce=False)(true.to(dev), pred.to(dev)).cpu().numpy(),
+                                       per.numpy(), rtol=1e-12)
+            p = pred.clone().requires_grad_(True)
+            ref = rc.LeastSquares(R, cpu)(img, p); ref.backward()
+            l, gr = run(S.LeastSquares(R, dev), img, pred, dev)
+            check(l, gr, ref.item(), p.grad.double().numpy(), loss_rtol=1e-4, rtol=2e-3, atol=1e-4, what=f"reference lsq R={R}")
+    q = torch.tensor(O.randquat(np.random.RandomState(1)))
+    np.testing.assert_allclose(S.quaternion.mat_from_quaternion(q.to(dev)).cpu().numpy(), rq.mat_from_quaternion(q).numpy(), atol=1e-15)

@@ -15,9 +15,15 @@ dev = torch.device("cuda:0")
 B, R = 32, 64
 true = O.random_params(B, 0); pred = O.perturbed_params(true, 7)
 img = S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(true.to(dev)).unsqueeze(1).contiguous()
-oc = O.ImplicitLoss(R, dev, 1.5, 260, form="loop")
+from oracle import ref_import
+if ref_import.available() or ref_import.staged():       # the UNMODIFIED reference classes with device='cuda:0' 
+    oc = ref_import.load()[0].ImplicitLoss(R, dev, 1.5, 260)
+    ref_name = "reference torch/classes.py ImplicitLoss on cuda:0 (fp64, oracle/_ref)"
+else:
+    oc = O.ImplicitLoss(R, dev, 1.5, 260, form="loop")
+    ref_name = "oracle loop form on cuda:0 (fp64)"
 crit = S.ImplicitLoss(R, dev, 1.5, 260)
-for name, fn in (("oracle loop form on cuda:0 (fp64)", oc), ("sq_recovery_b200", crit)):
+for name, fn in ((ref_name, oc), ("sq_recovery_b200", crit)):
     for rep in range(3):
         p = pred.to(dev).requires_grad_(True)
         torch.cuda.synchronize(); t0 = time.perf_counter()
