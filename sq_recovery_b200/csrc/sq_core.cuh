@@ -17,6 +17,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define SQ_HD __host__ __device__ __forceinline__
@@ -25,7 +26,7 @@
 #endif
 
 #if !defined(__CUDACC__)
-struct float2 { float x, y; };          // host build (tests/emu): the type only appears in unused default arguments
+struct float2 { float x, y; };          // host build (tests/emu)
 #endif
 
 namespace sq {
@@ -139,6 +140,8 @@ struct Sample {
     float wd[3];              // w_i * dh_i,  w = (qw, qw, 1)
     float qw, qa, qia, qB1;   // 2^(e2-1), sum w_i dh_i^2, its reciprocal, 2^(1-e1)
     float pad_;
+    // fp64 exponents for the refinement of gradient-carrying points (refined_point): 2/e2, 2/e1, e2/e1, e1
+    double pxy64, pz64, e21_64, e1_64;
 };
 struct SampleFull : Sample {
     double M[9];              // un-scaled rotation
@@ -224,6 +227,7 @@ SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, SampleFull& S
     S.pz = (float)(2.0 / S.e[0]);
     S.e21 = (float)(S.e[1] / S.e[0]);
     S.e1 = (float)S.e[0];
+    S.pxy64 = 2.0 / S.e[1]; S.pz64 = 2.0 / S.e[0]; S.e21_64 = S.e[1] / S.e[0]; S.e1_64 = S.e[0];
 }
 
 // s at plane "index" 0 for the column through grid point (ia, ib): base_i = Ms_i . ((gx,gy,0) - t), as hi/lo floats
@@ -354,6 +358,121 @@ SQ_HD void point_backward(const Fwd& f, float W, Bwd& b) {
 SQ_HD void fwd_neutral(Fwd& f) {
     f.sx = f.sy = f.sz = 1.f;
     f.d1 = f.d2 = 0.f; f.t1 = f.t2 = 1.f; f.h1 = f.h2 = 1.f; f.lG = 0.f; f.F = 1.f;
+}
+
+// ---------------------------------------------------------------- fp64 refinement of gradient-carrying points
+// At sigmoid sharpness k the gradient weight of a point is o (1 - o) with o = sigmoid(-x ln2), x = k log2(e) (F - 1): an
+// error dF in F becomes 375 dF in x at k = 260 (torch/train.py:64, classes.py:274).  The fp32 chain above carries
+// ~4e-7 (MUFU lg2 alone: 2e-7 absolute on each of up to three logarithms), i.e. dx ~ 1e-4, which is the whole gradient
+// tolerance (rtol 1e-4).  So for the few points that carry the gradient -- |x| < kRefine, about a quarter of the points
+// the compacted backward handles, ~0.4 % of the grid -- F - 1 is re-evaluated in fp64: geometry from the fp64 column
+// base, log2 / exp2 from two small constant tables plus a short polynomial (1e-13 relative), F - 1 as expm1.  No MUFU
+// approximation enters x; what the backward needs besides x (ratios bounded by 1, not amplified by k) is rounded to
+// fp32 from the same chain.  B200 issues DFMA at half the FP32 rate on a pipe of its own (profiles/peaks_r01.json:
+// 64 / clk / SM, co-issues with MUFU), so this costs ~150 instructions per refined point.
+// Host and device run the same arithmetic (tests/emu), tables included.
+#include "sq_tables.inc"
+#if defined(__CUDACC__)
+static __device__ const double kExp2TabDev[128] = {SQ_EXP2_TAB_VALUES};
+static __device__ __align__(16) const double kLog2TabDev[256] = {SQ_LOG2_TAB_VALUES};
+#endif
+#if !defined(__CUDA_ARCH__)
+static const double kExp2TabHost[128] = {SQ_EXP2_TAB_VALUES};
+static const double kLog2TabHost[256] = {SQ_LOG2_TAB_VALUES};
+#endif
+
+SQ_HD int dbl_hi(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(v);
+#else
+    long long b; memcpy(&b, &v, 8); return (int)(b >> 32);
+#endif
+}
+SQ_HD int dbl_lo(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(v);
+#else
+    long long b; memcpy(&b, &v, 8); return (int)(b & 0xffffffffll);
+#endif
+}
+SQ_HD double dbl_make(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    const long long b = ((long long)hi << 32) | (long long)(unsigned int)lo; double v; memcpy(&v, &b, 8); return v;
+#endif
+}
+// small int -> double without a conversion instruction (those share the MUFU pipe): 2^52 + 2^31 + k, minus the constant
+SQ_HD double int_to_dbl(int k) { return dbl_make(0x43300000, k ^ (int)0x80000000) - 4503601774854144.0; }
+
+// 2^y for |y| <= 1000, relative error ~1e-15: y = q/128 + f, 2^y = 2^floor(q/128) * T[q mod 128] * exp(f ln2)
+SQ_HD double exp2_acc(double y) {
+    const double kMagic = 6755399441055744.0;                // 1.5 * 2^52: adding it leaves round(v) in the low word
+    const double t = fma(y, 128.0, kMagic);
+    const int q = dbl_lo(t);
+    const double f = fma(t - kMagic, -0.0078125, y);         // y - q/128, |f| <= 1/256
+    const int j = q & 127, k = q >> 7;
+    const double z = f * kLn2;
+    double p = fma(z, 1.0 / 24.0, 1.0 / 6.0);
+    p = fma(p, z, 0.5); p = fma(p, z, 1.0); p = fma(p, z, 1.0);
+#if defined(__CUDA_ARCH__)
+    const double r = __ldg(&kExp2TabDev[j]) * p;
+#else
+    const double r = kExp2TabHost[j] * p;
+#endif
+    return dbl_make(dbl_hi(r) + (k << 20), dbl_lo(r));       // times 2^k (the result stays a normal number)
+}
+
+// log2(m) for a positive normal m, absolute error ~1e-15 + 1e-16 |result|: m = 2^k f, f in [1,2) split at the midpoints
+// c_j of 128 mantissa intervals: log2 m = k + log2 c_j + log1p(f / c_j - 1) / ln2
+SQ_HD double log2_acc(double m) {
+    const int hi = dbl_hi(m), lo = dbl_lo(m);
+    const int k = ((hi >> 20) & 0x7ff) - 1023;
+    const int j = (hi >> 13) & 127;
+    const double f = dbl_make((hi & 0x000fffff) | 0x3ff00000, lo);
+#if defined(__CUDA_ARCH__)
+    const double2 tab = __ldg(reinterpret_cast<const double2*>(kLog2TabDev) + j);
+    const double ic = tab.x, lc = tab.y;
+#else
+    const double ic = kLog2TabHost[2 * j], lc = kLog2TabHost[2 * j + 1];
+#endif
+    const double r = fma(f, ic, -1.0);                       // |r| < 1/250
+    double p = fma(r, 0.2, -0.25);
+    p = fma(p, r, 1.0 / 3.0); p = fma(p, r, -0.5); p = fma(p, r, 1.0);
+    return fma(p * r, 1.4426950408889634, lc + int_to_dbl(k));
+}
+
+#ifndef SQ_KREFINE
+#define SQ_KREFINE 8.0f
+#endif
+constexpr float kRefine = SQ_KREFINE;     // |x| below which a gradient-carrying point is re-evaluated in fp64
+
+// One point in fp64: s = base + cf d (d_i = Ms[i][2] step), the forward chain of point_forward() and x = kl (F - 1).
+// Not inlined: ~150 instructions that must not disturb the register allocation of the z walk.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+float refined_x(const Sample& S, double step, float kl, double b0, double b1, double b2, float cf) {
+    const double c = f2d(cf);
+    const double s0 = fma(c, S.Ms[2] * step, b0), s1 = fma(c, S.Ms[5] * step, b1), s2 = fma(c, S.Ms[8] * step, b2);
+    const double a0 = s0 == 0.0 ? 1e-2 : fabs(s0), a1 = s1 == 0.0 ? 1e-2 : fabs(s1), a2 = s2 == 0.0 ? 1e-2 : fabs(s2);
+    const double lA = S.pxy64 * log2_acc(a0), lB = S.pxy64 * log2_acc(a1), lC = S.pz64 * log2_acc(a2);
+    const double t1 = exp2_acc(-fmin(fabs(lA - lB), 64.0));
+    const double lE = S.e21_64 * (fmax(lA, lB) + log2_acc(1.0 + t1));
+    const double t2 = exp2_acc(-fmin(fabs(lE - lC), 64.0));
+    const double y = S.e1_64 * (fmax(lE, lC) + log2_acc(1.0 + t2));
+    double Fm1;                                               // F - 1 = 2^y - 1
+    if (fabs(y) < 0.0625) {
+        const double z = y * kLn2;                            // |z| < 0.044: the series is exact to 1e-16 after z^7
+        double p = fma(z, 1.0 / 5040.0, 1.0 / 720.0);
+        p = fma(p, z, 1.0 / 120.0); p = fma(p, z, 1.0 / 24.0); p = fma(p, z, 1.0 / 6.0); p = fma(p, z, 0.5); p = fma(p, z, 1.0);
+        Fm1 = p * z;
+    } else {
+        Fm1 = exp2_acc(fmin(fmax(y, -1000.0), 1000.0)) - 1.0;
+    }
+    return d2f(f2d(kl) * Fm1);
 }
 
 // ---------------------------------------------------------------- per-thread accumulators
@@ -575,13 +694,24 @@ struct ColGrad {       // two-moment accumulators of one column
 // (tau/n) sum_c cs_c is carried along and used when the depth is tiny (relative error < 0.4% there).
 // [c_lo, c_hi]: the (warp-uniform) z range to walk, from column_range() / warp_range().
 // running state of one column walk
+// Per-lane queue of gradient-carrying points (SQ_BWD_COMPACT), structure of arrays; entry e of this lane sits at
+// index e * stride (stride 32 in the kernels: one column of the warp's arrays per lane; 1 in the host build).
+struct BwdQueue {
+    float* cf;       // plane "index" of the point
+    float* pre;      // sum of T in front of it since the column's first gradient-carrying point; later: its suffix weight
+    float* x;        // log2 odds k log2(e) (F - 1) the scan used; later: the fp64-refined value for entries in rmask
+    float* d;        // refined entries: occupancy correction o(x refined) - o(x scan)
+    int stride;
+};
+
 struct ColState {
     float csl, cssum, tsum, psh, seen, T;
-    // SQ_BWD_COMPACT (device): this lane's column of the warp's queue of gradient-carrying points, entries queued, and
-    // whether a point had to be handled on the spot because the queue was full
-    float2* q;
+    // SQ_BWD_COMPACT: this lane's queue, entries queued, whether a point had to be handled on the spot because the
+    // queue was full, and which entries get the fp64 re-evaluation (|x| < kRefine)
+    BwdQueue q;
     int qn;
     bool spilled;
+    unsigned rmask;
 };
 
 // SQ_BWD_COMPACT.  The backward block runs for the whole warp as soon as ONE lane carries gradient, and the surface
@@ -690,11 +820,15 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
             SQ_BWD_HOOK(active);                // debug builds: statistics of how many lanes carry gradient
 #endif
             bool now = active;                  // lanes whose point is handled on the spot
-#if defined(__CUDA_ARCH__) && defined(SQ_BWD_COMPACT)
-            if (st.q) {
+#if defined(SQ_BWD_COMPACT)
+            if (st.q.cf) {
                 const bool room = st.qn < kBwdDepth;
                 if (active && room) {
-                    st.q[st.qn * 32] = make_float2(p.cf, st.psh);      // plane, T in front of it since the first active point
+                    const int at = st.qn * st.q.stride;
+                    st.q.cf[at] = p.cf;             // plane
+                    st.q.pre[at] = st.psh;          // T in front of it since the first active point
+                    st.q.x[at] = p.x;
+                    st.rmask |= (fabsf(p.x) < kRefine ? 1u : 0u) << st.qn;
                     ++st.qn;
                     st.seen = 1.0f;
                 }
@@ -725,6 +859,50 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
     st.tsum += st.T;
 }
 
+// ---- the queued points after the walk (SQ_BWD_COMPACT), three steps; `at` = index of the entry in the queue arrays
+// 1. refined entries: x from the fp64 chain, and the first-order change of the point's occupancy that goes with it
+SQ_HD void queue_refine_entry(const Sample& S, double step, float kl, const BwdQueue& q, int at,
+                              double b0, double b1, double b2) {
+    const float x0 = q.x[at];
+    const float x1 = refined_x(S, step, kl, b0, b1, b2, q.cf[at]);
+    const float eo = ex2(x1), o = rcp(1.0f + eo);
+    q.x[at] = x1;
+    q.d[at] = -(float)kLn2 * eo * o * o * (x1 - x0);      // d o / d x = -ln2 o (1 - o)
+}
+// 2. per column (its owner): suffix weights S_e = U - prefix_e, corrected to first order for the occupancy changes of the
+// column's refined entries.  T_c = exp(-tau cs_c) and cs_c sums the occupancies at or in front of c, so with
+// o_p -> o_p + d_p:  T_c -> T_c (1 - tau sum_{p <= c} d_p)  and
+//   S_e -> S_e - tau ( S_e sum_{p <= e} d_p  +  sum_{p > e} d_p S_p ).
+// The occupancy the scan saw carries the fp32 chain's error in x (~1e-4 at k = 260), and through tau cs it reaches the
+// weight of EVERY point behind; measured (tests/emu) this is the larger part of the fp32 gradient error.
+SQ_HD void queue_suffix_weights(const BwdQueue& q, int qn, unsigned rmask, float U, float tau) {
+    float dall = 0.f;
+    for (unsigned m = rmask; m; m &= m - 1u) {
+        int e = 0;
+        while (!((m >> e) & 1u)) ++e;
+        dall += q.d[e * q.stride];
+    }
+    float dsuf = 0.f, bsuf = 0.f;                            // over the refined entries behind e: sum d, sum d S
+    for (int e = qn - 1; e >= 0; --e) {
+        const int at = e * q.stride;
+        const float Se = U - q.pre[at];
+        q.pre[at] = Se - tau * fmaf(dall - dsuf, Se, bsuf);
+        if ((rmask >> e) & 1u) { const float d = q.d[at]; dsuf += d; bsuf = fmaf(d, Se, bsuf); }
+    }
+}
+// 3. every entry: forward redone in fp32 for the ratios the backward needs (not amplified by k), weight from the queue's x
+// and suffix weight.  sign = sign(depth - target) of the column.
+template <bool FIX>
+SQ_HD void queue_entry_backward(const Sample& S, const ImplicitParams& P, const float* bh, const float* bl, float cf,
+                                float x, float Sw, float sign, bool has, Bwd& b) {
+    Plane pl;
+    plane_forward<FIX>(S, P, bh, bl, cf, pl);
+    const float eo = ex2(x), o = rcp(1.0f + eo);
+    float W = eo * o * o * Sw * sign;
+    if (!has) { fwd_neutral(pl.f); W = 0.f; }
+    point_backward<FIX>(pl.f, W, b);
+}
+
 // ILP: number of z planes whose (independent) forward chains are in flight per thread.  A column walk is a serial
 // chain of ~8 dependent MUFU ops per plane; two planes in flight halve the latency of the longest work item, which
 // is what bounds the kernel at small batch.
@@ -737,11 +915,12 @@ template <bool BWD, bool FIX = true>
 // handled on the spot.
 SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams& P,
                             const float* bh, const float* bl, int c_lo, int c_hi, float* colgrad11,
-                            float2* bwd_q = nullptr, float* U_out = nullptr, int* qn_out = nullptr,
-                            bool* spilled_out = nullptr) {
+                            const BwdQueue* bwd_q = nullptr, float* U_out = nullptr, int* qn_out = nullptr,
+                            bool* spilled_out = nullptr, unsigned* rmask_out = nullptr) {
     // planes in front of the range: o = 0, cs = 0, T = 1 each
     ColState st;
-    st.q = bwd_q; st.qn = 0; st.spilled = false;
+    if (bwd_q) st.q = *bwd_q; else { st.q.cf = st.q.pre = st.q.x = st.q.d = nullptr; st.q.stride = 0; }
+    st.qn = 0; st.spilled = false; st.rmask = 0u;
     st.csl = 0.f;                                     // -tau log2(e) cs
     st.T = 1.0f;                                      // 2^csl
     st.tsum = (float)(g.n - 1 - c_hi);
@@ -786,7 +965,7 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
     st.cssum = fmaf(nb, st.csl, st.cssum);
     if (BWD) {
         const float U = fmaf(nb * st.seen, st.T, st.psh);
-        if (U_out) { *U_out = U; *qn_out = st.qn; *spilled_out = st.spilled; }
+        if (U_out) { *U_out = U; *qn_out = st.qn; *spilled_out = st.spilled; *rmask_out = st.rmask; }
         for (int i = 0; i < 3; ++i) {
             colgrad11[i]     = fmaf(U, cg.gs0[i], -cg.gs1[i]);
             colgrad11[3 + i] = fmaf(U, cg.gz0[i], -cg.gz1[i]);
@@ -813,6 +992,18 @@ SQ_HD void implicit_fold(Acc& acc, const float* colgrad11, float w, float dx, fl
     }
     acc.ge[0] = fmaf(w, colgrad11[9], acc.ge[0]);
     acc.ge[1] = fmaf(w, colgrad11[10], acc.ge[1]);
+}
+
+// one queued point's backward terms into the item's sums (dx, dy: its column's position relative to t)
+SQ_HD void acc_add_point(Acc& acc, const Bwd& b, float cf, float dx, float dy) {
+    for (int i = 0; i < 3; ++i) {
+        acc.gs[i] += b.gs[i];
+        acc.gm[3 * i + 0] = fmaf(b.gs[i], dx, acc.gm[3 * i + 0]);
+        acc.gm[3 * i + 1] = fmaf(b.gs[i], dy, acc.gm[3 * i + 1]);
+        acc.gm[3 * i + 2] = fmaf(b.gs[i], cf, acc.gm[3 * i + 2]);
+        acc.wa[i] += b.wa[i];
+    }
+    acc.ge[0] += b.ge[0]; acc.ge[1] += b.ge[1];
 }
 
 // ---------------------------------------------------------------- ExplicitLoss: one column

@@ -628,6 +628,10 @@ __device__ unsigned long long g_timeline[3 * 8192];
 __device__ unsigned int g_classes[kClasses];
 #endif
 
+// dynamic shared memory of the fwd+bwd kernel, per warp: 4 queue arrays + 9 x 32 column values + the deal-out list
+constexpr size_t kImplicitBwdSmemPerWarp = (size_t)kBwdDepth * 32 * (4 * sizeof(float) + sizeof(unsigned short)) + 9 * 32 * sizeof(float);
+static_assert(kImplicitBwdSmemPerWarp % 16 == 0, "per-warp regions stay 16-byte aligned");
+
 template <bool BWD, int THREADS, int MINB, int CPTMAX>      // CPTMAX: upper limit of L.cpt
 __global__ void __launch_bounds__(THREADS, MINB)
 implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, ImplicitParams P, int total_items,
@@ -636,11 +640,13 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
     __shared__ Sample Ssh[THREADS / 32];
     __shared__ __align__(16) float tiles[THREADS / 32][kRedFloats];
-#ifdef SQ_BWD_COMPACT       // per warp: queued gradient-carrying points, per-column data for them, the deal-out list
-    constexpr int kQW = BWD ? THREADS / 32 : 1, kQN = BWD ? kBwdDepth * 32 : 1;
-    __shared__ float2 qent[kQW][kQN];
-    __shared__ float colinfo[kQW][BWD ? 10 * 32 : 1];
-    __shared__ unsigned short qmap[kQW][kQN];
+#ifdef SQ_BWD_COMPACT       // per warp, in dynamic shared memory (BWD only; implicit_bwd_smem_bytes): the queued gradient-carrying
+                            // points (BwdQueue arrays), per-column data for them, the deal-out list
+    constexpr int kQN = kBwdDepth * 32;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    float* const qbuf = reinterpret_cast<float*>(dyn_smem + (size_t)(threadIdx.x >> 5) * kImplicitBwdSmemPerWarp);      // [4][kQN]
+    float* const colinfo_w = qbuf + 4 * kQN;                                                                         // [9][32]
+    unsigned short* const qmap_w = reinterpret_cast<unsigned short*>(colinfo_w + 9 * 32);                            // [kQN]
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& S = Ssh[warp];
@@ -720,9 +726,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #ifndef SQ_FIXHOIST      // hoisting the exact-zero fix-up out of the walk (two copies of the loop): measured 1 us
                          // SLOWER per call once everything else was in place (profiles/tune_r01.txt) -> off
 #ifdef SQ_BWD_COMPACT
-                float U = 0.f; int qn = 0; bool spilled = false;
-                depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg, BWD ? &qent[BWD ? warp : 0][lane] : nullptr,
-                                                   &U, &qn, &spilled);
+                float U = 0.f; int qn = 0; bool spilled = false; unsigned rmask = 0u;
+                const BwdQueue qlane{qbuf + lane, qbuf + kQN + lane, qbuf + 2 * kQN + lane, qbuf + 3 * kQN + lane, 32};
+                depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg, BWD ? &qlane : nullptr, &U, &qn, &spilled, &rmask);
 #else
                 depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
 #endif
@@ -749,11 +755,15 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                         loss_sum += fabsf(diff) - fabsf(tv);
                         wsg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
                     }
-                    if (wsg == 0.f) qn = 0;                    // its points carry no gradient after all
-                    int incl = qn;
+                    if (wsg == 0.f) { qn = 0; rmask = 0u; }    // its points carry no gradient after all
+                    // entries to refine in fp64 first in the deal-out list, the others behind them: one scan for both counts
+                    const int nr = __popc(rmask);
+                    const int cnt = (nr << 16) | (qn - nr);
+                    int incl = cnt;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t_; }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - qn;
+                    const int last = __shfl_sync(0xffffffffu, incl, 31);
+                    const int total_r = last >> 16, total = total_r + (last & 0xffff);
                     const bool any_spill = __any_sync(0xffffffffu, spilled && wsg != 0.f);
                     if (total > 0 || any_spill) {
                         Acc acc;
@@ -761,38 +771,40 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                         if (folded) { tile_get(tiles[warp], v); array_to_acc(v, acc); } else acc_zero(acc);
                         if (spilled && wsg != 0.f) implicit_fold(acc, cg, wsg, dxy[0], dxy[1]);      // handled on the spot
                         if (total > 0) {
-                            float* ci = colinfo[warp];
+                            float* ci = colinfo_w;
                             ci[0 * 32 + lane] = bh[0]; ci[1 * 32 + lane] = bh[1]; ci[2 * 32 + lane] = bh[2];
                             ci[3 * 32 + lane] = bl[0]; ci[4 * 32 + lane] = bl[1]; ci[5 * 32 + lane] = bl[2];
-                            ci[6 * 32 + lane] = U; ci[7 * 32 + lane] = wsg; ci[8 * 32 + lane] = dxy[0]; ci[9 * 32 + lane] = dxy[1];
-                            for (int e = 0; e < qn; ++e) qmap[warp][off + e] = (unsigned short)((lane << 8) | e);
+                            ci[6 * 32 + lane] = wsg; ci[7 * 32 + lane] = dxy[0]; ci[8 * 32 + lane] = dxy[1];
+                            {
+                                int at_r = (incl - cnt) >> 16, at_p = total_r + ((incl - cnt) & 0xffff);
+                                for (int e = 0; e < qn; ++e) {
+                                    const unsigned short id = (unsigned short)((lane << 8) | e);
+                                    if ((rmask >> e) & 1u) qmap_w[at_r++] = id; else qmap_w[at_p++] = id;
+                                }
+                            }
                             __syncwarp();
-                            // every lane gets a point per round; two rounds in flight (two independent MUFU chains)
+                            const BwdQueue qwarp{qbuf, qbuf + kQN, qbuf + 2 * kQN, qbuf + 3 * kQN, 32};
+                            // 1. the entries near the surface, dealt out evenly: x in fp64 (sq_core.cuh "fp64 refinement")
+                            for (int j = lane; j < total_r; j += 32) {
+                                const int m_ = qmap_w[j], l_ = m_ >> 8, e_ = m_ & 255;
+                                queue_refine_entry(S, g.step, P.kl, qwarp, e_ * 32 + l_,
+                                                   f2d(ci[0 * 32 + l_]) + f2d(ci[3 * 32 + l_]), f2d(ci[1 * 32 + l_]) + f2d(ci[4 * 32 + l_]),
+                                                   f2d(ci[2 * 32 + l_]) + f2d(ci[5 * 32 + l_]));
+                            }
+                            __syncwarp();
+                            // 2. every lane turns the prefixes of ITS column's entries into (corrected) suffix weights
+                            if (qn > 0) queue_suffix_weights(qlane, qn, rmask, U, P.tl * (float)kLn2);
+                            __syncwarp();
+                            // 3. all entries, dealt out evenly; two rounds in flight (two independent MUFU chains)
                             auto dealt = [&](int j, Bwd& bq, float& cfq, float& dx_, float& dy_) {
                                 const bool has = j < total;
-                                const int m_ = has ? qmap[warp][j] : 0, l_ = m_ >> 8, e_ = m_ & 255;
-                                float2 en = qent[warp][e_ * 32 + l_];
-                                if (!has) en = make_float2(1.0f, 0.0f);      // idle lane of the last round: never-written slot
+                                const int m_ = has ? qmap_w[j] : 0, l_ = m_ >> 8, at = (m_ & 255) * 32 + l_;
+                                // idle lane of the last round: a slot that may never have been written
+                                const float cf_ = has ? qwarp.cf[at] : 1.0f, x_ = has ? qwarp.x[at] : 0.0f, sw_ = has ? qwarp.pre[at] : 0.0f;
                                 const float cbh[3] = {ci[0 * 32 + l_], ci[1 * 32 + l_], ci[2 * 32 + l_]};
                                 const float cbl[3] = {ci[3 * 32 + l_], ci[4 * 32 + l_], ci[5 * 32 + l_]};
-                                Plane pl;
-                                plane_forward<true>(S, P, cbh, cbl, en.x, pl);
-                                // weight: do/dF factor, suffix sum of T behind the point (U - prefix), sign of the column
-                                float W = pl.eo * pl.o * pl.o * (ci[6 * 32 + l_] - en.y) * ci[7 * 32 + l_];
-                                if (!has) { fwd_neutral(pl.f); W = 0.f; }
-                                point_backward<true>(pl.f, W, bq);
-                                cfq = en.x; dx_ = ci[8 * 32 + l_]; dy_ = ci[9 * 32 + l_];
-                            };
-                            auto add = [&](const Bwd& bq, float cfq, float dx_, float dy_) {
-#pragma unroll
-                                for (int i = 0; i < 3; ++i) {
-                                    acc.gs[i] += bq.gs[i];
-                                    acc.gm[3 * i + 0] = fmaf(bq.gs[i], dx_, acc.gm[3 * i + 0]);
-                                    acc.gm[3 * i + 1] = fmaf(bq.gs[i], dy_, acc.gm[3 * i + 1]);
-                                    acc.gm[3 * i + 2] = fmaf(bq.gs[i], cfq, acc.gm[3 * i + 2]);
-                                    acc.wa[i] += bq.wa[i];
-                                }
-                                acc.ge[0] += bq.ge[0]; acc.ge[1] += bq.ge[1];
+                                queue_entry_backward<true>(S, P, cbh, cbl, cf_, x_, sw_, ci[6 * 32 + l_], has, bq);
+                                cfq = cf_; dx_ = ci[7 * 32 + l_]; dy_ = ci[8 * 32 + l_];
                             };
                             int j = lane;
 #ifndef SQ_DENSE_ILP1
@@ -800,14 +812,14 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                                 Bwd b0, b1; float c0, c1, x0, x1, y0, y1;
                                 dealt(j, b0, c0, x0, y0);
                                 dealt(j + 32, b1, c1, x1, y1);
-                                add(b0, c0, x0, y0);
-                                add(b1, c1, x1, y1);
+                                acc_add_point(acc, b0, c0, x0, y0);
+                                acc_add_point(acc, b1, c1, x1, y1);
                             }
 #endif
                             for (; j - lane < total; j += 32) {
                                 Bwd b0; float c0, x0, y0;
                                 dealt(j, b0, c0, x0, y0);
-                                add(b0, c0, x0, y0);
+                                acc_add_point(acc, b0, c0, x0, y0);
                             }
                             __syncwarp();
                         }
@@ -1209,9 +1221,9 @@ int check_scratch(int batch, int n, void* scratch, size_t bytes, Scratch* s) {
 
 // kernel launch that may overlap the tail of the preceding kernel in the stream (the kernel must call pdl_wait())
 template <typename... KArgs, typename... Args>
-cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args... args) {
+cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, size_t dyn_smem, cudaStream_t st, bool pdl, Args... args) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = dyn_smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1340,12 +1352,23 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
         ColumnKernelTimer timer(st);
         if (grad_pred) {
             const int blocks = persistent_blocks(items, SQ_IMPB_THREADS / 32, SQ_IMPB_MINB);
-            SQ_TRY(launch_dependent(implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB, SQ_IMPB_CPT>, blocks, SQ_IMPB_THREADS, st, pdl,
+            constexpr size_t dyn = kImplicitBwdSmemPerWarp * (SQ_IMPB_THREADS / 32);
+            {   // static + dynamic shared memory exceed 48 KB: opt in once per device (not a stream operation)
+                static bool opted[64] = {false};
+                int dev = 0;
+                cudaGetDevice(&dev);
+                if (dev >= 0 && dev < 64 && !opted[dev]) {
+                    SQ_TRY(cudaFuncSetAttribute(implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB, SQ_IMPB_CPT>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                    opted[dev] = true;
+                }
+            }
+            SQ_TRY(launch_dependent(implicit_kernel<true, SQ_IMPB_THREADS, SQ_IMPB_MINB, SQ_IMPB_CPT>, blocks, SQ_IMPB_THREADS, dyn, st, pdl,
                                     s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off,
                                     s.partials, depth_out));
         } else {
             const int blocks = persistent_blocks(items, SQ_IMPF_THREADS / 32, SQ_IMPF_MINB);
-            SQ_TRY(launch_dependent(implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB, SQ_IMPF_CPT>, blocks, SQ_IMPF_THREADS, st, pdl,
+            SQ_TRY(launch_dependent(implicit_kernel<false, SQ_IMPF_THREADS, SQ_IMPF_MINB, SQ_IMPF_CPT>, blocks, SQ_IMPF_THREADS, 0, st, pdl,
                                     s.pred, g, L, P, items, s.ctl, queue, s.queue_cap, target, target_stride_b, row_off, col_off,
                                     s.partials, depth_out));
         }
@@ -1355,7 +1378,7 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
 #ifndef SQ_SKIP_FINALIZE
     if (target) {
         const double nn = (double)n * n;
-        SQ_TRY(launch_dependent(finalize_kernel<FIN_IMPLICIT>, batch, kFinThreads, st, pdl,
+        SQ_TRY(launch_dependent(finalize_kernel<FIN_IMPLICIT>, batch, kFinThreads, 0, st, pdl,
                                 s.pred, g, batch, L.rows_per_sample, s.partials, 1.0 / nn,
                                 -(double)sharpness * (double)tau / (nn * n * (double)batch), pred_dtype, grad_pred, s.per_sample,
                                 per_sample, loss_out, &s.ctl->ticket, s.tv_sum, queue ? s.item_class : nullptr));

@@ -17,7 +17,16 @@ static void acc_to_double(const Acc& a, double* d) {
     d[15] += a.ge[0]; d[16] += a.ge[1]; d[17] += a.loss;
 }
 
+static int g_emu_refine = 1, g_emu_queue = 1;
+
 extern "C" {
+
+void emu_set_refine(int on) { g_emu_refine = on; }     // fp64 refinement of the queued points near the surface
+void emu_set_queue(int on) { g_emu_queue = on; }       // 0: every gradient point on the spot (two-moment path)
+
+// accuracy probes of the fp64 primitives
+double emu_exp2_acc(double y) { return exp2_acc(y); }
+double emu_log2_acc(double m) { return log2_acc(m); }
 
 // target: [B, n, n] in image orientation (row, col); depth_out optional [B, n, n] image orientation
 int emu_implicit(const double* pred, int B, int n, double step, double z0, const float* target, float tau, float k,
@@ -35,7 +44,12 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
             int c_lo, c_hi;
             column_range(S, g, P.bound, bh, c_lo, c_hi);
             warp_range(n, c_lo, c_hi);
-            const float depth = grad ? implicit_column<true>(S, g, P, bh, bl, c_lo, c_hi, cg)
+            // the kernels' compacted backward, one column at a time: walk with a queue of gradient-carrying points, fp64
+            // refinement of the entries near the surface, corrected suffix weights, backward per entry
+            float qcf[kBwdDepth], qpre[kBwdDepth], qx[kBwdDepth], qd[kBwdDepth];
+            const BwdQueue q{qcf, qpre, qx, qd, 1};
+            float U = 0.f; int qn = 0; bool spilled = false; unsigned rmask = 0u;
+            const float depth = grad ? implicit_column<true>(S, g, P, bh, bl, c_lo, c_hi, cg, g_emu_queue ? &q : nullptr, &U, &qn, &spilled, &rmask)
                                      : implicit_column<false>(S, g, P, bh, bl, c_lo, c_hi, cg);
             const int row = n - 1 - ib, col = ia;
             if (depth_out) depth_out[(size_t)b * n * n + row * n + col] = depth;
@@ -45,7 +59,19 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
             a.loss = fabsf(diff);
             if (grad) {
                 const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                implicit_fold(a, cg, w, (float)(grid_coord(g, ia) - S.t[0]), (float)(grid_coord(g, ib) - S.t[1]));
+                const float dx = (float)(grid_coord(g, ia) - S.t[0]), dy = (float)(grid_coord(g, ib) - S.t[1]);
+                if (!g_emu_queue || spilled) implicit_fold(a, cg, w, dx, dy);
+                if (g_emu_queue && w != 0.f && qn > 0) {
+                    if (!g_emu_refine) rmask = 0u;
+                    const double b0 = (double)bh[0] + (double)bl[0], b1 = (double)bh[1] + (double)bl[1], b2 = (double)bh[2] + (double)bl[2];
+                    for (int e = 0; e < qn; ++e) if ((rmask >> e) & 1u) queue_refine_entry(S, g.step, P.kl, q, e, b0, b1, b2);
+                    queue_suffix_weights(q, qn, rmask, U, tau);
+                    for (int e = 0; e < qn; ++e) {
+                        Bwd bq;
+                        queue_entry_backward<true>(S, P, bh, bl, qcf[e], qx[e], qpre[e], w, true, bq);
+                        acc_add_point(a, bq, qcf[e], dx, dy);
+                    }
+                }
             }
             acc_to_double(a, accd);
         }

@@ -14,11 +14,13 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        out = os.path.join(tempfile.gettempdir(), f"libsqemu_{os.getuid()}.so")
+        flags = os.environ.get("SQ_EMU_FLAGS", "").split()            # experiments: -DSQ_KREFINE=32.0f ...
+        tag = ("_" + "".join(c if c.isalnum() else "_" for c in "".join(flags))) if flags else ""
+        out = os.path.join(tempfile.gettempdir(), f"libsqemu_{os.getuid()}{tag}.so")
         src = os.path.join(HERE, "emu.cpp")
         hdr = os.path.join(ROOT, "sq_recovery_b200", "csrc", "sq_core.cuh")
         if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.dirname(hdr),
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", *flags, "-I", os.path.dirname(hdr),
                                    "-x", "c++", src, "-o", out])
         _lib = ctypes.CDLL(out)
     return _lib

@@ -44,24 +44,14 @@ def run(crit, true, pred, dev):
     return loss.item(), pred.grad.double().cpu().numpy()
 
 
-def check(loss, grad, ref_loss, ref_grad, loss_rtol=LOSS_RTOL, rtol=GRAD_RTOL, atol=GRAD_ATOL, what="", keep=None,
-          statistical=False):
-    """Loss within loss_rtol; every gradient entry within rtol/atol.
-
-    statistical=True is used only for fresh random draws at sigmoid_sharpness 260: there the fp32 kernel's per-term
-    accuracy (|s| rounding and MUFU error amplified by k, DESIGN.md "precision") sits at the tolerance, the error of a
-    sample's gradient is a random variable (profiles/parity_sweep_r01.json: median 0.15x, p95 0.5x, max ~1.0-1.2x
-    tolerance), and a fixed-seed all-entries assertion would only encode the luck of the seed.  The criterion is then:
-    at least 90% of the samples fully within tolerance and none beyond 2x."""
+def check(loss, grad, ref_loss, ref_grad, loss_rtol=LOSS_RTOL, rtol=GRAD_RTOL, atol=GRAD_ATOL, what="", keep=None):
+    """Loss within loss_rtol; EVERY gradient entry within rtol/atol (`keep`: per-sample mask, see unambiguous())."""
     ref_loss = float(ref_loss)
     assert abs(loss - ref_loss) <= loss_rtol * abs(ref_loss) + 1e-12, f"{what}: loss {loss} vs {ref_loss}"
     err = np.abs(grad - ref_grad) / (atol + rtol * np.abs(ref_grad))
     if keep is not None:
         err = err[np.asarray(keep)]
-    if statistical:
-        per_sample = err.max(axis=1)
-        assert per_sample.max() <= 2.0, f"{what}: worst gradient error {per_sample.max():.2f}x tolerance"
-        assert (per_sample <= 1.0).mean() >= 0.9, f"{what}: only {(per_sample <= 1.0).mean():.0%} of samples within tolerance"
+    if err.size == 0:
         return
     assert err.max() <= 1.0, f"{what}: worst gradient error {err.max():.2f}x tolerance at {np.unravel_index(err.argmax(), err.shape)}"
 
@@ -198,8 +188,7 @@ def test_against_oracle(seed, B, R, dev, S):
             l, gr = run(S.ImplicitLoss(R, dev, *args), img, pred, dev)
             keep = unambiguous(oc, img, pred)
             assert keep.sum() >= B - 2
-            check(l, gr, ref.item(), p.grad.double().numpy(), what=f"implicit{args} B={B} R={R}", keep=keep,
-                  statistical=(args[1] == 260))
+            check(l, gr, ref.item(), p.grad.double().numpy(), what=f"implicit{args} B={B} R={R}", keep=keep)
         p = pred.clone().requires_grad_(True)
         ref = O.ExplicitLoss(R, "cpu")(true, p); ref.backward()
         l, gr = run(S.ExplicitLoss(R, dev), true, pred, dev)
@@ -272,7 +261,7 @@ def test_full_size_properties(dev, S):
     ps = pred[idx].clone().requires_grad_(True)
     ls = crit(target[idx], ps); ls.backward()
     check(ls.item(), ps.grad.double().cpu().numpy(), ref.item(), po.grad.double().numpy(), what="slice of config 2",
-          keep=unambiguous(oc, target[idx].cpu(), pred[idx].cpu()), statistical=True)
+          keep=unambiguous(oc, target[idx].cpu(), pred[idx].cpu()))
     # ExplicitLoss / IoU identities at full size
     ex = S.ExplicitLoss(R, dev)
     assert ex(true, true).item() == 0.0
@@ -716,6 +705,23 @@ def test_against_the_live_reference(dev, S):
             p = pred.clone().requires_grad_(True)
             ref = rc.LeastSquares(R, cpu)(img, p); ref.backward()
             l, gr = run(S.LeastSquares(R, dev), img, pred, dev)
-            check(l, gr, ref.item(), p.grad.double().numpy(), loss_rtol=1e-4, rtol=2e-3, atol=1e-4, what=f"reference lsq R={R}")
+            rg = p.grad.double().numpy()            # the reference itself is fp32 here (classes.py:319): row-relative tolerance
+            assert abs(l - ref.item()) <= 1e-4 * abs(ref.item())
+            assert (np.abs(gr - rg) <= 1e-3 * np.abs(rg).max(axis=1, keepdims=True) + 2e-3 * np.abs(rg) + 1e-5).all()
     q = torch.tensor(O.randquat(np.random.RandomState(1)))
     np.testing.assert_allclose(S.quaternion.mat_from_quaternion(q.to(dev)).cpu().numpy(), rq.mat_from_quaternion(q).numpy(), atol=1e-15)
+
+
+def test_parity_sweep_every_sample(dev, S):
+    """Every sample of the frozen parity sweep (tests/golden/parity_sweep_refs.npz: 36 seeds x 2 prediction styles at
+    R = 16 / 32 / 64, tau 1.5 / k 260 and the defaults; 4032 samples) meets the gradient tolerance entry by entry --
+    the criterion round 1 could only meet statistically at k = 260."""
+    refs = load_golden("parity_sweep_refs.npz")
+    for R in (16, 32, 64):
+        preds, imgs = refs[f"R{R}_pred"], refs[f"R{R}_img"]
+        for (tau, k) in ((1.5, 260.0), (1.0, 100.0)):
+            tag = f"R{R}_t{tau:g}_k{k:g}"
+            crit = S.ImplicitLoss(R, dev, tau, k)
+            for c in range(preds.shape[0]):
+                l, gr = run(crit, imgs[c], preds[c], dev)
+                check(l, gr, refs[tag + "_loss"][c], refs[tag + "_grad"][c], what=f"{tag} call {c}", keep=refs[tag + "_keep"][c])
