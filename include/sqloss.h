@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 typedef void* sq_stream_t;           /* cudaStream_t */
-enum { SQ_F32 = 0, SQ_F64 = 1 };
+enum { SQ_F32 = 0, SQ_F64 = 1, SQ_U8 = 2 };   /* SQ_U8: 8-bit depth images of the host-buffer calls only */
 
 /* Library / device introspection. */
 const char* sq_version(void);
@@ -139,6 +139,21 @@ void sq_ctx_destroy(sq_ctx* ctx);
 int sq_implicit_loss_host(sq_ctx* ctx, const float* pred_host, int batch, int render_size,
                           const float* images_host, int height, int width, float tau, float sharpness,
                           double* loss_host, float* grad_host);
+
+/* The same in two halves, on one of the context's two slots (0 or 1), so that a caller can keep two batches in flight:
+ * while one slot's kernels run, the other slot's images cross PCIe.
+ *   submit  enqueues the copies and kernels of one ImplicitLoss call on the slot's stream and returns at once.
+ *           images_host [batch,H,W] of image_dtype SQ_F32, or SQ_U8 for 8-bit depth images -- the reference's data are
+ *           8-bit BMPs divided by 255 (torch/test.py:29-30, torch/classes.py:82-88); every sampled pixel is multiplied by
+ *           image_scale (1/255 for such images, 1 for fp32 depth in [0,1]).  Pinned (or registered) images are sampled
+ *           in place over PCIe: only the sectors holding sampled pixels cross the bus.  pred_host and images_host must
+ *           stay valid and unchanged until the matching wait.  cudaErrorNotReady if the slot still holds a result.
+ *   wait    blocks until that call has finished and copies loss (and the gradient if it was asked for) out.
+ */
+int sq_implicit_loss_host_submit(sq_ctx* ctx, int slot, const float* pred_host, int batch, int render_size,
+                                 const void* images_host, int image_dtype, int height, int width, float image_scale,
+                                 float tau, float sharpness, int want_grad);
+int sq_implicit_loss_host_wait(sq_ctx* ctx, int slot, double* loss_host, float* grad_host);
 
 /* ExplicitLoss on host data: parameters [batch,12] fp32, grid of ExplicitLoss(render_size). */
 int sq_explicit_loss_host(sq_ctx* ctx, const float* true_host, const float* pred_host, int batch, int render_size,

@@ -7,7 +7,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_v
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SQ_LIBSQLOSS") or os.path.join(HERE, "libsqloss.so")   # override: tuning builds only
-SQ_F32, SQ_F64 = 0, 1
+SQ_F32, SQ_F64, SQ_U8 = 0, 1, 2
 
 _lib = None
 
@@ -39,6 +39,9 @@ _PROTOS = {
     "sq_ctx_destroy": (None, [c_void_p]),
     "sq_implicit_loss_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_float,
                                       c_void_p, c_void_p]),
+    "sq_implicit_loss_host_submit": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_float,
+                                             c_float, c_float, c_int]),
+    "sq_implicit_loss_host_wait": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "sq_explicit_loss_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sq_iou_counts_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }

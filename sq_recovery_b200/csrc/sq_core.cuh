@@ -914,7 +914,7 @@ template <bool BWD, bool FIX = true>
 // bwd_q / U_out / qn_out / spilled_out: SQ_BWD_COMPACT only (see ColState); colgrad11 then holds only what was
 // handled on the spot.
 SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams& P,
-                            const float* bh, const float* bl, int c_lo, int c_hi, float* colgrad11,
+                            const float* bh, const float* bl, int c_lo, int c_hi, int lane_lo, float* colgrad11,
                             const BwdQueue* bwd_q = nullptr, float* U_out = nullptr, int* qn_out = nullptr,
                             bool* spilled_out = nullptr, unsigned* rmask_out = nullptr) {
     // planes in front of the range: o = 0, cs = 0, T = 1 each
@@ -933,8 +933,13 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
     }
     int c = c_hi;
     float cfi = (float)c_hi;                          // plane "index": exact small integers, z0/step for plane 0
+    // The walk ends early once no lane of the warp needs the planes that are left: a lane is finished when its
+    // transmittance has fallen below 2^-kDeep (what lies behind adds < n 2^-kDeep to the depth and carries no gradient, see
+    // kDeep) or when the walk has left the lane's OWN culled range [lane_lo, ..] (the warp walks the union).  The planes
+    // not walked are accounted for in closed form below, like the planes behind the range.
+    bool stop = false;
 #if SQ_IMP_ILP >= 2
-    for (; c - (SQ_IMP_ILP - 1) >= c_lo; c -= SQ_IMP_ILP, cfi -= (float)SQ_IMP_ILP) {
+    for (; !stop && c - (SQ_IMP_ILP - 1) >= c_lo; c -= SQ_IMP_ILP, cfi -= (float)SQ_IMP_ILP) {
         Plane p[SQ_IMP_ILP];
 #if defined(__CUDA_ARCH__) && SQ_F32X2 && SQ_IMP_ILP == 2
         if (SQ_F32X2 >= 2 || !BWD) {
@@ -952,15 +957,21 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
 #pragma unroll
 #endif
         for (int j = 0; j < SQ_IMP_ILP; ++j) plane_scan<BWD, FIX>(P, p[j], st, cg);
+#ifndef SQ_NO_EARLY_EXIT
+        stop = !SQ_ANY(st.csl > -kDeep && c - SQ_IMP_ILP >= lane_lo);
+#endif
     }
 #endif
-    for (; c >= c_lo; --c, cfi -= 1.0f) {
+    for (; !stop && c >= c_lo; --c, cfi -= 1.0f) {
         Plane p0;
         plane_forward<FIX>(S, P, bh, bl, (c == 0) ? S.cf0 : cfi, p0);
         plane_scan<BWD, FIX>(P, p0, st, cg);
+#ifndef SQ_NO_EARLY_EXIT
+        stop = !SQ_ANY(st.csl > -kDeep && c - 1 >= lane_lo);
+#endif
     }
-    // planes behind the range: o = 0, cs and T stay what they are
-    const float nb = (float)c_lo;
+    // planes behind the range (and planes left out by the early exit): o = 0, cs and T stay what they are
+    const float nb = (float)(c + 1);
     st.tsum = fmaf(nb, st.T, st.tsum);
     st.cssum = fmaf(nb, st.csl, st.cssum);
     if (BWD) {

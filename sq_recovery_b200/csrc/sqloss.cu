@@ -713,6 +713,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 int c_lo, c_hi;
                 column_range(S, g, P.bound, b32, c_lo, c_hi);
                 if (!valid) { c_lo = 0; c_hi = -1; }           // masked lanes do not widen the warp's range
+                const int own_lo = c_hi >= c_lo ? c_lo : g.n;  // this lane's own range (the early exit of the walk looks at it)
                 warp_range(g.n, c_lo, c_hi);
                 if (c_hi < c_lo) {                             // warp-uniform: no occupancy anywhere, depth is exactly 0
 #ifndef SQ_EARLY_CLAIM
@@ -728,15 +729,15 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #ifdef SQ_BWD_COMPACT
                 float U = 0.f; int qn = 0; bool spilled = false; unsigned rmask = 0u;
                 const BwdQueue qlane{qbuf + lane, qbuf + kQN + lane, qbuf + 2 * kQN + lane, qbuf + 3 * kQN + lane, 32};
-                depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg, BWD ? &qlane : nullptr, &U, &qn, &spilled, &rmask);
+                depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg, BWD ? &qlane : nullptr, &U, &qn, &spilled, &rmask);
 #else
-                depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
+                depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg);
 #endif
 #else
                 if (__any_sync(0xffffffffu, column_zero_possible(S, bh)))
-                    depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, cg);
+                    depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg);
                 else
-                    depth = implicit_column<BWD, false>(S, g, P, bh, bl, c_lo, c_hi, cg);
+                    depth = implicit_column<BWD, false>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg);
 #endif
 #ifndef SQ_EARLY_CLAIM
                 // Claim the next item only now, after the walk: the cursor -> queue -> Sample chain then stalls this warp
@@ -1182,17 +1183,20 @@ field_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int mode
 
 // ------------------------------------------------------------------------------------------------ host-image gather
 // Nearest-neighbour sampling of depth images that live in PINNED HOST memory, read directly over PCIe (zero copy):
-// only the sampled 32-byte sectors cross the bus (1/4 of the bytes at 256 -> 64), instead of the whole images.
+// only the sectors that hold sampled pixels cross the bus, instead of the whole images.  PIX = float, or unsigned char for
+// 8-bit depth images (the reference's data are 8-bit BMPs divided by 255, torch/test.py:29-30, classes.py:82-88): a quarter
+// of the bytes again; the division happens here (scale = 1/255).
+template <typename PIX>
 __global__ void __launch_bounds__(256)
-gather_targets_kernel(const float* __restrict__ host_images, long long stride_b, const int* __restrict__ row_off,
-                      const int* __restrict__ col_off, int R, int batch, float* __restrict__ out) {
+gather_targets_kernel(const PIX* __restrict__ host_images, long long stride_b, const int* __restrict__ row_off,
+                      const int* __restrict__ col_off, int R, int batch, float scale, float* __restrict__ out) {
     const size_t total = (size_t)batch * R * R;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int col = (int)(i % R);
         const size_t t = i / R;
         const int row = (int)(t % R);
         const size_t b = t / R;
-        out[i] = host_images[b * (size_t)stride_b + row_off[row] + col_off[col]];
+        out[i] = (float)host_images[b * (size_t)stride_b + row_off[row] + col_off[col]] * scale;
     }
 }
 
@@ -1535,24 +1539,33 @@ int sq_field(const void* params, int params_dtype, int batch, int n, double step
 }
 
 // ------------------------------------------------------------------------------------------------ host-buffer API
+// An sq_ctx owns kSlots independent slots on one device; a slot = a stream, a device arena (carved per call; the scratch,
+// whose Control block is zeroed when the arena is allocated, always sits at its start) and pinned staging.  The blocking
+// calls use slot 0.  sq_implicit_loss_host_submit / _wait expose the slots: while slot A's kernels run, slot B's inputs
+// cross PCIe.
+constexpr int kSlots = 2;
+struct sq_slot {
+    cudaStream_t stream;
+    char* dev; size_t dev_bytes;
+    char* pin; size_t pin_bytes;
+    size_t out_off, out_bytes;           // where the pending call's results sit in `pin`
+    int pending_batch; bool pending, pending_grad;
+};
 struct sq_ctx {
     int device;
-    cudaStream_t stream;
-    char* dev; size_t dev_bytes;          // one device arena, carved per call; the scratch (with its Control block,
-                                          // zeroed when the arena is allocated) always sits at its start
-    char* pin; size_t pin_bytes;          // pinned staging for results
+    sq_slot slot[kSlots];
 };
 
-static int ctx_reserve(sq_ctx* c, size_t dev_bytes, size_t pin_bytes) {
+static int slot_reserve(sq_slot* c, size_t dev_bytes, size_t pin_bytes) {
     if (dev_bytes > c->dev_bytes) {
-        if (c->dev) SQ_TRY(cudaFree(c->dev));
+        if (c->dev) { SQ_TRY(cudaStreamSynchronize(c->stream)); SQ_TRY(cudaFree(c->dev)); }
         c->dev = nullptr; c->dev_bytes = 0;
         SQ_TRY(cudaMalloc(&c->dev, dev_bytes));
         c->dev_bytes = dev_bytes;
         SQ_TRY(cudaMemsetAsync(c->dev, 0, sizeof(Control), c->stream));
     }
     if (pin_bytes > c->pin_bytes) {
-        if (c->pin) SQ_TRY(cudaFreeHost(c->pin));
+        if (c->pin) { SQ_TRY(cudaStreamSynchronize(c->stream)); SQ_TRY(cudaFreeHost(c->pin)); }
         c->pin = nullptr; c->pin_bytes = 0;
         SQ_TRY(cudaMallocHost(&c->pin, pin_bytes));
         c->pin_bytes = pin_bytes;
@@ -1565,9 +1578,20 @@ int sq_ctx_create(int device, sq_ctx** out) {
     SQ_TRY(cudaSetDevice(device));
     sq_ctx* c = new (std::nothrow) sq_ctx();
     if (!c) return (int)cudaErrorMemoryAllocation;
-    c->device = device; c->dev = nullptr; c->dev_bytes = 0; c->pin = nullptr; c->pin_bytes = 0;
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete c; return (int)e; }
+    c->device = device;
+    for (int i = 0; i < kSlots; ++i) {
+        sq_slot& sl = c->slot[i];
+        sl.stream = nullptr; sl.dev = nullptr; sl.dev_bytes = 0; sl.pin = nullptr; sl.pin_bytes = 0;
+        sl.out_off = sl.out_bytes = 0; sl.pending_batch = 0; sl.pending = sl.pending_grad = false;
+    }
+    for (int i = 0; i < kSlots; ++i) {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            for (int j = 0; j < i; ++j) cudaStreamDestroy(c->slot[j].stream);
+            delete c;
+            return (int)e;
+        }
+    }
     *out = c;
     return 0;
 }
@@ -1575,9 +1599,13 @@ int sq_ctx_create(int device, sq_ctx** out) {
 void sq_ctx_destroy(sq_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->dev) cudaFree(c->dev);
-    if (c->pin) cudaFreeHost(c->pin);
-    cudaStreamDestroy(c->stream);
+    for (int i = 0; i < kSlots; ++i) {
+        sq_slot& sl = c->slot[i];
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.dev) cudaFree(sl.dev);
+        if (sl.pin) cudaFreeHost(sl.pin);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     delete c;
 }
 
@@ -1591,76 +1619,105 @@ static void nearest_offsets(int in, int out, int stride, int* off) {
     }
 }
 
-int sq_implicit_loss_host(sq_ctx* c, const float* pred_host, int batch, int render_size, const float* images_host,
-                          int height, int width, float tau, float sharpness, double* loss_host, float* grad_host) {
-    if (!c || !pred_host || !images_host || batch <= 0 || render_size <= 0) return (int)cudaErrorInvalidValue;
-    SQ_TRY(cudaSetDevice(c->device));
+int sq_implicit_loss_host_submit(sq_ctx* ctx, int slot, const float* pred_host, int batch, int render_size,
+                                 const void* images_host, int image_dtype, int height, int width, float image_scale,
+                                 float tau, float sharpness, int want_grad) {
+    if (!ctx || slot < 0 || slot >= kSlots || !pred_host || !images_host || batch <= 0 || render_size <= 0 ||
+        height <= 0 || width <= 0 || (image_dtype != SQ_F32 && image_dtype != SQ_U8))
+        return (int)cudaErrorInvalidValue;
+    SQ_TRY(cudaSetDevice(ctx->device));
+    sq_slot* c = &ctx->slot[slot];
+    if (c->pending) return (int)cudaErrorNotReady;          // the previous submit on this slot has not been waited for
     const int R = render_size;
+    const size_t px = image_dtype == SQ_U8 ? 1 : sizeof(float);
     // images in pinned (or registered) host memory are sampled in place over PCIe; pageable memory is copied whole
     cudaPointerAttributes attr;
-    const float* mapped = nullptr;
+    const void* mapped = nullptr;
     if (cudaPointerGetAttributes(&attr, images_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
-        mapped = static_cast<const float*>(attr.devicePointer);
+        mapped = attr.devicePointer;
     else
         cudaGetLastError();
     const size_t b_pred = align_up(sizeof(float) * 12 * (size_t)batch, 256);
-    const size_t b_img = align_up(sizeof(float) * (size_t)batch * (mapped ? (size_t)R * R : (size_t)height * width), 256);
+    const size_t b_img = align_up(sizeof(float) * (size_t)batch * R * R, 256);                 // the compact [batch, R, R] fp32 target
+    const size_t b_raw = mapped ? 0 : align_up(px * (size_t)batch * height * width, 256);       // pageable images, copied whole
     const size_t b_off = align_up(sizeof(int) * 4 * (size_t)R, 256);
     const size_t b_out = align_up(sizeof(double) + sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_scr = sq_scratch_bytes(batch, R);
-    int rc = ctx_reserve(c, align_up(b_scr, 256) + b_pred + b_img + b_off + b_out, b_off + b_out);
+    int rc = slot_reserve(c, align_up(b_scr, 256) + b_pred + b_img + b_raw + b_off + b_out, b_off + b_out);
     if (rc) return rc;
     char* d = c->dev;
     void* d_scr = d; d += align_up(b_scr, 256);
     float* d_pred = reinterpret_cast<float*>(d); d += b_pred;
     float* d_img = reinterpret_cast<float*>(d); d += b_img;
+    void* d_raw = d; d += b_raw;
     int* d_off = reinterpret_cast<int*>(d); d += b_off;
     double* d_loss = reinterpret_cast<double*>(d);
     float* d_grad = reinterpret_cast<float*>(d + sizeof(double)); d += b_out;
     int* h_off = reinterpret_cast<int*>(c->pin);
-    char* h_out = c->pin + b_off;
     nearest_offsets(height, R, width, h_off);
     nearest_offsets(width, R, 1, h_off + R);
+    for (int i = 0; i < R; ++i) { h_off[2 * R + i] = i * R; h_off[3 * R + i] = i; }             // identity tables of the compact target
     SQ_TRY(cudaMemcpyAsync(d_pred, pred_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
-    SQ_TRY(cudaMemcpyAsync(d_off, h_off, sizeof(int) * 2 * (size_t)R, cudaMemcpyHostToDevice, c->stream));
-    long long stride_b = (long long)height * width;
-    const int* d_row = d_off;
-    const int* d_col = d_off + R;
-    if (mapped) {
-        // gather into a compact [batch, R, R] image, then address it with identity tables kept behind the real ones
-        int* h_id = h_off + 2 * R;
-        for (int i = 0; i < R; ++i) { h_id[i] = i * R; h_id[R + i] = i; }
-        int* d_id = d_off + 2 * R;
-        SQ_TRY(cudaMemcpyAsync(d_id, h_id, sizeof(int) * 2 * (size_t)R, cudaMemcpyHostToDevice, c->stream));
-        gather_targets_kernel<<<1184, 256, 0, c->stream>>>(mapped, stride_b, d_row, d_col, R, batch, d_img);
-        SQ_TRY(cudaGetLastError());
-        stride_b = (long long)R * R; d_row = d_id; d_col = d_id + R;
-    } else {
-        SQ_TRY(cudaMemcpyAsync(d_img, images_host, sizeof(float) * (size_t)batch * height * width, cudaMemcpyHostToDevice, c->stream));
+    SQ_TRY(cudaMemcpyAsync(d_off, h_off, sizeof(int) * 4 * (size_t)R, cudaMemcpyHostToDevice, c->stream));
+    const void* src = mapped;
+    if (!mapped) {
+        SQ_TRY(cudaMemcpyAsync(d_raw, images_host, px * (size_t)batch * height * width, cudaMemcpyHostToDevice, c->stream));
+        src = d_raw;
     }
-    rc = sq_implicit_loss(d_pred, SQ_F32, batch, R, 1.0 / (double)(R - 1), 1e-4, d_img, stride_b,
-                          d_row, d_col, tau, sharpness, d_loss, nullptr, grad_host ? d_grad : nullptr, nullptr,
+    const long long stride_b = (long long)height * width;
+    if (image_dtype == SQ_U8)
+        gather_targets_kernel<unsigned char><<<1184, 256, 0, c->stream>>>(static_cast<const unsigned char*>(src), stride_b, d_off, d_off + R,
+                                                                         R, batch, image_scale, d_img);
+    else
+        gather_targets_kernel<float><<<1184, 256, 0, c->stream>>>(static_cast<const float*>(src), stride_b, d_off, d_off + R, R, batch,
+                                                                 image_scale, d_img);
+    SQ_TRY(cudaGetLastError());
+    rc = sq_implicit_loss(d_pred, SQ_F32, batch, R, 1.0 / (double)(R - 1), 1e-4, d_img, (long long)R * R,
+                          d_off + 2 * R, d_off + 3 * R, tau, sharpness, d_loss, nullptr, want_grad ? d_grad : nullptr, nullptr,
                           d_scr, b_scr, c->stream);
     if (rc) return rc;
-    const size_t out_bytes = sizeof(double) + (grad_host ? sizeof(float) * 12 * (size_t)batch : 0);
-    SQ_TRY(cudaMemcpyAsync(h_out, d_loss, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-    SQ_TRY(cudaStreamSynchronize(c->stream));
-    if (loss_host) memcpy(loss_host, h_out, sizeof(double));
-    if (grad_host) memcpy(grad_host, h_out + sizeof(double), sizeof(float) * 12 * (size_t)batch);
+    c->out_off = b_off;
+    c->out_bytes = sizeof(double) + (want_grad ? sizeof(float) * 12 * (size_t)batch : 0);
+    SQ_TRY(cudaMemcpyAsync(c->pin + c->out_off, d_loss, c->out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->pending = true; c->pending_grad = want_grad != 0; c->pending_batch = batch;
     return 0;
 }
 
-int sq_explicit_loss_host(sq_ctx* c, const float* true_host, const float* pred_host, int batch, int render_size,
+int sq_implicit_loss_host_wait(sq_ctx* ctx, int slot, double* loss_host, float* grad_host) {
+    if (!ctx || slot < 0 || slot >= kSlots) return (int)cudaErrorInvalidValue;
+    sq_slot* c = &ctx->slot[slot];
+    if (!c->pending) return (int)cudaErrorInvalidValue;
+    if (grad_host && !c->pending_grad) return (int)cudaErrorInvalidValue;
+    SQ_TRY(cudaSetDevice(ctx->device));
+    c->pending = false;
+    SQ_TRY(cudaStreamSynchronize(c->stream));
+    const char* h_out = c->pin + c->out_off;
+    if (loss_host) memcpy(loss_host, h_out, sizeof(double));
+    if (grad_host) memcpy(grad_host, h_out + sizeof(double), sizeof(float) * 12 * (size_t)c->pending_batch);
+    return 0;
+}
+
+int sq_implicit_loss_host(sq_ctx* c, const float* pred_host, int batch, int render_size, const float* images_host,
+                          int height, int width, float tau, float sharpness, double* loss_host, float* grad_host) {
+    int rc = sq_implicit_loss_host_submit(c, 0, pred_host, batch, render_size, images_host, SQ_F32, height, width, 1.0f, tau,
+                                          sharpness, grad_host ? 1 : 0);
+    if (rc) return rc;
+    return sq_implicit_loss_host_wait(c, 0, loss_host, grad_host);
+}
+
+int sq_explicit_loss_host(sq_ctx* ctx, const float* true_host, const float* pred_host, int batch, int render_size,
                           double* loss_host, float* grad_host) {
-    if (!c || !true_host || !pred_host || batch <= 0 || render_size <= 0) return (int)cudaErrorInvalidValue;
-    SQ_TRY(cudaSetDevice(c->device));
+    if (!ctx || !true_host || !pred_host || batch <= 0 || render_size <= 0) return (int)cudaErrorInvalidValue;
+    SQ_TRY(cudaSetDevice(ctx->device));
+    sq_slot* c = &ctx->slot[0];
+    if (c->pending) return (int)cudaErrorNotReady;
     // arange(0, 1 + step, step) of the reference: count the entries the way numpy does (ceil((stop-start)/step))
     const double step = 1.0 / (double)render_size;
     const int n = (int)ceil((1.0 + step) / step);
     const size_t b_par = align_up(sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_out = align_up(sizeof(double) + sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_scr = sq_scratch_bytes(batch, n);
-    int rc = ctx_reserve(c, align_up(b_scr, 256) + 2 * b_par + b_out, b_out);
+    int rc = slot_reserve(c, align_up(b_scr, 256) + 2 * b_par + b_out, b_out);
     if (rc) return rc;
     char* d = c->dev;
     void* d_scr = d; d += align_up(b_scr, 256);
@@ -1681,16 +1738,18 @@ int sq_explicit_loss_host(sq_ctx* c, const float* true_host, const float* pred_h
     return 0;
 }
 
-int sq_iou_counts_host(sq_ctx* c, const float* true_host, const float* pred_host, int batch, int render_size,
+int sq_iou_counts_host(sq_ctx* ctx, const float* true_host, const float* pred_host, int batch, int render_size,
                        long long* inter_host, long long* uni_host) {
-    if (!c || !true_host || !pred_host || !inter_host || !uni_host || batch <= 0 || render_size <= 1)
+    if (!ctx || !true_host || !pred_host || !inter_host || !uni_host || batch <= 0 || render_size <= 1)
         return (int)cudaErrorInvalidValue;
-    SQ_TRY(cudaSetDevice(c->device));
+    SQ_TRY(cudaSetDevice(ctx->device));
+    sq_slot* c = &ctx->slot[0];
+    if (c->pending) return (int)cudaErrorNotReady;
     const int n = render_size;
     const size_t b_par = align_up(sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_out = align_up(sizeof(long long) * 2 * (size_t)batch, 256);
     const size_t b_scr = sq_scratch_bytes(batch, n);
-    int rc = ctx_reserve(c, align_up(b_scr, 256) + 2 * b_par + b_out, b_out);
+    int rc = slot_reserve(c, align_up(b_scr, 256) + 2 * b_par + b_out, b_out);
     if (rc) return rc;
     char* d = c->dev;
     void* d_scr = d; d += align_up(b_scr, 256);

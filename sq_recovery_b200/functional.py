@@ -352,6 +352,7 @@ class HostContext:
 
     def __init__(self, device: int = 0):
         self._h = ctypes.c_void_p()
+        self._pending = {}
         _lib.check(_lib.lib().sq_ctx_create(device, ctypes.byref(self._h)), "sq_ctx_create")
 
     def close(self):
@@ -381,6 +382,35 @@ class HostContext:
                                               ctypes.cast(ctypes.byref(loss), ctypes.c_void_p),
                                               grad.ctypes.data_as(ctypes.c_void_p) if want_grad else None)
         _lib.check(rc, "sq_implicit_loss_host")
+        return loss.value, grad
+
+    def submit_implicit(self, slot, pred, images, render_size, tau, sharpness, want_grad=True, image_scale=None):
+        """First half of a pipelined ImplicitLoss call on slot 0 or 1 (sq_implicit_loss_host_submit).  `images` is a
+        float32 or uint8 numpy array (B, [1,] H, W) -- uint8 images are divided by 255 on the device unless image_scale
+        says otherwise; pinned images (e.g. a pinned torch tensor's .numpy()) are sampled in place over PCIe.  Both arrays
+        are kept alive, and must stay unchanged, until result(slot)."""
+        pred, p_pred = self._np(pred, np.float32)
+        if images.dtype == np.uint8:
+            images, tag, scale = np.ascontiguousarray(images), _lib.SQ_U8, 1.0 / 255.0
+        else:
+            images, tag, scale = np.ascontiguousarray(images, dtype=np.float32), _lib.SQ_F32, 1.0
+        if image_scale is not None:
+            scale = float(image_scale)
+        B = pred.shape[0]
+        H, W = images.shape[-2], images.shape[-1]
+        rc = _lib.lib().sq_implicit_loss_host_submit(self._h, slot, p_pred, B, render_size, images.ctypes.data_as(ctypes.c_void_p),
+                                                     tag, H, W, scale, tau, sharpness, 1 if want_grad else 0)
+        _lib.check(rc, "sq_implicit_loss_host_submit")
+        self._pending[slot] = (pred, images, B, want_grad)
+
+    def result(self, slot):
+        """Second half: blocks until the slot's call is done; returns (loss, grad or None)."""
+        pred, images, B, want_grad = self._pending.pop(slot)
+        loss = ctypes.c_double()
+        grad = np.empty((B, 12), dtype=np.float32) if want_grad else None
+        rc = _lib.lib().sq_implicit_loss_host_wait(self._h, slot, ctypes.cast(ctypes.byref(loss), ctypes.c_void_p),
+                                                   grad.ctypes.data_as(ctypes.c_void_p) if want_grad else None)
+        _lib.check(rc, "sq_implicit_loss_host_wait")
         return loss.value, grad
 
     def explicit_loss(self, true, pred, render_size, want_grad=True):

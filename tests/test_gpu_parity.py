@@ -332,6 +332,26 @@ def test_host_entry_points(dev, S):
     i, u = ctx.iou_counts(true.numpy(), pred.numpy(), R)
     i2, u2 = S.IoUAccuracy(R, dev).counts(true.to(dev), pred.to(dev))
     assert np.array_equal(i, i2.cpu().numpy()) and np.array_equal(u, u2.cpu().numpy())
+    # two calls in flight on the context's two slots (submit / wait), fp32 and 8-bit images, pinned and pageable
+    crit = S.ImplicitLoss(R, dev, 1.5, 260)
+    u8 = (img * 255.0).round().clamp(0, 255).to(torch.uint8)
+    as_f32 = u8.float() * np.float32(1.0 / 255.0)          # what the device makes of the 8-bit pixels
+    want_f = run(crit, img, pred, dev)
+    want_u = run(crit, as_f32, pred, dev)
+    pin_u8 = torch.empty(u8.shape, dtype=torch.uint8).pin_memory(); pin_u8.copy_(u8)
+    pin_f = torch.empty(img.shape, dtype=torch.float32).pin_memory(); pin_f.copy_(img)
+    for a, b in ((pin_f.numpy(), pin_u8.numpy()), (img.numpy(), u8.numpy())):
+        ctx.submit_implicit(0, pred.numpy(), a, R, 1.5, 260.0)
+        ctx.submit_implicit(1, pred.numpy(), b, R, 1.5, 260.0)
+        with pytest.raises(RuntimeError):                   # a slot holds one call at a time
+            ctx.submit_implicit(1, pred.numpy(), b, R, 1.5, 260.0)
+        l1, g1 = ctx.result(1)
+        l0, g0 = ctx.result(0)
+        assert l0 == want_f[0] and np.array_equal(g0.astype(np.float64), want_f[1])
+        assert l1 == want_u[0] and np.array_equal(g1.astype(np.float64), want_u[1])
+    ctx.submit_implicit(0, pred.numpy(), pin_u8.numpy(), R, 1.5, 260.0, want_grad=False)
+    l0, g0 = ctx.result(0)
+    assert g0 is None and abs(l0 - want_u[0]) <= 1e-12
     ctx.close()
 
 
