@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libsqloss.so")
+LIB_COUNT = os.path.join(HERE, "libsqloss_count.so")
 PEAKS = os.path.join(HERE, "sq_peaks")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-ftz=true", "-std=c++17"]
@@ -34,12 +35,16 @@ def _stale(out: str, srcs) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, "sqloss.cu"), os.path.join(CSRC, "sq_core.cuh"), os.path.join(ROOT, "include", "sqloss.h")]
+    srcs = [os.path.join(CSRC, "sqloss.cu"), os.path.join(CSRC, "sq_core.cuh"), os.path.join(ROOT, "include", "sqloss.h"),
+            os.path.join(CSRC, "sq_tables.inc")]
     if force or _stale(LIB, srcs):
         cmd = [_nvcc(), *ARCH, *FLAGS, "-shared", "-Xcompiler", "-fPIC", "-o", LIB, srcs[0]]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)
+    # the counting build (bench.py: walked fraction, issued-op counts): same sources, -DSQ_COUNT; never the timed library
+    if force or _stale(LIB_COUNT, srcs):
+        subprocess.check_call([_nvcc(), *ARCH, *FLAGS, "-DSQ_COUNT", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_COUNT, srcs[0]])
     peaks_src = os.path.join(CSRC, "peaks.cu")
     if force or _stale(PEAKS, [peaks_src]):
         subprocess.check_call([_nvcc(), *ARCH, "-O3", "-o", PEAKS, peaks_src])

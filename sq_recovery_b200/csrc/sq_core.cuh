@@ -29,6 +29,10 @@
 struct float2 { float x, y; };          // host build (tests/emu)
 #endif
 
+#ifndef SQ_COUNT_HOOK
+#define SQ_COUNT_HOOK(i, n) do { } while (0)
+#endif
+
 namespace sq {
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -405,8 +409,18 @@ SQ_HD double dbl_make(int hi, int lo) {
 // small int -> double without a conversion instruction (those share the MUFU pipe): 2^52 + 2^31 + k, minus the constant
 SQ_HD double int_to_dbl(int k) { return dbl_make(0x43300000, k ^ (int)0x80000000) - 4503601774854144.0; }
 
+// where the tables are read from: the constant arrays (host build; device: through L1), or a copy in shared memory
+struct RefTabs { const double* e2; const double* l2; };
+SQ_HD RefTabs default_tabs() {
+#if defined(__CUDA_ARCH__)
+    return RefTabs{kExp2TabDev, kLog2TabDev};
+#else
+    return RefTabs{kExp2TabHost, kLog2TabHost};
+#endif
+}
+
 // 2^y for |y| <= 1000, relative error ~1e-15: y = q/128 + f, 2^y = 2^floor(q/128) * T[q mod 128] * exp(f ln2)
-SQ_HD double exp2_acc(double y) {
+SQ_HD double exp2_acc(double y, const RefTabs& tb) {
     const double kMagic = 6755399441055744.0;                // 1.5 * 2^52: adding it leaves round(v) in the low word
     const double t = fma(y, 128.0, kMagic);
     const int q = dbl_lo(t);
@@ -415,26 +429,22 @@ SQ_HD double exp2_acc(double y) {
     const double z = f * kLn2;
     double p = fma(z, 1.0 / 24.0, 1.0 / 6.0);
     p = fma(p, z, 0.5); p = fma(p, z, 1.0); p = fma(p, z, 1.0);
-#if defined(__CUDA_ARCH__)
-    const double r = __ldg(&kExp2TabDev[j]) * p;
-#else
-    const double r = kExp2TabHost[j] * p;
-#endif
+    const double r = tb.e2[j] * p;
     return dbl_make(dbl_hi(r) + (k << 20), dbl_lo(r));       // times 2^k (the result stays a normal number)
 }
 
 // log2(m) for a positive normal m, absolute error ~1e-15 + 1e-16 |result|: m = 2^k f, f in [1,2) split at the midpoints
 // c_j of 128 mantissa intervals: log2 m = k + log2 c_j + log1p(f / c_j - 1) / ln2
-SQ_HD double log2_acc(double m) {
+SQ_HD double log2_acc(double m, const RefTabs& tb) {
     const int hi = dbl_hi(m), lo = dbl_lo(m);
     const int k = ((hi >> 20) & 0x7ff) - 1023;
     const int j = (hi >> 13) & 127;
     const double f = dbl_make((hi & 0x000fffff) | 0x3ff00000, lo);
 #if defined(__CUDA_ARCH__)
-    const double2 tab = __ldg(reinterpret_cast<const double2*>(kLog2TabDev) + j);
+    const double2 tab = reinterpret_cast<const double2*>(tb.l2)[j];
     const double ic = tab.x, lc = tab.y;
 #else
-    const double ic = kLog2TabHost[2 * j], lc = kLog2TabHost[2 * j + 1];
+    const double ic = tb.l2[2 * j], lc = tb.l2[2 * j + 1];
 #endif
     const double r = fma(f, ic, -1.0);                       // |r| < 1/250
     double p = fma(r, 0.2, -0.25);
@@ -448,21 +458,24 @@ SQ_HD double log2_acc(double m) {
 constexpr float kRefine = SQ_KREFINE;     // |x| below which a gradient-carrying point is re-evaluated in fp64
 
 // One point in fp64: s = base + cf d (d_i = Ms[i][2] step), the forward chain of point_forward() and x = kl (F - 1).
-// Not inlined: ~150 instructions that must not disturb the register allocation of the z walk.
+#ifdef SQ_REFINE_NOINLINE
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #else
 inline
 #endif
-float refined_x(const Sample& S, double step, float kl, double b0, double b1, double b2, float cf) {
+#else
+SQ_HD
+#endif
+float refined_x(const Sample& S, double step, float kl, double b0, double b1, double b2, float cf, const RefTabs& tb) {
     const double c = f2d(cf);
     const double s0 = fma(c, S.Ms[2] * step, b0), s1 = fma(c, S.Ms[5] * step, b1), s2 = fma(c, S.Ms[8] * step, b2);
     const double a0 = s0 == 0.0 ? 1e-2 : fabs(s0), a1 = s1 == 0.0 ? 1e-2 : fabs(s1), a2 = s2 == 0.0 ? 1e-2 : fabs(s2);
-    const double lA = S.pxy64 * log2_acc(a0), lB = S.pxy64 * log2_acc(a1), lC = S.pz64 * log2_acc(a2);
-    const double t1 = exp2_acc(-fmin(fabs(lA - lB), 64.0));
-    const double lE = S.e21_64 * (fmax(lA, lB) + log2_acc(1.0 + t1));
-    const double t2 = exp2_acc(-fmin(fabs(lE - lC), 64.0));
-    const double y = S.e1_64 * (fmax(lE, lC) + log2_acc(1.0 + t2));
+    const double lA = S.pxy64 * log2_acc(a0, tb), lB = S.pxy64 * log2_acc(a1, tb), lC = S.pz64 * log2_acc(a2, tb);
+    const double t1 = exp2_acc(-fmin(fabs(lA - lB), 64.0), tb);
+    const double lE = S.e21_64 * (fmax(lA, lB) + log2_acc(1.0 + t1, tb));
+    const double t2 = exp2_acc(-fmin(fabs(lE - lC), 64.0), tb);
+    const double y = S.e1_64 * (fmax(lE, lC) + log2_acc(1.0 + t2, tb));
     double Fm1;                                               // F - 1 = 2^y - 1
     if (fabs(y) < 0.0625) {
         const double z = y * kLn2;                            // |z| < 0.044: the series is exact to 1e-16 after z^7
@@ -470,7 +483,7 @@ float refined_x(const Sample& S, double step, float kl, double b0, double b1, do
         p = fma(p, z, 1.0 / 120.0); p = fma(p, z, 1.0 / 24.0); p = fma(p, z, 1.0 / 6.0); p = fma(p, z, 0.5); p = fma(p, z, 1.0);
         Fm1 = p * z;
     } else {
-        Fm1 = exp2_acc(fmin(fmax(y, -1000.0), 1000.0)) - 1.0;
+        Fm1 = exp2_acc(fmin(fmax(y, -1000.0), 1000.0), tb) - 1.0;
     }
     return d2f(f2d(kl) * Fm1);
 }
@@ -699,7 +712,8 @@ struct ColGrad {       // two-moment accumulators of one column
 struct BwdQueue {
     float* cf;       // plane "index" of the point
     float* pre;      // sum of T in front of it since the column's first gradient-carrying point; later: its suffix weight
-    float* x;        // log2 odds k log2(e) (F - 1) the scan used; later: the fp64-refined value for entries in rmask
+    float* x;        // the weight o (1 - o) = eo o^2 of the point; for entries in rmask the log2 odds x = k log2(e) (F - 1)
+                     // the scan used, replaced by the weight at the fp64-refined x in queue_refine_entry()
     float* d;        // refined entries: occupancy correction o(x refined) - o(x scan)
     int stride;
 };
@@ -810,6 +824,9 @@ __device__ __forceinline__ void plane_forward2(const Sample& S, const ImplicitPa
 // scan step of one plane: transmittance, suffix-sum bookkeeping and (for gradient-carrying warps) the backward
 template <bool BWD, bool FIX>
 SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, ColGrad& cg) {
+#if defined(__CUDA_ARCH__)
+    SQ_COUNT_HOOK(0, 1);
+#endif
     st.csl = fmaf(p.o, -P.tl, st.csl);
     st.cssum += st.csl;
     st.T = ex2(st.csl);
@@ -827,8 +844,9 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
                     const int at = st.qn * st.q.stride;
                     st.q.cf[at] = p.cf;             // plane
                     st.q.pre[at] = st.psh;          // T in front of it since the first active point
-                    st.q.x[at] = p.x;
-                    st.rmask |= (fabsf(p.x) < kRefine ? 1u : 0u) << st.qn;
+                    const bool shell = fabsf(p.x) < kRefine;
+                    st.q.x[at] = shell ? p.x : p.eo * p.o * p.o;     // refined later: x; else the weight o (1 - o) itself
+                    st.rmask |= (shell ? 1u : 0u) << st.qn;
                     ++st.qn;
                     st.seen = 1.0f;
                 }
@@ -838,6 +856,9 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
             if (SQ_ANY(now))
 #endif
             {
+#if defined(__CUDA_ARCH__)
+                SQ_COUNT_HOOK(1, 1);
+#endif
                 // do/dF = -k o (1-o) = -k eo o^2 ; the -k is applied in finalize
                 const float W = now ? p.eo * p.o * p.o : 0.0f;
                 Fwd fa = p.f;
@@ -862,12 +883,12 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
 // ---- the queued points after the walk (SQ_BWD_COMPACT), three steps; `at` = index of the entry in the queue arrays
 // 1. refined entries: x from the fp64 chain, and the first-order change of the point's occupancy that goes with it
 SQ_HD void queue_refine_entry(const Sample& S, double step, float kl, const BwdQueue& q, int at,
-                              double b0, double b1, double b2) {
+                              double b0, double b1, double b2, const RefTabs& tb) {
     const float x0 = q.x[at];
-    const float x1 = refined_x(S, step, kl, b0, b1, b2, q.cf[at]);
-    const float eo = ex2(x1), o = rcp(1.0f + eo);
-    q.x[at] = x1;
-    q.d[at] = -(float)kLn2 * eo * o * o * (x1 - x0);      // d o / d x = -ln2 o (1 - o)
+    const float x1 = refined_x(S, step, kl, b0, b1, b2, q.cf[at], tb);
+    const float eo = ex2(x1), o = rcp(1.0f + eo), w = eo * o * o;
+    q.x[at] = w;
+    q.d[at] = -(float)kLn2 * w * (x1 - x0);               // d o / d x = -ln2 o (1 - o)
 }
 // 2. per column (its owner): suffix weights S_e = U - prefix_e, corrected to first order for the occupancy changes of the
 // column's refined entries.  T_c = exp(-tau cs_c) and cs_c sums the occupancies at or in front of c, so with
@@ -890,17 +911,17 @@ SQ_HD void queue_suffix_weights(const BwdQueue& q, int qn, unsigned rmask, float
         if ((rmask >> e) & 1u) { const float d = q.d[at]; dsuf += d; bsuf = fmaf(d, Se, bsuf); }
     }
 }
-// 3. every entry: forward redone in fp32 for the ratios the backward needs (not amplified by k), weight from the queue's x
-// and suffix weight.  sign = sign(depth - target) of the column.
+// 3. every entry: forward redone in fp32 for the ratios the backward needs (not amplified by k); weight o (1 - o) and
+// suffix weight from the queue.  sign = sign(depth - target) of the column.
 template <bool FIX>
-SQ_HD void queue_entry_backward(const Sample& S, const ImplicitParams& P, const float* bh, const float* bl, float cf,
-                                float x, float Sw, float sign, bool has, Bwd& b) {
-    Plane pl;
-    plane_forward<FIX>(S, P, bh, bl, cf, pl);
-    const float eo = ex2(x), o = rcp(1.0f + eo);
-    float W = eo * o * o * Sw * sign;
-    if (!has) { fwd_neutral(pl.f); W = 0.f; }
-    point_backward<FIX>(pl.f, W, b);
+SQ_HD void queue_entry_backward(const Sample& S, const float* bh, const float* bl, float cf,
+                                float w, float Sw, float sign, bool has, Bwd& b) {
+    Fwd f;
+    point_forward<FIX>(S, fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]), fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]),
+                       fmaf(cf, S.dh[2], bh[2]) + fmaf(cf, S.dl[2], bl[2]), f);
+    float W = w * Sw * sign;
+    if (!has) { fwd_neutral(f); W = 0.f; }
+    point_backward<FIX>(f, W, b);
 }
 
 // ILP: number of z planes whose (independent) forward chains are in flight per thread.  A column walk is a serial

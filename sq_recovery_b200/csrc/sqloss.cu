@@ -27,6 +27,15 @@ __device__ unsigned long long g_bwd_stats[2];
 #define SQ_BWD_HOOK(a) do { const unsigned m_ = __ballot_sync(0xffffffffu, (a)); if ((threadIdx.x & 31) == 0) { \
     atomicAdd(&g_bwd_stats[0], 1ull); atomicAdd(&g_bwd_stats[1], (unsigned long long)__popc(m_)); } } while (0)
 #endif
+#ifdef SQ_COUNT         // counting build (libsqloss_count.so, bench.py): what the implicit column kernel did, per launch
+// [0] warp plane steps of the z walk (32 point evaluations each)   [1] on-the-spot backward blocks (queue full)
+// [2] deal-out rounds of the compacted backward (all entries)       [3] deal-out rounds of the fp64 refinement
+// [4] work items processed   [5] column groups with occupancy   [6] queued gradient points   [7] of them refined in fp64
+__device__ unsigned long long g_count[8];
+#define SQ_COUNT_HOOK(i, n) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_count[i], (unsigned long long)(n)); } while (0)
+#else
+#define SQ_COUNT_HOOK(i, n) do { } while (0)
+#endif
 #include "sq_core.cuh"
 
 using namespace sq;
@@ -650,6 +659,18 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& S = Ssh[warp];
+#if defined(SQ_BWD_COMPACT) && !defined(SQ_TABLES_GLOBAL)
+    // the tables of the fp64 refinement, copied to shared memory once per block (3 KB; they are read with per-lane indices)
+    __shared__ __align__(16) double tabs[BWD ? 384 : 2];
+    if (BWD) {
+        for (int i = threadIdx.x; i < 128; i += THREADS) tabs[i] = kExp2TabDev[i];
+        for (int i = threadIdx.x; i < 256; i += THREADS) tabs[128 + i] = kLog2TabDev[i];
+        __syncthreads();                                   // the only block-level barrier; before any work is taken
+    }
+    const RefTabs tb{tabs, tabs + 128};
+#else
+    const RefTabs tb = default_tabs();
+#endif
     // Persistent warps pull work items from a global cursor, most expensive first (plan kernel).  The next item and its
     // Sample are fetched while the current item is processed.  No block-level barrier anywhere.
     // Items the plan kernel has proven empty are never touched: depth is exactly 0 on all their columns (depth_out was
@@ -674,6 +695,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
             int b, chunk;
             L.split(wp.item, b, chunk);
             pre.commit(&S, lane);
+            SQ_COUNT_HOOK(4, 1);
 
             // Per-thread sums of the item live in the warp's shared-memory tile (the layout the final reduction reads),
             // not in 18 registers: they are touched once per non-empty column.
@@ -721,6 +743,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #endif
                     continue;
                 }
+                SQ_COUNT_HOOK(5, 1);
                 float bh[3], bl[3], cg[11], dxy[2];
                 column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
                 float depth;
@@ -785,12 +808,14 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                             }
                             __syncwarp();
                             const BwdQueue qwarp{qbuf, qbuf + kQN, qbuf + 2 * kQN, qbuf + 3 * kQN, 32};
+                            SQ_COUNT_HOOK(6, total); SQ_COUNT_HOOK(7, total_r);
+                            SQ_COUNT_HOOK(3, (total_r + 31) / 32); SQ_COUNT_HOOK(2, (total + 31) / 32);
                             // 1. the entries near the surface, dealt out evenly: x in fp64 (sq_core.cuh "fp64 refinement")
                             for (int j = lane; j < total_r; j += 32) {
                                 const int m_ = qmap_w[j], l_ = m_ >> 8, e_ = m_ & 255;
                                 queue_refine_entry(S, g.step, P.kl, qwarp, e_ * 32 + l_,
                                                    f2d(ci[0 * 32 + l_]) + f2d(ci[3 * 32 + l_]), f2d(ci[1 * 32 + l_]) + f2d(ci[4 * 32 + l_]),
-                                                   f2d(ci[2 * 32 + l_]) + f2d(ci[5 * 32 + l_]));
+                                                   f2d(ci[2 * 32 + l_]) + f2d(ci[5 * 32 + l_]), tb);
                             }
                             __syncwarp();
                             // 2. every lane turns the prefixes of ITS column's entries into (corrected) suffix weights
@@ -804,7 +829,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                                 const float cf_ = has ? qwarp.cf[at] : 1.0f, x_ = has ? qwarp.x[at] : 0.0f, sw_ = has ? qwarp.pre[at] : 0.0f;
                                 const float cbh[3] = {ci[0 * 32 + l_], ci[1 * 32 + l_], ci[2 * 32 + l_]};
                                 const float cbl[3] = {ci[3 * 32 + l_], ci[4 * 32 + l_], ci[5 * 32 + l_]};
-                                queue_entry_backward<true>(S, P, cbh, cbl, cf_, x_, sw_, ci[6 * 32 + l_], has, bq);
+                                queue_entry_backward<true>(S, cbh, cbl, cf_, x_, sw_, ci[6 * 32 + l_], has, bq);
                                 cfq = cf_; dx_ = ci[7 * 32 + l_]; dy_ = ci[8 * 32 + l_];
                             };
                             int j = lane;
@@ -1291,6 +1316,17 @@ const char* sq_error_string(int err) { return cudaGetErrorString((cudaError_t)er
 int sq_device_sm_count(int device, int* sm_count) {
     return (int)cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device);
 }
+
+#ifdef SQ_COUNT
+int sq_debug_counters(unsigned long long* host_out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(host_out, g_count, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess && reset) {
+        const unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_count, zero, sizeof zero);
+    }
+    return (int)e;
+}
+#endif
 
 #ifdef SQ_TIMELINE
 int sq_debug_timeline(unsigned long long* host_out, int n) {

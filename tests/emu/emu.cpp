@@ -25,8 +25,8 @@ void emu_set_refine(int on) { g_emu_refine = on; }     // fp64 refinement of the
 void emu_set_queue(int on) { g_emu_queue = on; }       // 0: every gradient point on the spot (two-moment path)
 
 // accuracy probes of the fp64 primitives
-double emu_exp2_acc(double y) { return exp2_acc(y); }
-double emu_log2_acc(double m) { return log2_acc(m); }
+double emu_exp2_acc(double y) { return exp2_acc(y, default_tabs()); }
+double emu_log2_acc(double m) { return log2_acc(m, default_tabs()); }
 
 // target: [B, n, n] in image orientation (row, col); depth_out optional [B, n, n] image orientation
 int emu_implicit(const double* pred, int B, int n, double step, double z0, const float* target, float tau, float k,
@@ -64,11 +64,11 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
                 if (g_emu_queue && w != 0.f && qn > 0) {
                     if (!g_emu_refine) rmask = 0u;
                     const double b0 = (double)bh[0] + (double)bl[0], b1 = (double)bh[1] + (double)bl[1], b2 = (double)bh[2] + (double)bl[2];
-                    for (int e = 0; e < qn; ++e) if ((rmask >> e) & 1u) queue_refine_entry(S, g.step, P.kl, q, e, b0, b1, b2);
+                    for (int e = 0; e < qn; ++e) if ((rmask >> e) & 1u) queue_refine_entry(S, g.step, P.kl, q, e, b0, b1, b2, default_tabs());
                     queue_suffix_weights(q, qn, rmask, U, tau);
                     for (int e = 0; e < qn; ++e) {
                         Bwd bq;
-                        queue_entry_backward<true>(S, P, bh, bl, qcf[e], qx[e], qpre[e], w, true, bq);
+                        queue_entry_backward<true>(S, bh, bl, qcf[e], qx[e], qpre[e], w, true, bq);
                         acc_add_point(a, bq, qcf[e], dx, dy);
                     }
                 }

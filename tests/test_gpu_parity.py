@@ -351,7 +351,7 @@ def test_host_entry_points(dev, S):
         assert l1 == want_u[0] and np.array_equal(g1.astype(np.float64), want_u[1])
     ctx.submit_implicit(0, pred.numpy(), pin_u8.numpy(), R, 1.5, 260.0, want_grad=False)
     l0, g0 = ctx.result(0)
-    assert g0 is None and abs(l0 - want_u[0]) <= 1e-12
+    assert g0 is None and abs(l0 - want_u[0]) <= 1e-6 * abs(want_u[0])      # the forward-only kernel (packed fp32 pairs)
     ctx.close()
 
 
