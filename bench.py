@@ -164,15 +164,167 @@ def measured_mufu_peak():
 
 
 def ncu_summary():
-    """Issued XU (MUFU pipe) warp instructions and DRAM bytes per launch of the dominant kernel, from the committed ncu
-    capture of this same seeded workload (tools/profile_step.py + tools/ncu_summary.py), or None."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "implicit_kernel_ncu_summary.json")))
-    except Exception:
-        return None
+    """DRAM bytes per launch of the dominant kernel and the ncu count of its XU-pipe instructions, from the committed
+    `ncu --set full` capture of this seeded workload (tools/profile_step.py + tools/ncu_summary.py), or None."""
+    for name in ("implicit_kernel_ncu_summary_r02.json", "implicit_kernel_ncu_summary.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            d["file"] = "profiles/" + name
+            return d
+        except Exception:
+            continue
+    return None
+
+
+class PcieSampler:
+    """NVML PCIe receive counter (bytes the GPU pulled from the host) while a loop runs: the measured H2D traffic."""
+
+    def __init__(self, index):
+        self.rx, self.stop_flag, self.thread = [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+
+    def start(self):
+        if self.nv is None:
+            return
+        def loop():
+            while not self.stop_flag:
+                try:      # KB/s over the driver's 20 ms window
+                    self.rx.append(self.nv.nvmlDeviceGetPcieThroughput(self.h, self.nv.NVML_PCIE_UTIL_RX_BYTES))
+                except Exception:
+                    break
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        vals = [v for v in self.rx if v > 0]
+        return (float(np.mean(vals)) * 1024.0) if vals else None          # bytes / s
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+class Workload:
+    """Four independent input batches of one parameter distribution, the step on them (public class call + backward), its
+    CUDA-graph captures, and the timing / counting of it."""
+
+    def __init__(self, name, size_range, S, O, dev, rank, side):
+        self.name, self.dev, self.S = name, dev, S
+        self.crit = S.ImplicitLoss(R, dev, TAU, SHARP)
+        render = S.ImplicitLoss(H, dev, TAU, SHARP)            # synthetic depth maps = soft renders of the true params
+        self.sets = []
+        for k in range(4):                                      # 4 independent batches, rotated -> inputs exceed L2
+            true = O.random_params(B, 1000 * rank + k, size_range=size_range)
+            pred = O.perturbed_params(true, 7 + k).to(dev)
+            img = render.depth_projection(true.to(dev)).unsqueeze(1).contiguous()
+            self.sets.append((img, pred))
+        torch.cuda.synchronize()
+        self.graphs, self.quad, self.quad_out = [], None, []
+        self.side = side
+
+    def eager_step(self, i):
+        img, pred = self.sets[i % 4]
+        p = pred.detach().requires_grad_(True)
+        loss = self.crit(img, p)
+        loss.backward()
+        return loss, p.grad
+
+    def capture(self):
+        """The same step captured once per input set (public API inside the capture: the class call and .backward());
+        replaying it removes the ~100 us of Python/autograd launch overhead per step, which is longer than the kernels.
+        And the four steps back to back in ONE graph: a single launch then covers ~0.2 ms of GPU work, so the host's
+        launch rate cannot leave the GPU idle between steps.  Same kernels, same work per step.  Warm-up and capture run
+        on one side stream: the per-stream workspace must exist before a capture starts."""
+        dev, side = self.dev, self.side
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for k in range(4):
+                for _ in range(2):
+                    self.eager_step(k)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        for k in range(4):
+            gph = torch.cuda.CUDAGraph()
+            img, pred = self.sets[k]
+            p = pred.detach().requires_grad_(True)
+            with torch.cuda.graph(gph, stream=side):
+                loss_k = self.crit(img, p)
+                loss_k.backward()
+            self.graphs.append((gph, loss_k, p))
+        self.quad = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.quad, stream=side):
+            for k in range(4):
+                img, pred = self.sets[k]
+                p = pred.detach().requires_grad_(True)
+                loss_k = self.crit(img, p)
+                loss_k.backward()
+                self.quad_out.append((loss_k, p))
+
+    def step(self, i):
+        if not self.graphs:
+            return self.eager_step(i)
+        gph, loss_k, p = self.graphs[i % 4]
+        gph.replay()
+        return loss_k, p.grad
+
+    def run(self, steps):
+        """`steps` steps enqueued back to back (four per graph launch when captured); returns the last (loss, grad)."""
+        if self.graphs:
+            for _ in range(steps // 4):
+                self.quad.replay()
+            out = (self.quad_out[3][0], self.quad_out[3][1].grad)
+            for i in range(steps - steps % 4, steps):
+                out = self.step(i)
+            return out
+        for i in range(steps):
+            out = self.eager_step(i)
+        return out
+
+    def kernel_ms(self, lib, n):
+        """The column kernel alone: CUDA events recorded around its launch on its stream (sq_profile_events), eager."""
+        ms = []
+        for i in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); b.record()                              # materialise the cudaEvent_t handles
+            torch.cuda.synchronize()
+            lib.sq_profile_events(a.cuda_event, b.cuda_event)
+            self.eager_step(i)
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.mean(ms))
+
+    def counts(self):
+        """What the column kernel did per launch on these inputs (counting build), averaged over the four batches."""
+        from sq_recovery_b200 import counting
+        per = [counting.implicit_counts(img, pred, R, TAU, SHARP, want_grad=True) for img, pred in self.sets]
+        keys = per[0]["counters"].keys()
+        return {"counters": {k: float(np.mean([p["counters"][k] for p in per])) for k in keys},
+                "walked_fraction": float(np.mean([p["walked_fraction"] for p in per])),
+                "point_evaluations": float(np.mean([p["point_evaluations"] for p in per])),
+                "xu_warp_inst_model": float(np.mean([p["xu_warp_inst_model"] for p in per]))}
+
+
+def roofline_block(kernel_ms, counts, peak, ncu, pts, clock):
+    peak_gops = peak["mufu_per_clk_sm"] * peak["sms"] * peak["sm_mhz"] * 1e6 / 1e9       # thread-MUFU ops/s, measured
+    issued = counts["xu_warp_inst_model"] * 32 if counts else None
+    achieved = issued / (kernel_ms * 1e-3) / 1e9 if issued else None
+    dense_equiv = pts * MUFU_PER_POINT / (kernel_ms * 1e-3) / 1e9
+    out = {"bound": "sfu", "kernel": "implicit_kernel<true>", "achieved": achieved, "peak": peak_gops, "unit": "G MUFU-op/s",
+           "frac": (achieved / peak_gops) if achieved else None, "kernel_ms": kernel_ms,
+           "issued_xu_warp_inst_per_launch": counts["xu_warp_inst_model"] if counts else None,
+           "walked_fraction": counts["walked_fraction"] if counts else None,
+           "evaluated_gpoints_per_s": counts["point_evaluations"] / (kernel_ms * 1e-3) / 1e9 if counts else None,
+           "counters_per_launch": counts["counters"] if counts else None,
+           "reference_algorithm_equivalent": {"mufu_per_point": MUFU_PER_POINT, "achieved": dense_equiv, "frac": dense_equiv / peak_gops},
+           "sm_mhz_during_run": clock}
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     from sq_recovery_b200 import inputs as O                # seeded randsq / randquat workloads
@@ -187,63 +339,12 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     steps, warmup = args.steps, max(args.warmup, 3)
-
-    crit = S.ImplicitLoss(R, dev, TAU, SHARP)
-    render = S.ImplicitLoss(H, dev, TAU, SHARP)             # synthetic depth maps = soft renders of the true params
-    sets = []
-    for k in range(4):                                      # 4 independent batches, rotated -> inputs exceed L2
-        true = O.random_params(B, 1000 * rank + k)
-        pred = O.perturbed_params(true, 7 + k).to(dev)
-        img = render.depth_projection(true.to(dev)).unsqueeze(1).contiguous()
-        sets.append((img, pred))
-    torch.cuda.synchronize()
-
-    def step(i):
-        img, pred = sets[i % 4]
-        p = pred.detach().requires_grad_(True)
-        loss = crit(img, p)
-        loss.backward()
-        return loss, p.grad
-
-    # The same step captured once per input set in a CUDA graph (public API inside the capture: the class call and
-    # .backward()); replaying it removes the ~100 us of Python/autograd launch overhead per step, which is longer
-    # than the kernels themselves.
-    graphs = []
+    side = torch.cuda.Stream(dev)
+    main = Workload("config2", O.SIZE_RANGE, S, O, dev, rank, side)
+    dense = Workload("dense", O.DENSE_SIZE_RANGE, S, O, dev, rank, side)
     if not args.eager:
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for k in range(4):
-                for _ in range(2):
-                    step(k)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize()
-        for k in range(4):
-            gph = torch.cuda.CUDAGraph()
-            img, pred = sets[k]
-            p = pred.detach().requires_grad_(True)
-            with torch.cuda.graph(gph, stream=side):
-                loss_k = crit(img, p)
-                loss_k.backward()
-            graphs.append((gph, loss_k, p))
-        # ... and the four steps (one per input set) back to back in ONE graph: a single launch then covers ~220 us of
-        # GPU work, so the host's launch rate (10-20 us per graph launch on these boxes, more on a busy host) cannot
-        # leave the GPU idle between steps.  Same kernels, same work per step.
-        quad = torch.cuda.CUDAGraph()
-        quad_out = []
-        with torch.cuda.graph(quad, stream=side):
-            for k in range(4):
-                img, pred = sets[k]
-                p = pred.detach().requires_grad_(True)
-                loss_k = crit(img, p)
-                loss_k.backward()
-                quad_out.append((loss_k, p))
-        eager_step = step
-
-        def step(i):                                        # noqa: F811  (graph replay of the step above)
-            gph, loss_k, p = graphs[i % 4]
-            gph.replay()
-            return loss_k, p.grad
+        main.capture()
+        dense.capture()
 
     def barrier():
         if world > 1:
@@ -254,83 +355,108 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     for i in range(warmup):
-        step(i)
-    if graphs:
-        for _ in range(3):
-            quad.replay()
+        main.step(i)
+    main.run(12)
     # The timed region may last only milliseconds, shorter than nvidia-smi's sampling period, so the same step is
     # also run untimed for ~0.7 s right before it with the sampler on: the clocks / throttle reasons reported are
     # those of this workload under sustained load, and the timed steps follow back to back.
     t_soak = time.perf_counter()
     while time.perf_counter() - t_soak < 0.7:
-        for i in range(50):
-            step(i)
+        main.run(48)
         torch.cuda.synchronize()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    if graphs:
-        for _ in range(steps // 4):                         # four steps per graph launch ...
-            quad.replay()
-        loss, grad = quad_out[3][0], quad_out[3][1].grad
-        for i in range(steps - steps % 4, steps):           # ... and the remainder one by one
-            loss, grad = step(i)
-    else:
-        for i in range(steps):
-            loss, grad = step(i)
+    loss, grad = main.run(steps)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    # dominant kernel alone, CUDA events recorded around its launch on its stream (sq_profile_events); eager launches
-    kms = []
-    one = eager_step if graphs else step
-    for i in range(min(steps, 20)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); b.record()                              # materialise the cudaEvent_t handles
-        torch.cuda.synchronize()
-        _lib.lib().sq_profile_events(a.cuda_event, b.cuda_event)
-        one(i)
-        torch.cuda.synchronize()
-        kms.append(a.elapsed_time(b))
-    # eager (no graph) step time for comparison
-    eager_ms = None
-    if graphs:
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(min(steps, 20)):
-            eager_step(i)
-        e1.record(); torch.cuda.synchronize()
-        eager_ms = e0.elapsed_time(e1) / min(steps, 20)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    assert torch.isfinite(loss).item() and torch.isfinite(grad).all().item()
+    # the second workload: objects that fill the grid (a ~ U(0.5, 1)), where culling cannot help
+    dsteps = max(4, min(steps, 80))
+    dense.run(8)
+    barrier()
+    ev0.record()
+    dense.run(dsteps)
+    ev1.record()
+    barrier()
+    dms = ev0.elapsed_time(ev1)
+    kms = main.kernel_ms(_lib.lib(), min(steps, 20))
+    dkms = dense.kernel_ms(_lib.lib(), min(steps, 12))
+    eager_ms = None
+    if main.graphs:                                         # eager (no graph) step time for comparison
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(min(steps, 20)):
+            main.eager_step(i)
+        ev1.record(); torch.cuda.synchronize()
+        eager_ms = ev0.elapsed_time(ev1) / min(steps, 20)
+    t = torch.tensor([ms, dms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
-    assert torch.isfinite(loss).item() and torch.isfinite(grad).all().item()
+    ms, dms = t[0].item(), t[1].item()
 
-    # ---- e2e: host buffers -> C-ABI host call -> host results, copies inside the timed region
+    # ---- e2e: host buffers -> C-ABI host calls -> host results, copies inside the timed region.  Headline: 8-bit depth
+    # images (what the reference's data are, torch/test.py:29-30) in pinned memory, two calls in flight on the context's
+    # two slots (sq_implicit_loss_host_submit / _wait): while one batch is being computed the next one crosses PCIe.
+    # Also reported: the blocking fp32-image call of round 1.
     ctx = HostContext(local)
     h_sets = []
-    for img, pred in sets[:2]:
-        hi = torch.empty(img.shape, dtype=torch.float32).pin_memory(); hi.copy_(img)
+    for img, pred in main.sets:
+        hu = torch.empty(img.shape, dtype=torch.uint8).pin_memory(); hu.copy_((img * 255.0).round().clamp(0, 255).to(torch.uint8))
+        hf = torch.empty(img.shape, dtype=torch.float32).pin_memory(); hf.copy_(img)
         hp = torch.empty(pred.shape, dtype=torch.float32).pin_memory(); hp.copy_(pred)
-        h_sets.append((hi.numpy(), hp.numpy()))
+        h_sets.append((hu.numpy(), hf.numpy(), hp.numpy()))
+
+    def pipelined(n):
+        """n steps, two in flight; every step: pinned inputs in, loss + gradient out to host memory."""
+        ctx.submit_implicit(0, h_sets[0][2], h_sets[0][0], R, TAU, SHARP)
+        out = None
+        for i in range(n):
+            if i + 1 < n:
+                ctx.submit_implicit((i + 1) % 2, h_sets[(i + 1) % 4][2], h_sets[(i + 1) % 4][0], R, TAU, SHARP)
+            out = ctx.result(i % 2)
+        return out
+
+    pipelined(6)
     for i in range(3):
-        ctx.implicit_loss(h_sets[i % 2][1], h_sets[i % 2][0], R, TAU, SHARP)
+        ctx.implicit_loss(h_sets[i % 4][2], h_sets[i % 4][1], R, TAU, SHARP)
     barrier()
-    e2e_steps = min(steps, 20)
+    e2e_steps = max(4, steps)
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        l_h, g_h = ctx.implicit_loss(h_sets[i % 2][1], h_sets[i % 2][0], R, TAU, SHARP)
+    l_h, g_h = pipelined(e2e_steps)
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    barrier()
+    f32_steps = min(steps, 20)
+    t0 = time.perf_counter()
+    for i in range(f32_steps):
+        l_f, g_f = ctx.implicit_loss(h_sets[i % 4][2], h_sets[i % 4][1], R, TAU, SHARP)
+    f32_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, f32_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = te.item()
-    with torch.no_grad():                                   # the host path and the torch path agree
-        l_t = crit(*sets[(e2e_steps - 1) % 2]).item()
+    e2e_s, f32_s = te[0].item(), te[1].item()
+    # measured H2D traffic of the same loop (NVML PCIe receive counter, ~1 s of it)
+    pcie = None
+    if rank == 0:
+        ps = PcieSampler(local)
+        ps.start()
+        t0 = time.perf_counter(); n_soak = 0
+        while time.perf_counter() - t0 < 1.0:
+            pipelined(64); n_soak += 64
+        soak_s = time.perf_counter() - t0
+        rate = ps.stop()
+        if rate:
+            pcie = {"rx_bytes_per_s": rate, "bytes_per_step": rate * soak_s / n_soak, "steps": n_soak,
+                    "how": "nvmlDeviceGetPcieThroughput(RX) averaged over ~1 s of the same pipelined loop"}
+    with torch.no_grad():                                   # the host paths and the torch path agree
+        k_last = (e2e_steps - 1) % 4
+        img_u = torch.from_numpy(h_sets[k_last][0]).to(dev).float() * np.float32(1.0 / 255.0)
+        l_t = main.crit(img_u, main.sets[k_last][1]).item()
         assert abs(l_h - l_t) <= 1e-6 * abs(l_t) and np.isfinite(g_h).all(), (l_h, l_t)
+        l_t = main.crit(*main.sets[(f32_steps - 1) % 4]).item()
+        assert abs(l_f - l_t) <= 1e-6 * abs(l_t) and np.isfinite(g_f).all(), (l_f, l_t)
     ctx.close()
 
     if rank == 0:
@@ -338,58 +464,54 @@ def run_gpu(args):
         value = world * pts * steps / (ms * 1e-3) / 1e9
         peak = measured_mufu_peak()
         clock = clocks["sm_mhz"] or peak["sm_mhz"]
-        kernel_ms = float(np.mean(kms))
-        peak_gops = peak["mufu_per_clk_sm"] * peak["sms"] * peak["sm_mhz"] * 1e6 / 1e9       # thread-MUFU ops/s, measured
         ncu = ncu_summary()
-        # ISSUED MUFU-pipe thread-ops per launch (ncu count for this seeded workload; includes the f64<->f32
-        # conversions, which share the pipe) over the kernel time measured live = true pipe utilisation.
-        issued = ncu["xu_warp_inst_per_launch"] * 32 if ncu else None
-        achieved = issued / (kernel_ms * 1e-3) / 1e9 if issued else None
-        dense_equiv = pts * MUFU_PER_POINT / (kernel_ms * 1e-3) / 1e9
-        # Dispatch model measured with csrc/peaks.cu on this GPU (profiles/peaks_r01.json, EX2_FFMA{4,6,8}): per
-        # scheduler a MUFU warp-instruction costs ~6 issue cycles and any other one ~0.9, and the XU itself 8 per MUFU:
-        # t >= max(8 Nm, 6 Nm + 0.9 No) / (4 schedulers x SMs x clock).  This is the bound the kernel actually runs into.
-        dispatch = None
-        if ncu and ncu.get("warp_inst_per_launch"):
-            nm, no = ncu["xu_warp_inst_per_launch"], ncu["warp_inst_per_launch"] - ncu["xu_warp_inst_per_launch"]
-            cyc = max(8.0 * nm, 6.0 * nm + 0.9 * no) / (4 * peak["sms"])
-            t_us = cyc / clock
-            dispatch = {"mufu_warp_inst": nm, "other_warp_inst": no, "bound_us": t_us, "kernel_us": kernel_ms * 1e3,
-                        "frac": t_us / (kernel_ms * 1e3),
-                        "model": "max(8 Nm, 6 Nm + 0.9 No) issue cycles per scheduler (profiles/peaks_r01.json EX2_FFMA*)"}
+        try:
+            c_main, c_dense = main.counts(), dense.counts()
+        except Exception as e:      # the counting build is optional evidence, not part of the product path
+            c_main = c_dense = None
+            print(f"counting build unavailable: {e}", file=sys.stderr)
+        roof = roofline_block(kms, c_main, peak, ncu, pts, clock)
+        roof["traffic"] = ncu["dram_bytes_per_launch"] if ncu else None
+        roof["ncu"] = {"file": ncu.get("file"), "xu_warp_inst_per_launch": ncu.get("xu_warp_inst_per_launch"),
+                       "warp_inst_per_launch": ncu.get("warp_inst_per_launch")} if ncu else None
+        roof["how"] = ("achieved = MUFU-pipe (XU) thread-ops the kernel ISSUES per launch / live CUDA-event kernel time (events "
+                       "around the launch, eager: includes ~3 us of launch latency).  Issued ops = events counted by the "
+                       "counting build of the same sources (libsqloss_count.so) on these inputs x the per-event MUFU cost read "
+                       "off the kernel source (sq_recovery_b200/counting.py); the committed ncu capture holds the hardware count "
+                       "for comparison.  The kernel skips grid points whose occupancy is below 2^-40, stops a column once its "
+                       "transmittance is gone and evaluates F with 8 MUFU ops instead of 10, so issued ops are far fewer than "
+                       "the reference algorithm's 16 per grid point (`reference_algorithm_equivalent`)")
+        roof["peak_source"] = (f"{peak['source']}: {peak['mufu_per_clk_sm']:.2f} MUFU/clk/SM x {peak['sms']} SMs x "
+                               f"{peak['sm_mhz']:.0f} MHz (measured)")
+        droof = roofline_block(dkms, c_dense, peak, None, pts, clock)
+        h2d_u8 = B * R * min(W, R * 32) + B * 12 * 4 + 4 * R * 4       # sectors of the sampled rows + parameters + offset tables
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), launch="CUDA graph replay, four steps (one per input set) per graph launch" if graphs else "eager",
-                           eager_ms_per_step=eager_ms),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "launch": "CUDA graph replay, four steps (one per input set) per graph launch" if main.graphs else "eager",
+            "eager_ms_per_step": eager_ms,
+            "walked_fraction": roof["walked_fraction"], "evaluated_gpoints_per_s": roof["evaluated_gpoints_per_s"],
             "clocks": clocks,
             "e2e": {"value": world * pts * e2e_steps / e2e_s / 1e9, "unit": UNIT,
-                    # the pinned depth maps are sampled in place over PCIe: only the 32-byte sectors holding sampled
-                    # pixels cross the bus (ncu dram_bytes_read of the same access pattern: 16.9 MB at 256 -> 64)
-                    "h2d_bytes_per_step": B * R * min(W * 4, R * 32) + B * 12 * 4 + 4 * R * 4,
-                    "d2h_bytes_per_step": 8 + B * 12 * 4, "host_image_bytes": B * H * W * 4,
-                    "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "api": "sq_implicit_loss_host (include/sqloss.h) on pinned host buffers"},
+                    # the pinned 8-bit depth maps are sampled in place over PCIe: the 32-byte sectors of the sampled rows
+                    # cross the bus (every 4th row of a 256 x 256 image, all of its 256 bytes)
+                    "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": 8 + B * 12 * 4,
+                    "h2d_bytes_per_step_measured": pcie["bytes_per_step"] if pcie else None, "pcie": pcie,
+                    "host_image_bytes": B * H * W, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "api": "sq_implicit_loss_host_submit / _wait (include/sqloss.h): uint8 depth images and fp32 parameters in "
+                           "pinned host memory, loss + gradient back to host memory every step, two calls in flight",
+                    "blocking_f32_images": {"value": world * pts * f32_steps / f32_s / 1e9, "ms_per_step": f32_s / f32_steps * 1e3,
+                                            "h2d_bytes_per_step": B * R * min(W * 4, R * 32) + B * 12 * 4 + 4 * R * 4,
+                                            "api": "sq_implicit_loss_host, fp32 images, one call at a time (round 1's e2e)"}},
             "gpu_launches": 3 * steps,
-            "roofline": {"bound": "sfu", "kernel": "implicit_kernel<true>", "achieved": achieved, "peak": peak_gops,
-                         "unit": "G MUFU-op/s", "frac": (achieved / peak_gops) if achieved else None,
-                         "traffic": ncu["dram_bytes_per_launch"] if ncu else None,
-                         "kernel_ms": kernel_ms,
-                         "how": "achieved = MUFU-pipe thread-ops the kernel ISSUES per launch (profiles/"
-                                "implicit_kernel_ncu_summary.json) / live CUDA-event kernel time (events around the launch: "
-                                "includes ~5 us of launch latency); the kernel skips grid points whose occupancy is below "
-                                "2^-40 (box + ellipsoid bounds) and evaluates F with 8 MUFU ops instead of 10, so issued ops "
-                                "are far fewer than the reference algorithm's 16 per grid point",
-                         "dispatch_bound": dispatch,
-                         "reference_algorithm_equivalent": {"mufu_per_point": MUFU_PER_POINT, "achieved": dense_equiv,
-                                                            "frac": dense_equiv / peak_gops},
-                         "peak_source": f"{peak['source']}: {peak['mufu_per_clk_sm']:.2f} MUFU/clk/SM x {peak['sms']} SMs x "
-                                        f"{peak['sm_mhz']:.0f} MHz (of measured)",
-                         "sm_mhz_during_run": clock},
+            "roofline": roof,
+            "dense": {"workload": f"same call, sizes a ~ U{O.DENSE_SIZE_RANGE} (objects fill the grid; BASELINE config 2 draws "
+                                  f"a ~ U{O.SIZE_RANGE})", "value": world * pts * dsteps / (dms * 1e-3) / 1e9, "unit": UNIT,
+                      "steps": dsteps, "ms_per_step": dms / dsteps, "roofline": droof},
         }
         if world == 1:
-            line["cpu_baseline"] = cpu_reference(3, 1)[0]
+            line["cpu_baseline"] = cpu_reference(5, 1)[0]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=4096)
     ap.add_argument("--render", type=int, default=128)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--out", default="", help="also append the JSON line to this file")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -65,12 +66,16 @@ def main():
         if rank == 0:
             per_pair_iou = torch.cat(parts)
     if rank == 0:
-        n_ex = ex.xyz.shape[1] if False else R + 1
-        print(json.dumps({"harness": "sweep", "n_gpus": world, "pairs": args.pairs, "render_size": R,
-                          "iou_ms": ms_iou, "iou_gpoints_per_s": args.pairs * R ** 3 / ms_iou / 1e6,
-                          "explicit_fwd_ms": ms_ex, "explicit_gpoints_per_s": args.pairs * n_ex ** 3 / ms_ex / 1e6,
-                          "batch_iou": g_iou.item(), "mean_explicit_loss": g_loss.item(),
-                          "per_pair_iou_mean": per_pair_iou.mean().item(), "per_pair_iou_count": per_pair_iou.numel()}), flush=True)
+        n_ex = ex._n
+        line = json.dumps({"harness": "sweep", "n_gpus": world, "pairs": args.pairs, "render_size": R,
+                           "iou_ms": ms_iou, "iou_gpoints_per_s": args.pairs * R ** 3 / ms_iou / 1e6,
+                           "explicit_fwd_ms": ms_ex, "explicit_gpoints_per_s": args.pairs * n_ex ** 3 / ms_ex / 1e6,
+                           "batch_iou": g_iou.item(), "mean_explicit_loss": g_loss.item(),
+                           "per_pair_iou_mean": per_pair_iou.mean().item(), "per_pair_iou_count": per_pair_iou.numel()})
+        print(line, flush=True)
+        if args.out:
+            with open(args.out, "a") as f:
+                f.write(line + "\n")
     if world > 1:
         dist.destroy_process_group()
 

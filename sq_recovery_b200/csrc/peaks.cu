@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) bench_kernel(float* out, int iters, float
             for (int j = 0; j < ILP; ++j) {
                 if (OP == EX2) v[j] = ex2f(v[j]);
                 else if (OP == LG2) v[j] = lg2f(v[j]);
-                else if (OP == RCP) v[j] = rcpf(v[j]) + c2;      // + FADD so rcp(rcp(x)) cannot be folded
+                else if (OP == RCP) v[j] = fadd(rcpf(v[j]), c2);   // + FADD (volatile asm, like every op here) keeps x near 1
                 else if (OP == MUFU_MIX) { v[j] = (k % 3 == 0) ? ex2f(v[j]) : (k % 3 == 1) ? lg2f(v[j]) : rcpf(v[j]); }
                 else if (OP == FFMA) v[j] = ffma(v[j], c1, c2);
                 else if (OP == FADD) v[j] = fadd(v[j], c2);

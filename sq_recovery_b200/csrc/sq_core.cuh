@@ -39,7 +39,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr double kLn2 = 0.6931471805599453;
 constexpr float kAbsFix = 1e-2f;          // |s| used when s == 0  (s^2 := 1e-4, classes.py:171-173)
 #ifndef SQ_KACTIVE
-#define SQ_KACTIVE 32.0f
+#define SQ_KACTIVE 24.0f
 #endif
 constexpr float kActive = SQ_KACTIVE;     // |log2 of the sigmoid odds| beyond which o(1-o) < 2^-kActive is dropped
 
@@ -553,7 +553,7 @@ SQ_HD void finalize_sample(const SampleFull& S, const Grid& g, const double* acc
 //   to 1.053 at k = 260: 25 % fewer points to evaluate.
 SQ_HD float cull_bound(float kl) { return sqrtf((1.0f + 128.0f / kl) * 1.002f); }
 #ifndef SQ_IMPLICIT_CULL_BITS
-#define SQ_IMPLICIT_CULL_BITS 40.0f
+#define SQ_IMPLICIT_CULL_BITS 32.0f
 #endif
 constexpr float kImplicitCullBits = SQ_IMPLICIT_CULL_BITS;
 
@@ -693,7 +693,7 @@ SQ_HD bool column_zero_possible(const Sample& S, const float* bh) {
 struct ImplicitParams { float kl; float tl; float bound; };     // k log2(e), tau log2(e), implicit_cull_bound(kl)
 
 #ifndef SQ_KDEEP
-#define SQ_KDEEP 40.0f
+#define SQ_KDEEP 32.0f
 #endif
 constexpr float kDeep = SQ_KDEEP;       // points behind 2^-kDeep of transmittance carry no gradient (S_c < n 2^-kDeep)
 
@@ -890,26 +890,30 @@ SQ_HD void queue_refine_entry(const Sample& S, double step, float kl, const BwdQ
     q.x[at] = w;
     q.d[at] = -(float)kLn2 * w * (x1 - x0);               // d o / d x = -ln2 o (1 - o)
 }
-// 2. per column (its owner): suffix weights S_e = U - prefix_e, corrected to first order for the occupancy changes of the
+// 2. suffix weight of entry e of a column, S_e = U - prefix_e, corrected to first order for the occupancy changes of the
 // column's refined entries.  T_c = exp(-tau cs_c) and cs_c sums the occupancies at or in front of c, so with
 // o_p -> o_p + d_p:  T_c -> T_c (1 - tau sum_{p <= c} d_p)  and
 //   S_e -> S_e - tau ( S_e sum_{p <= e} d_p  +  sum_{p > e} d_p S_p ).
 // The occupancy the scan saw carries the fp32 chain's error in x (~1e-4 at k = 260), and through tau cs it reaches the
-// weight of EVERY point behind; measured (tests/emu) this is the larger part of the fp32 gradient error.
-SQ_HD void queue_suffix_weights(const BwdQueue& q, int qn, unsigned rmask, float U, float tau) {
-    float dall = 0.f;
+// weight of EVERY point behind; measured (tests/emu, profiles/parity_sweep_r02.json) this is the larger part of the
+// fp32 gradient error.  Evaluated per dealt entry by a loop over the column's refined entries (one to three, typically:
+// the planes where the column crosses the surface); `col` = index of the column's entry 0 in the queue arrays.
+SQ_HD int lowest_bit(unsigned m) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+SQ_HD float queue_suffix_weight(const BwdQueue& q, int col, int e, unsigned rmask, float U, float tau) {
+    const float Se = U - q.pre[col + e * q.stride];
+    float a = 0.f, b = 0.f;                                  // sum of d over refined entries at or before e; sum of d S behind e
     for (unsigned m = rmask; m; m &= m - 1u) {
-        int e = 0;
-        while (!((m >> e) & 1u)) ++e;
-        dall += q.d[e * q.stride];
+        const int ei = lowest_bit(m), at = col + ei * q.stride;
+        const float d = q.d[at];
+        if (ei <= e) a += d; else b = fmaf(d, U - q.pre[at], b);
     }
-    float dsuf = 0.f, bsuf = 0.f;                            // over the refined entries behind e: sum d, sum d S
-    for (int e = qn - 1; e >= 0; --e) {
-        const int at = e * q.stride;
-        const float Se = U - q.pre[at];
-        q.pre[at] = Se - tau * fmaf(dall - dsuf, Se, bsuf);
-        if ((rmask >> e) & 1u) { const float d = q.d[at]; dsuf += d; bsuf = fmaf(d, Se, bsuf); }
-    }
+    return Se - tau * fmaf(a, Se, b);
 }
 // 3. every entry: forward redone in fp32 for the ratios the backward needs (not amplified by k); weight o (1 - o) and
 // suffix weight from the queue.  sign = sign(depth - target) of the column.

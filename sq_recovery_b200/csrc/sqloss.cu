@@ -637,8 +637,8 @@ __device__ unsigned long long g_timeline[3 * 8192];
 __device__ unsigned int g_classes[kClasses];
 #endif
 
-// dynamic shared memory of the fwd+bwd kernel, per warp: 4 queue arrays + 9 x 32 column values + the deal-out list
-constexpr size_t kImplicitBwdSmemPerWarp = (size_t)kBwdDepth * 32 * (4 * sizeof(float) + sizeof(unsigned short)) + 9 * 32 * sizeof(float);
+// dynamic shared memory of the fwd+bwd kernel, per warp: 4 queue arrays + 11 x 32 column values + the deal-out list
+constexpr size_t kImplicitBwdSmemPerWarp = (size_t)kBwdDepth * 32 * (4 * sizeof(float) + sizeof(unsigned short)) + 11 * 32 * sizeof(float);
 static_assert(kImplicitBwdSmemPerWarp % 16 == 0, "per-warp regions stay 16-byte aligned");
 
 template <bool BWD, int THREADS, int MINB, int CPTMAX>      // CPTMAX: upper limit of L.cpt
@@ -654,14 +654,14 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
     constexpr int kQN = kBwdDepth * 32;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float* const qbuf = reinterpret_cast<float*>(dyn_smem + (size_t)(threadIdx.x >> 5) * kImplicitBwdSmemPerWarp);      // [4][kQN]
-    float* const colinfo_w = qbuf + 4 * kQN;                                                                         // [9][32]
-    unsigned short* const qmap_w = reinterpret_cast<unsigned short*>(colinfo_w + 9 * 32);                            // [kQN]
+    float* const colinfo_w = qbuf + 4 * kQN;                                                                         // [11][32]
+    unsigned short* const qmap_w = reinterpret_cast<unsigned short*>(colinfo_w + 11 * 32);                            // [kQN]
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& S = Ssh[warp];
 #if defined(SQ_BWD_COMPACT) && !defined(SQ_TABLES_GLOBAL)
     // the tables of the fp64 refinement, copied to shared memory once per block (3 KB; they are read with per-lane indices)
-    __shared__ __align__(16) double tabs[BWD ? 384 : 2];
+    __shared__ __align__(16) double tabs[BWD ? 384 : 130];      // (forward-only: never read)
     if (BWD) {
         for (int i = threadIdx.x; i < 128; i += THREADS) tabs[i] = kExp2TabDev[i];
         for (int i = threadIdx.x; i < 256; i += THREADS) tabs[128 + i] = kLog2TabDev[i];
@@ -799,6 +799,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                             ci[0 * 32 + lane] = bh[0]; ci[1 * 32 + lane] = bh[1]; ci[2 * 32 + lane] = bh[2];
                             ci[3 * 32 + lane] = bl[0]; ci[4 * 32 + lane] = bl[1]; ci[5 * 32 + lane] = bl[2];
                             ci[6 * 32 + lane] = wsg; ci[7 * 32 + lane] = dxy[0]; ci[8 * 32 + lane] = dxy[1];
+                            ci[9 * 32 + lane] = U; ci[10 * 32 + lane] = __uint_as_float(rmask);
                             {
                                 int at_r = (incl - cnt) >> 16, at_p = total_r + ((incl - cnt) & 0xffff);
                                 for (int e = 0; e < qn; ++e) {
@@ -818,15 +819,15 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                                                    f2d(ci[2 * 32 + l_]) + f2d(ci[5 * 32 + l_]), tb);
                             }
                             __syncwarp();
-                            // 2. every lane turns the prefixes of ITS column's entries into (corrected) suffix weights
-                            if (qn > 0) queue_suffix_weights(qlane, qn, rmask, U, P.tl * (float)kLn2);
-                            __syncwarp();
-                            // 3. all entries, dealt out evenly; two rounds in flight (two independent MUFU chains)
+                            // 2. + 3. all entries, dealt out evenly: suffix weight (corrected for the refined entries of the
+                            // entry's column), forward redone, backward; two rounds in flight (two independent MUFU chains)
+                            const float tau = P.tl * (float)kLn2;
                             auto dealt = [&](int j, Bwd& bq, float& cfq, float& dx_, float& dy_) {
                                 const bool has = j < total;
-                                const int m_ = has ? qmap_w[j] : 0, l_ = m_ >> 8, at = (m_ & 255) * 32 + l_;
+                                const int m_ = has ? qmap_w[j] : 0, l_ = m_ >> 8, e_ = m_ & 255, at = e_ * 32 + l_;
                                 // idle lane of the last round: a slot that may never have been written
-                                const float cf_ = has ? qwarp.cf[at] : 1.0f, x_ = has ? qwarp.x[at] : 0.0f, sw_ = has ? qwarp.pre[at] : 0.0f;
+                                const float cf_ = has ? qwarp.cf[at] : 1.0f, x_ = has ? qwarp.x[at] : 0.0f;
+                                const float sw_ = has ? queue_suffix_weight(qwarp, l_, e_, __float_as_uint(ci[10 * 32 + l_]), ci[9 * 32 + l_], tau) : 0.0f;
                                 const float cbh[3] = {ci[0 * 32 + l_], ci[1 * 32 + l_], ci[2 * 32 + l_]};
                                 const float cbl[3] = {ci[3 * 32 + l_], ci[4 * 32 + l_], ci[5 * 32 + l_]};
                                 queue_entry_backward<true>(S, cbh, cbl, cf_, x_, sw_, ci[6 * 32 + l_], has, bq);

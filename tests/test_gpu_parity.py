@@ -745,3 +745,38 @@ def test_parity_sweep_every_sample(dev, S):
             for c in range(preds.shape[0]):
                 l, gr = run(crit, imgs[c], preds[c], dev)
                 check(l, gr, refs[tag + "_loss"][c], refs[tag + "_grad"][c], what=f"{tag} call {c}", keep=refs[tag + "_keep"][c])
+
+
+def test_train_harness(dev, S, tmp_path):
+    """harness/train_step.py (the structure of torch/train.py:72-175): a few epochs on a tiny synthetic set -- finite,
+    the training loss goes down, validation loss / IoU are recorded, the best-val checkpoint is written in the reference's
+    dict format and resuming continues from it; and the fused-heads loss equals the unfused one on the same network."""
+    from harness import train_step
+    from harness.model import SQRegressor
+    ck = str(tmp_path / "model.pt")
+    hist = train_step.main(["--batch", "16", "--epochs", "3", "--steps-per-epoch", "4", "--val-batches", "1", "--lr", "1e-3",
+                            "--checkpoint", ck])
+    assert len(hist["loss"]) == 3 and all(np.isfinite(hist["loss"])) and all(np.isfinite(hist["val_loss"]))
+    assert hist["loss"][-1] < hist["loss"][0]
+    assert all(0.0 <= a <= 1.0 for e in hist["val_acc"] for a in e)
+    saved = torch.load(ck, weights_only=False)
+    assert set(saved) == {"epoch", "model_state_dict", "optimizer_state_dict", "loss"}
+    assert set(saved["loss"]) == {"loss", "val_loss", "val_acc"}
+    best = int(np.argmin(hist["val_loss"]))
+    assert saved["epoch"] == best and len(saved["loss"]["loss"]) == best + 1
+    more = train_step.main(["--batch", "16", "--epochs", "1", "--steps-per-epoch", "4", "--val-batches", "1", "--checkpoint", ck,
+                            "--resume"])
+    assert len(more["loss"]) == best + 2                                 # history continues after the restored epoch
+    # heads fused into the loss kernels == sigmoid / normalise / cat in torch, on one network and one batch
+    torch.manual_seed(1)
+    net = SQRegressor().to(dev)
+    true = O.random_params(8, 5).to(dev)
+    crit = S.ImplicitLoss(64, dev, 1.5, 260)
+    images = S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(true).unsqueeze(1).contiguous()
+    l1 = crit(images, net(images)); l1.backward()
+    g1 = net.trunk.fc[2].weight.grad.clone()
+    net.zero_grad()
+    l2 = crit.from_heads(images, net(images, raw=True)); l2.backward()
+    g2 = net.trunk.fc[2].weight.grad
+    assert abs(l1.item() - l2.item()) <= 1e-5 * abs(l1.item())
+    assert (g1 - g2).norm().item() <= 2e-2 * g1.norm().item()           # fp32 heads vs fp64-in-kernel heads at k = 260
