@@ -426,9 +426,8 @@ SQ_HD double exp2_acc(double y, const RefTabs& tb) {
     const int q = dbl_lo(t);
     const double f = fma(t - kMagic, -0.0078125, y);         // y - q/128, |f| <= 1/256
     const int j = q & 127, k = q >> 7;
-    const double z = f * kLn2;
-    double p = fma(z, 1.0 / 24.0, 1.0 / 6.0);
-    p = fma(p, z, 0.5); p = fma(p, z, 1.0); p = fma(p, z, 1.0);
+    const double z = f * kLn2, z2 = z * z;                  // exp(z) = (1 + z) + z^2 (1/2 + z/6) + z^4/24, shallow (latency)
+    const double p = fma(z2 * z2, 1.0 / 24.0, fma(z2, fma(z, 1.0 / 6.0, 0.5), 1.0 + z));
     const double r = tb.e2[j] * p;
     return dbl_make(dbl_hi(r) + (k << 20), dbl_lo(r));       // times 2^k (the result stays a normal number)
 }
@@ -447,9 +446,9 @@ SQ_HD double log2_acc(double m, const RefTabs& tb) {
     const double ic = tb.l2[2 * j], lc = tb.l2[2 * j + 1];
 #endif
     const double r = fma(f, ic, -1.0);                       // |r| < 1/250
-    double p = fma(r, 0.2, -0.25);
-    p = fma(p, r, 1.0 / 3.0); p = fma(p, r, -0.5); p = fma(p, r, 1.0);
-    return fma(p * r, 1.4426950408889634, lc + int_to_dbl(k));
+    const double r2 = r * r;                                 // log1p(r) = r + r^2 (-1/2 + r/3) + r^4 (-1/4 + r/5), shallow
+    const double p = fma(r2 * r2, fma(r, 0.2, -0.25), fma(r2, fma(r, 1.0 / 3.0, -0.5), r));
+    return fma(p, 1.4426950408889634, lc + int_to_dbl(k));
 }
 
 #ifndef SQ_KREFINE
@@ -479,9 +478,10 @@ float refined_x(const Sample& S, double step, float kl, double b0, double b1, do
     double Fm1;                                               // F - 1 = 2^y - 1
     if (fabs(y) < 0.0625) {
         const double z = y * kLn2;                            // |z| < 0.044: the series is exact to 1e-16 after z^7
-        double p = fma(z, 1.0 / 5040.0, 1.0 / 720.0);
-        p = fma(p, z, 1.0 / 120.0); p = fma(p, z, 1.0 / 24.0); p = fma(p, z, 1.0 / 6.0); p = fma(p, z, 0.5); p = fma(p, z, 1.0);
-        Fm1 = p * z;
+        const double z2 = z * z, z4 = z2 * z2;
+        const double hi = fma(z2, 1.0 / 5040.0, fma(z, 1.0 / 720.0, 1.0 / 120.0));          // z^4 .. z^6 terms
+        const double lo = fma(z2, fma(z, 1.0 / 24.0, 1.0 / 6.0), fma(z, 0.5, 1.0));          // 1 .. z^3 terms
+        Fm1 = z * fma(z4, hi, lo);
     } else {
         Fm1 = exp2_acc(fmin(fmax(y, -1000.0), 1000.0), tb) - 1.0;
     }
@@ -822,7 +822,7 @@ __device__ __forceinline__ void plane_forward2(const Sample& S, const ImplicitPa
 #endif
 
 // scan step of one plane: transmittance, suffix-sum bookkeeping and (for gradient-carrying warps) the backward
-template <bool BWD, bool FIX>
+template <bool BWD, bool FIX, bool QUEUE>      // QUEUE: gradient-carrying points go to the lane's BwdQueue (SQ_BWD_COMPACT)
 SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, ColGrad& cg) {
 #if defined(__CUDA_ARCH__)
     SQ_COUNT_HOOK(0, 1);
@@ -838,7 +838,7 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
 #endif
             bool now = active;                  // lanes whose point is handled on the spot
 #if defined(SQ_BWD_COMPACT)
-            if (st.q.cf) {
+            if (QUEUE) {
                 const bool room = st.qn < kBwdDepth;
                 if (active && room) {
                     const int at = st.qn * st.q.stride;
@@ -935,16 +935,16 @@ SQ_HD void queue_entry_backward(const Sample& S, const float* bh, const float* b
 #define SQ_IMP_ILP 2
 #endif
 
-template <bool BWD, bool FIX = true>
-// bwd_q / U_out / qn_out / spilled_out: SQ_BWD_COMPACT only (see ColState); colgrad11 then holds only what was
-// handled on the spot.
+template <bool BWD, bool FIX = true, bool QUEUE = false>
+// QUEUE (SQ_BWD_COMPACT): bwd_q / U_out / qn_out / spilled_out / rmask_out are used (see ColState); colgrad11 then holds
+// only what was handled on the spot.
 SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams& P,
                             const float* bh, const float* bl, int c_lo, int c_hi, int lane_lo, float* colgrad11,
                             const BwdQueue* bwd_q = nullptr, float* U_out = nullptr, int* qn_out = nullptr,
                             bool* spilled_out = nullptr, unsigned* rmask_out = nullptr) {
     // planes in front of the range: o = 0, cs = 0, T = 1 each
     ColState st;
-    if (bwd_q) st.q = *bwd_q; else { st.q.cf = st.q.pre = st.q.x = st.q.d = nullptr; st.q.stride = 0; }
+    if (QUEUE) st.q = *bwd_q; else { st.q.cf = st.q.pre = st.q.x = st.q.d = nullptr; st.q.stride = 0; }
     st.qn = 0; st.spilled = false; st.rmask = 0u;
     st.csl = 0.f;                                     // -tau log2(e) cs
     st.T = 1.0f;                                      // 2^csl
@@ -981,7 +981,7 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < SQ_IMP_ILP; ++j) plane_scan<BWD, FIX>(P, p[j], st, cg);
+        for (int j = 0; j < SQ_IMP_ILP; ++j) plane_scan<BWD, FIX, QUEUE>(P, p[j], st, cg);
 #ifndef SQ_NO_EARLY_EXIT
         stop = !SQ_ANY(st.csl > -kDeep && c - SQ_IMP_ILP >= lane_lo);
 #endif
@@ -990,7 +990,7 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
     for (; !stop && c >= c_lo; --c, cfi -= 1.0f) {
         Plane p0;
         plane_forward<FIX>(S, P, bh, bl, (c == 0) ? S.cf0 : cfi, p0);
-        plane_scan<BWD, FIX>(P, p0, st, cg);
+        plane_scan<BWD, FIX, QUEUE>(P, p0, st, cg);
 #ifndef SQ_NO_EARLY_EXIT
         stop = !SQ_ANY(st.csl > -kDeep && c - 1 >= lane_lo);
 #endif
@@ -1001,7 +1001,7 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
     st.cssum = fmaf(nb, st.csl, st.cssum);
     if (BWD) {
         const float U = fmaf(nb * st.seen, st.T, st.psh);
-        if (U_out) { *U_out = U; *qn_out = st.qn; *spilled_out = st.spilled; *rmask_out = st.rmask; }
+        if (QUEUE) { *U_out = U; *qn_out = st.qn; *spilled_out = st.spilled; *rmask_out = st.rmask; }
         for (int i = 0; i < 3; ++i) {
             colgrad11[i]     = fmaf(U, cg.gs0[i], -cg.gs1[i]);
             colgrad11[3 + i] = fmaf(U, cg.gz0[i], -cg.gz1[i]);
@@ -1049,6 +1049,53 @@ SQ_HD void acc_add_point(Acc& acc, const Bwd& b, float cf, float dx, float dy) {
 // range an SQ's occupancy is exactly 0 and its chain is not evaluated.
 struct Range { int lo, hi; };
 
+// SQ_EXP_PAIR: where both superquadrics are in range, their two forward chains -- the same instruction sequence on
+// different data and different per-sample constants -- run as packed fp32 pairs (true SQ in .x, predicted in .y).
+#ifndef SQ_EXP_PAIR
+#define SQ_EXP_PAIR 1
+#endif
+#if defined(__CUDA_ARCH__) && SQ_F32X2 && SQ_EXP_PAIR
+template <bool FIX>
+__device__ __forceinline__ void forward_pair(const Sample& Sa, const Sample& Sb, float kl, float cf,
+                                             const float* bha, const float* bla, const float* bhb, const float* blb,
+                                             Fwd& fa, Fwd& fb, float& oa, float& ob, float& xb, float& eb) {
+    const F2 c = f2(cf, cf);
+    F2 s[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        s[i] = add2(fma2(c, f2(Sa.dh[i], Sb.dh[i]), f2(bha[i], bhb[i])), fma2(c, f2(Sa.dl[i], Sb.dl[i]), f2(bla[i], blb[i])));
+    fa.sx = s[0].x; fa.sy = s[1].x; fa.sz = s[2].x;
+    fb.sx = s[0].y; fb.sy = s[1].y; fb.sz = s[2].y;
+    F2 m[3] = {s[0], s[1], s[2]};
+    if (FIX) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { m[i].x = (m[i].x == 0.0f) ? kAbsFix : m[i].x; m[i].y = (m[i].y == 0.0f) ? kAbsFix : m[i].y; }
+    }
+    const F2 pxy = f2(Sa.pxy, Sb.pxy), one = f2(1.0f, 1.0f);
+    const F2 lA = mul2(pxy, f2(lg2_abs(m[0].x), lg2_abs(m[0].y)));
+    const F2 lB = mul2(pxy, f2(lg2_abs(m[1].x), lg2_abs(m[1].y)));
+    const F2 lC = mul2(f2(Sa.pz, Sb.pz), f2(lg2_abs(m[2].x), lg2_abs(m[2].y)));
+    const F2 d1 = sub2(lA, lB);
+    const F2 t1 = f2(ex2_neg_abs(d1.x), ex2_neg_abs(d1.y));
+    const F2 u1 = add2(t1, one);
+    const F2 h1 = f2(lg2(u1.x), lg2(u1.y));
+    const F2 lE = mul2(f2(Sa.e21, Sb.e21), add2(f2(fmaxf(lA.x, lB.x), fmaxf(lA.y, lB.y)), h1));
+    const F2 d2 = sub2(lE, lC);
+    const F2 t2 = f2(ex2_neg_abs(d2.x), ex2_neg_abs(d2.y));
+    const F2 u2 = add2(t2, one);
+    const F2 h2 = f2(lg2(u2.x), lg2(u2.y));
+    const F2 lG = add2(f2(fmaxf(lE.x, lC.x), fmaxf(lE.y, lC.y)), h2);
+    const F2 yy = mul2(f2(Sa.e1, Sb.e1), lG);
+    const F2 F = f2(ex2(yy.x), ex2(yy.y));
+    const F2 xx = fma2(F, f2(kl, kl), f2(-kl, -kl));
+    const F2 eo = f2(ex2(xx.x), ex2(xx.y));
+    const F2 v = add2(eo, one);
+    fa.d1 = d1.x; fa.t1 = t1.x; fa.h1 = h1.x; fa.d2 = d2.x; fa.t2 = t2.x; fa.h2 = h2.x; fa.lG = lG.x; fa.F = F.x;
+    fb.d1 = d1.y; fb.t1 = t1.y; fb.h1 = h1.y; fb.d2 = d2.y; fb.t2 = t2.y; fb.h2 = h2.y; fb.lG = lG.y; fb.F = F.y;
+    oa = rcp(v.x); ob = rcp(v.y); xb = xx.y; eb = eo.y;
+}
+#endif
+
 // one z plane of explicit_column; HAS_T / HAS_P: whether the true / predicted SQ can be occupied on this plane
 template <bool BWD, bool HAS_T, bool HAS_P>
 SQ_HD void explicit_step(const Sample& St, const Sample& Sp, float kl, float cf,
@@ -1056,6 +1103,12 @@ SQ_HD void explicit_step(const Sample& St, const Sample& Sp, float kl, float cf,
                          float& sq, float* gs, float* gz, Acc& acc) {
     float ot = 0.f, op = 0.f, xp = 1e30f, ep = 0.f;
     Fwd ft, fp;
+#if defined(__CUDA_ARCH__) && SQ_F32X2 && SQ_EXP_PAIR
+    if (HAS_T && HAS_P) {
+        forward_pair<true>(St, Sp, kl, cf, bht, blt, bhp, blp, ft, fp, ot, op, xp, ep);
+    } else
+#endif
+    {
     if (HAS_T)
         point_forward<true>(St, fmaf(cf, St.dh[0], bht[0]) + fmaf(cf, St.dl[0], blt[0]),
                                 fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
@@ -1066,6 +1119,7 @@ SQ_HD void explicit_step(const Sample& St, const Sample& Sp, float kl, float cf,
                                 fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]), fp);
     if (HAS_T) { float xt, et; ot = occupancy(ft.F, kl, xt, et); }
     if (HAS_P) op = occupancy(fp.F, kl, xp, ep);
+    }
     const float d = ot - op;
     sq = fmaf(d, d, sq);
     if (BWD && HAS_P) {

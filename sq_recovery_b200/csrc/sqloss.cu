@@ -613,6 +613,19 @@ struct WorkPipe {
         next = next_pos < total ? wm.item(queue, cap, next_pos, lane) : -1;
         return next >= 0 && next_pos < empty_from;         // true: an item that needs its Sample
     }
+    // The same claim in three stages, so that its two dependent L2 round trips (cursor, queue) are spent under other work
+    // of the warp instead of stalling it: issue the cursor atomic; later turn its result into a queue lookup; later use
+    // the item (the caller then fetches its Sample).
+    int pend_pos;
+    __device__ __forceinline__ void claim_issue(int lane) {
+        pend_pos = 0;
+        if (lane == 0) pend_pos = (int)(atomicAdd(cursor, 1u) + gridDim.x * (blockDim.x >> 5));
+    }
+    __device__ __forceinline__ void claim_lookup(int lane) {
+        next_pos = __shfl_sync(0xffffffffu, pend_pos, 0);
+        next = next_pos < total ? wm.item(queue, cap, next_pos, lane) : -1;
+    }
+    __device__ __forceinline__ bool claim_finish() const { return next >= 0 && next_pos < empty_from; }
     __device__ __forceinline__ void rotate() { item = next; item_pos = next_pos; next = -1; }
 };
 
@@ -662,10 +675,14 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #if defined(SQ_BWD_COMPACT) && !defined(SQ_TABLES_GLOBAL)
     // the tables of the fp64 refinement, copied to shared memory once per block (3 KB; they are read with per-lane indices)
     __shared__ __align__(16) double tabs[BWD ? 384 : 130];      // (forward-only: never read)
-    if (BWD) {
-        for (int i = threadIdx.x; i < 128; i += THREADS) tabs[i] = kExp2TabDev[i];
-        for (int i = threadIdx.x; i < 256; i += THREADS) tabs[128 + i] = kLog2TabDev[i];
-        __syncthreads();                                   // the only block-level barrier; before any work is taken
+    constexpr int kTabRegs = (384 + THREADS - 1) / THREADS;
+    double tab_reg[kTabRegs];
+    if (BWD) {                                              // loads issued now, stored after the first work item is claimed
+#pragma unroll
+        for (int r = 0; r < kTabRegs; ++r) {
+            const int i = threadIdx.x + r * THREADS;
+            tab_reg[r] = i < 128 ? kExp2TabDev[i] : (i < 384 ? kLog2TabDev[i - 128] : 0.0);
+        }
     }
     const RefTabs tb{tabs, tabs + 128};
 #else
@@ -688,6 +705,13 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
     {
         SampleFetch pre;
         if (wp.item >= 0) pre.fetch(samples + L.sample_of(wp.item), lane);
+#if defined(SQ_BWD_COMPACT) && !defined(SQ_TABLES_GLOBAL)
+        if (BWD) {
+#pragma unroll
+            for (int r = 0; r < kTabRegs; ++r) { const int i = threadIdx.x + r * THREADS; if (i < 384) tabs[i] = tab_reg[r]; }
+            __syncthreads();                               // the only block-level barrier: every warp passes here once
+        }
+#endif
         while (wp.item >= 0) {
 #ifdef SQ_TIMELINE
             t_last_fetch = gtime(); ++n_items;
@@ -752,7 +776,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #ifdef SQ_BWD_COMPACT
                 float U = 0.f; int qn = 0; bool spilled = false; unsigned rmask = 0u;
                 const BwdQueue qlane{qbuf + lane, qbuf + kQN + lane, qbuf + 2 * kQN + lane, qbuf + 3 * kQN + lane, 32};
-                depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg, BWD ? &qlane : nullptr, &U, &qn, &spilled, &rmask);
+                depth = implicit_column<BWD, true, BWD>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg, &qlane, &U, &qn, &spilled, &rmask);
 #else
                 depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg);
 #endif
@@ -767,6 +791,13 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 // for ~1300 cycles, but the kernel is bound by instruction dispatch and the other warps of the scheduler
                 // fill the gap; an item claimed at the start of a long walk, on the other hand, is work no idle warp can
                 // take -- during the end-game that was the tail of the kernel.
+#if defined(SQ_BWD_COMPACT) && !defined(SQ_NO_STAGED_CLAIM)
+                const bool staged = BWD && k == L.cpt - 1;     // fwd+bwd: the claim is spread over the backward passes
+                if (staged) wp.claim_issue(lane);
+                else
+#else
+                const bool staged = false;
+#endif
                 if (k == L.cpt - 1 && wp.claim(lane)) pre.fetch(samples + L.sample_of(wp.next), lane);
 #endif
 #if defined(SQ_BWD_COMPACT)
@@ -789,6 +820,12 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     const int last = __shfl_sync(0xffffffffu, incl, 31);
                     const int total_r = last >> 16, total = total_r + (last & 0xffff);
                     const bool any_spill = __any_sync(0xffffffffu, spilled && wsg != 0.f);
+#ifndef SQ_EARLY_CLAIM
+                    if (staged) {
+                        wp.claim_lookup(lane);
+                        if (total == 0 && wp.claim_finish()) pre.fetch(samples + L.sample_of(wp.next), lane);
+                    }
+#endif
                     if (total > 0 || any_spill) {
                         Acc acc;
                         float v[kRedStride];
@@ -819,6 +856,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                                                    f2d(ci[2 * 32 + l_]) + f2d(ci[5 * 32 + l_]), tb);
                             }
                             __syncwarp();
+#ifndef SQ_EARLY_CLAIM
+                            if (staged && wp.claim_finish()) pre.fetch(samples + L.sample_of(wp.next), lane);
+#endif
                             // 2. + 3. all entries, dealt out evenly: suffix weight (corrected for the refined entries of the
                             // entry's column), forward redone, backward; two rounds in flight (two independent MUFU chains)
                             const float tau = P.tl * (float)kLn2;

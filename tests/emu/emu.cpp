@@ -49,8 +49,10 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
             float qcf[kBwdDepth], qpre[kBwdDepth], qx[kBwdDepth], qd[kBwdDepth];
             const BwdQueue q{qcf, qpre, qx, qd, 1};
             float U = 0.f; int qn = 0; bool spilled = false; unsigned rmask = 0u;
-            const float depth = grad ? implicit_column<true>(S, g, P, bh, bl, c_lo, c_hi, c_hi >= c_lo ? c_lo : n, cg, g_emu_queue ? &q : nullptr, &U, &qn, &spilled, &rmask)
-                                     : implicit_column<false>(S, g, P, bh, bl, c_lo, c_hi, c_hi >= c_lo ? c_lo : n, cg);
+            const int own_lo = c_hi >= c_lo ? c_lo : n;
+            const float depth = !grad ? implicit_column<false>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg)
+                              : g_emu_queue ? implicit_column<true, true, true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg, &q, &U, &qn, &spilled, &rmask)
+                                            : implicit_column<true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg);
             const int row = n - 1 - ib, col = ia;
             if (depth_out) depth_out[(size_t)b * n * n + row * n + col] = depth;
             const float tgt = target ? target[(size_t)b * n * n + row * n + col] : 0.f;
