@@ -1052,7 +1052,7 @@ struct Range { int lo, hi; };
 // SQ_EXP_PAIR: where both superquadrics are in range, their two forward chains -- the same instruction sequence on
 // different data and different per-sample constants -- run as packed fp32 pairs (true SQ in .x, predicted in .y).
 #ifndef SQ_EXP_PAIR
-#define SQ_EXP_PAIR 1
+#define SQ_EXP_PAIR 0
 #endif
 #if defined(__CUDA_ARCH__) && SQ_F32X2 && SQ_EXP_PAIR
 template <bool FIX>

@@ -625,7 +625,8 @@ struct WorkPipe {
         next_pos = __shfl_sync(0xffffffffu, pend_pos, 0);
         next = next_pos < total ? wm.item(queue, cap, next_pos, lane) : -1;
     }
-    __device__ __forceinline__ bool claim_finish() const { return next >= 0 && next_pos < empty_from; }
+    // decided on the position alone: the looked-up item id is not touched before the caller forms the Sample address
+    __device__ __forceinline__ bool claim_finish() const { return next_pos < total && next_pos < empty_from; }
     __device__ __forceinline__ void rotate() { item = next; item_pos = next_pos; next = -1; }
 };
 
@@ -748,9 +749,6 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 const int ia = it.ia, ib = it.ib;
                 const bool valid = it.valid(L);
                 const int row = g.n - 1 - ib, col = ia;        // classes.py:279: img[row, col] = depth[x = col, y = n-1-row]
-                float tv = tvs[0];                             // select, not an indexed load: tvs stays in registers
-#pragma unroll
-                for (int q = 1; q < CPTMAX; ++q) tv = k == q ? tvs[q] : tv;
                 it.next(L);
                 // which planes can hold occupancy: decided from the fp32 base; the exact (fp64) one is formed only for
                 // groups that have some
@@ -804,6 +802,12 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 if (BWD) {
                     // sign of (depth - target) per column; 0 for masked lanes
                     float wsg = 0.f;
+                    // the target pixel (issued before the walk, a miss to HBM) is first touched HERE: without the fence the
+                    // compiler forms |tv| right behind the load and the warp waits out the miss before it starts walking
+                    float tv = tvs[0];                         // select, not an indexed load: tvs stays in registers
+#pragma unroll
+                    for (int q = 1; q < CPTMAX; ++q) tv = k == q ? tvs[q] : tv;
+                    asm volatile("" : "+f"(tv));
                     if (valid) {
                         if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
                         const float diff = depth - tv;
@@ -900,6 +904,10 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 if (valid) {
                     if (depth_out) depth_out[((size_t)b * g.n + row) * g.n + col] = depth;
                     if (target) {
+                        float tv = tvs[0];
+#pragma unroll
+                        for (int q = 1; q < CPTMAX; ++q) tv = k == q ? tvs[q] : tv;
+                        asm volatile("" : "+f"(tv));           // first touch of the pixel after the walk (see above)
                         const float diff = depth - tv;
                         loss_sum += fabsf(diff) - fabsf(tv);
                         if (BWD && diff != 0.f) {
