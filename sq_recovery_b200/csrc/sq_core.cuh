@@ -882,13 +882,15 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
 
 // ---- the queued points after the walk (SQ_BWD_COMPACT), three steps; `at` = index of the entry in the queue arrays
 // 1. refined entries: x from the fp64 chain, and the first-order change of the point's occupancy that goes with it
-SQ_HD void queue_refine_entry(const Sample& S, double step, float kl, const BwdQueue& q, int at,
-                              double b0, double b1, double b2, const RefTabs& tb) {
-    const float x0 = q.x[at];
-    const float x1 = refined_x(S, step, kl, b0, b1, b2, q.cf[at], tb);
+SQ_HD void queue_store_refined(const BwdQueue& q, int at, float x0, float x1) {
     const float eo = ex2(x1), o = rcp(1.0f + eo), w = eo * o * o;
     q.x[at] = w;
     q.d[at] = -(float)kLn2 * w * (x1 - x0);               // d o / d x = -ln2 o (1 - o)
+}
+SQ_HD void queue_refine_entry(const Sample& S, double step, float kl, const BwdQueue& q, int at,
+                              double b0, double b1, double b2, const RefTabs& tb) {
+    const float x0 = q.x[at];
+    queue_store_refined(q, at, x0, refined_x(S, step, kl, b0, b1, b2, q.cf[at], tb));
 }
 // 2. suffix weight of entry e of a column, S_e = U - prefix_e, corrected to first order for the occupancy changes of the
 // column's refined entries.  T_c = exp(-tau cs_c) and cs_c sums the occupancies at or in front of c, so with

@@ -853,8 +853,27 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                             SQ_COUNT_HOOK(6, total); SQ_COUNT_HOOK(7, total_r);
                             SQ_COUNT_HOOK(3, (total_r + 31) / 32); SQ_COUNT_HOOK(2, (total + 31) / 32);
                             // 1. the entries near the surface, dealt out evenly: x in fp64 (sq_core.cuh "fp64 refinement")
-                            for (int j = lane; j < total_r; j += 32) {
-                                const int m_ = qmap_w[j], l_ = m_ >> 8, e_ = m_ & 255;
+                            // (SQ_REFINE_ILP2: two rounds in flight where there are that many -- measured 6 us SLOWER per call,
+                            // profiles/tune_r02.txt: the second chain's registers cost the walk its allocation)
+                            int jr = lane;
+#ifdef SQ_REFINE_ILP2
+                            for (; jr - lane + 32 < total_r; jr += 64) {
+                                const bool has1 = jr + 32 < total_r;
+                                const int m0 = qmap_w[jr], l0 = m0 >> 8, a0 = (m0 & 255) * 32 + l0;
+                                const int m1 = has1 ? qmap_w[jr + 32] : m0, l1 = m1 >> 8, a1 = (m1 & 255) * 32 + l1;
+                                const float x0 = qwarp.x[a0], x1 = qwarp.x[a1];
+                                const float r0 = refined_x(S, g.step, P.kl, f2d(ci[0 * 32 + l0]) + f2d(ci[3 * 32 + l0]),
+                                                           f2d(ci[1 * 32 + l0]) + f2d(ci[4 * 32 + l0]), f2d(ci[2 * 32 + l0]) + f2d(ci[5 * 32 + l0]),
+                                                           qwarp.cf[a0], tb);
+                                const float r1 = refined_x(S, g.step, P.kl, f2d(ci[0 * 32 + l1]) + f2d(ci[3 * 32 + l1]),
+                                                           f2d(ci[1 * 32 + l1]) + f2d(ci[4 * 32 + l1]), f2d(ci[2 * 32 + l1]) + f2d(ci[5 * 32 + l1]),
+                                                           qwarp.cf[a1], tb);
+                                queue_store_refined(qwarp, a0, x0, r0);
+                                if (has1) queue_store_refined(qwarp, a1, x1, r1);
+                            }
+#endif
+                            for (; jr < total_r; jr += 32) {
+                                const int m_ = qmap_w[jr], l_ = m_ >> 8, e_ = m_ & 255;
                                 queue_refine_entry(S, g.step, P.kl, qwarp, e_ * 32 + l_,
                                                    f2d(ci[0 * 32 + l_]) + f2d(ci[3 * 32 + l_]), f2d(ci[1 * 32 + l_]) + f2d(ci[4 * 32 + l_]),
                                                    f2d(ci[2 * 32 + l_]) + f2d(ci[5 * 32 + l_]), tb);
