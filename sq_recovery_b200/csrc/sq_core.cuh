@@ -176,62 +176,78 @@ SQ_HD void heads_backward(const double* hp, double hrn, const double* q, double*
 }
 
 // p: 12 raw parameters [a1 a2 a3 e1 e2 t1 t2 t3 qx qy qz qw].  clamp per classes.py:129-136 (IoU: no clamp, :398).
-SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, SampleFull& S) {
-    const double lo[8] = {0.05, 0.05, 0.05, 0.1, 0.1, 0.0, 0.0, 0.0};
-    double v[8];
-    for (int i = 0; i < 8; ++i) {
-        double x = p[i];
-        float m = 1.0f;
-        if (clamp) {
-            if (x < lo[i]) { x = lo[i]; m = 0.0f; }
-            if (x > 1.0) { x = 1.0; m = 0.0f; }
-        }
-        v[i] = x;
-        S.mask[i] = m;
+// prep_sample() in independent parts, so that the plan kernel can spread them over the lanes of a warp (the serial fp64
+// chain of one lane was 2.5 us of the call): part 0..2 = row i of the scaled rotation and everything derived from it,
+// part 3 = exponents and the power-mean weights, then prep_finish() once parts 0..3 are visible.
+SQ_HD double clamped_param(const double* p, bool clamp, int i, float* mask = nullptr) {
+    const double lo = i < 3 ? 0.05 : (i < 5 ? 0.1 : 0.0);     // a in [0.05, 1], e in [0.1, 1], t in [0, 1]  (classes.py:129-136)
+    double x = p[i];
+    float m = 1.0f;
+    if (clamp) {
+        if (x < lo) { x = lo; m = 0.0f; }
+        if (x > 1.0) { x = 1.0; m = 0.0f; }
     }
-    for (int i = 0; i < 3; ++i) { S.a[i] = v[i]; S.t[i] = v[5 + i]; }
-    S.e[0] = v[3]; S.e[1] = v[4];
-    for (int i = 0; i < 4; ++i) S.q[i] = p[8 + i];
-    // M = mat(conj(q)) = mat(q)^T   (quaternion.py:19-21, 46-67)
-    const double x = -p[8], y = -p[9], z = -p[10], w = p[11];
-    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
-    const double twx = tx * w, twy = ty * w, twz = tz * w;
-    const double txx = tx * x, txy = ty * x, txz = tz * x;
-    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    S.M[0] = 1.0 - (tyy + tzz); S.M[1] = txy - twz;         S.M[2] = txz + twy;
-    S.M[3] = txy + twz;         S.M[4] = 1.0 - (txx + tzz); S.M[5] = tyz - twx;
-    S.M[6] = txz - twy;         S.M[7] = tyz + twx;         S.M[8] = 1.0 - (txx + tyy);
-    for (int i = 0; i < 3; ++i) {
-        const double ia = 1.0 / S.a[i];
+    if (mask) *mask = m;
+    return x;
+}
+SQ_HD void prep_part(const double* p, bool clamp, const Grid& g, SampleFull& S, int part) {
+    if (part < 3) {
+        const int i = part;
+        // M = mat(conj(q)) = mat(q)^T   (quaternion.py:19-21, 46-67), row i
+        const double x = -p[8], y = -p[9], z = -p[10], w = p[11];
+        const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+        const double twx = tx * w, twy = ty * w, twz = tz * w;
+        const double txx = tx * x, txy = ty * x, txz = tz * x;
+        const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+        double m0, m1, m2;
+        if (i == 0)      { m0 = 1.0 - (tyy + tzz); m1 = txy - twz;         m2 = txz + twy; }
+        else if (i == 1) { m0 = txy + twz;         m1 = 1.0 - (txx + tzz); m2 = tyz - twx; }
+        else             { m0 = txz - twy;         m1 = tyz + twx;         m2 = 1.0 - (txx + tyy); }
+        S.M[3 * i] = m0; S.M[3 * i + 1] = m1; S.M[3 * i + 2] = m2;
+        const double a = clamped_param(p, clamp, i);
+        const double t0 = clamped_param(p, clamp, 5), t1 = clamped_param(p, clamp, 6), t2 = clamped_param(p, clamp, 7);
+        const double ia = 1.0 / a;
         S.ia[i] = ia;
-        for (int j = 0; j < 3; ++j) S.Ms[3 * i + j] = S.M[3 * i + j] * ia;
-        split2(S.Ms[3 * i + 2] * g.step, S.dh[i], S.dl[i]);
+        const double s0 = m0 * ia, s1 = m1 * ia, s2 = m2 * ia;
+        S.Ms[3 * i] = s0; S.Ms[3 * i + 1] = s1; S.Ms[3 * i + 2] = s2;
+        split2(s2 * g.step, S.dh[i], S.dl[i]);
         S.idh[i] = 1.0f / S.dh[i];
-        S.mf[2 * i] = (float)S.Ms[3 * i]; S.mf[2 * i + 1] = (float)S.Ms[3 * i + 1];
-        S.of[i] = (float)-(S.Ms[3 * i] * S.t[0] + S.Ms[3 * i + 1] * S.t[1] + S.Ms[3 * i + 2] * S.t[2]);
+        S.mf[2 * i] = (float)s0; S.mf[2 * i + 1] = (float)s1;
+        S.of[i] = (float)-(s0 * t0 + s1 * t1 + s2 * t2);
+    } else {
+        const double e1 = clamped_param(p, clamp, 3), e2 = clamped_param(p, clamp, 4);
+        // Power-mean inequality, for exponents 2/e >= 2:  F >= 2^(e1-1) (2^(e2-1) (sx^2 + sy^2) + sz^2); the factors
+        // are 1 for e > 1 (unclamped IoU parameters).  Non-positive e: no bound (the reference yields inf/nan there).
+        const double w1 = e2 > 0.0 ? (e2 < 1.0 ? exp2(e2 - 1.0) : 1.0) : 0.0;
+        const double b1 = e1 > 0.0 ? (e1 < 1.0 ? exp2(1.0 - e1) : 1.0) : 1e30;
+        S.qw = (float)w1; S.qB1 = (float)b1;
+        S.pxy64 = 2.0 / e2; S.pz64 = 2.0 / e1; S.e21_64 = e2 / e1; S.e1_64 = e1;
+        S.pxy = (float)S.pxy64; S.pz = (float)S.pz64; S.e21 = (float)S.e21_64; S.e1 = (float)e1;
+        S.cf0 = (float)(g.z0 / g.step);
     }
+}
+SQ_HD void prep_finish(const double* p, bool clamp, const Grid& g, SampleFull& S) {
+    for (int i = 0; i < 8; ++i) {
+        float m;
+        const double v = clamped_param(p, clamp, i, &m);
+        S.mask[i] = m;
+        if (i < 3) S.a[i] = v; else if (i < 5) S.e[i - 3] = v; else S.t[i - 5] = v;
+    }
+    for (int i = 0; i < 4; ++i) S.q[i] = p[8 + i];
     S.pad_ = 0.f;
     S.heads = 0; S.pad2_ = 0; S.hrn = 1.0;
     for (int i = 0; i < 8; ++i) S.hp[i] = 0.0;
-    {
-        // Power-mean inequality, for exponents 2/e >= 2:  F >= 2^(e1-1) (2^(e2-1) (sx^2 + sy^2) + sz^2); the factors
-        // are 1 for e > 1 (unclamped IoU parameters).  Non-positive e: no bound (the reference yields inf/nan there).
-        const double w1 = S.e[1] > 0.0 ? (S.e[1] < 1.0 ? exp2(S.e[1] - 1.0) : 1.0) : 0.0;
-        const double b1 = S.e[0] > 0.0 ? (S.e[0] < 1.0 ? exp2(1.0 - S.e[0]) : 1.0) : 1e30;
-        double al = 0.0;
-        for (int i = 0; i < 3; ++i) {
-            const double wi = i < 2 ? w1 : 1.0, d = S.Ms[3 * i + 2] * g.step;
-            S.wd[i] = (float)(wi * d);
-            al += wi * d * d;
-        }
-        S.qw = (float)w1; S.qa = (float)al; S.qia = (float)(1.0 / al); S.qB1 = (float)b1;
+    double al = 0.0;                                           // ellipsoid of column_range(): needs rows and qw
+    for (int i = 0; i < 3; ++i) {
+        const double wi = i < 2 ? (double)S.qw : 1.0, d = S.Ms[3 * i + 2] * g.step;
+        S.wd[i] = (float)(wi * d);
+        al += wi * d * d;
     }
-    S.cf0 = (float)(g.z0 / g.step);
-    S.pxy = (float)(2.0 / S.e[1]);
-    S.pz = (float)(2.0 / S.e[0]);
-    S.e21 = (float)(S.e[1] / S.e[0]);
-    S.e1 = (float)S.e[0];
-    S.pxy64 = 2.0 / S.e[1]; S.pz64 = 2.0 / S.e[0]; S.e21_64 = S.e[1] / S.e[0]; S.e1_64 = S.e[0];
+    S.qa = (float)al; S.qia = (float)(1.0 / al);
+}
+SQ_HD void prep_sample(const double* p, bool clamp, const Grid& g, SampleFull& S) {
+    for (int part = 0; part < 4; ++part) prep_part(p, clamp, g, S, part);
+    prep_finish(p, clamp, g, S);
 }
 
 // s at plane "index" 0 for the column through grid point (ia, ib): base_i = Ms_i . ((gx,gy,0) - t), as hi/lo floats
@@ -916,6 +932,19 @@ SQ_HD float queue_suffix_weight(const BwdQueue& q, int col, int e, unsigned rmas
         if (ei <= e) a += d; else b = fmaf(d, U - q.pre[at], b);
     }
     return Se - tau * fmaf(a, Se, b);
+}
+// The same occupancy changes move the rendered depth of the column: depth = 1 - sum_c T_c / n, so
+//   depth -> depth + (tau / n) sum_{refined p} d_p S_p.
+// At 1e-7 it is invisible in one pixel, but it has the sign of the MUFU lg2 bias on every surface pixel, and for an object
+// that fills the image and a prediction close to the target (loss ~ 3e-3) it is 2e-5 of the loss (measured); the loss
+// tolerance is rtol 1e-5.  Returns sum d_p S_p for one column (its owner adds sign * tau / n * this to the loss).
+SQ_HD float queue_depth_shift(const BwdQueue& q, int col, unsigned rmask, float U) {
+    float acc = 0.f;
+    for (unsigned m = rmask; m; m &= m - 1u) {
+        const int at = col + lowest_bit(m) * q.stride;
+        acc = fmaf(q.d[at], U - q.pre[at], acc);
+    }
+    return acc;
 }
 // 3. every entry: forward redone in fp32 for the ratios the backward needs (not amplified by k); weight o (1 - o) and
 // suffix weight from the queue.  sign = sign(depth - target) of the column.

@@ -178,11 +178,12 @@ struct Control {
 };
 static_assert(sizeof(Control) == 256, "Control block is 256 bytes");
 
+constexpr int kRow = 20;                 // floats per partial row: the kAccN sums, then the loss-centring pair (see implicit_kernel)
 struct Scratch {
     Control* ctl;
     SampleFull* pred;      // [batch]
     SampleFull* tru;       // [batch]
-    float* partials;       // [batch * rows_per_sample][kAccN]
+    float* partials;       // [batch * rows_per_sample][kRow]
     double* per_sample;    // [batch]
     double* tv_sum;        // [batch] sum |target| over the sample's pixels (ImplicitLoss)
     unsigned long long* counts;   // [batch][2] (IoU)
@@ -204,7 +205,7 @@ size_t scratch_layout(int batch, int n, char* base, Scratch* s) {
     size_t rows_ps = (size_t)L.rows_per_sample;
     const size_t lsq_rows = (size_t)(L.slots + kThreads - 1) / kThreads;
     if (lsq_rows > rows_ps) rows_ps = lsq_rows;
-    const size_t o_part = take(sizeof(float) * kAccN * rows_ps * (size_t)batch);
+    const size_t o_part = take(sizeof(float) * kRow * rows_ps * (size_t)batch);
     const size_t o_ps = take(sizeof(double) * (size_t)batch);
     const size_t o_tv = take(sizeof(double) * (size_t)batch);
     const size_t o_cnt = take(sizeof(unsigned long long) * 2 * (size_t)batch);
@@ -318,21 +319,34 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
         if (b == 0) { ctl->ticket = 0u; ctl->cursor = 0u; }
         if (counts) { counts[2 * b] = 0ull; counts[2 * b + 1] = 0ull; }
     }
-    if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < NS) {        // lane 0 of warp 0 (and of warp 1 for the second SQ)
-        const int w = threadIdx.x >> 5;
-        double p[12];
-        load_params(w == 0 ? params_a : params_b, dtype, b, p);
-        if (heads) {                                       // rows are raw network-head outputs (sq_implicit_loss_heads)
-            double raw[12], hp[8], hrn;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) raw[i] = p[i];
-            heads_forward(raw, p, hp, hrn);
-            prep_sample(p, clamp != 0, g, Ssh[w]);
-            Ssh[w].heads = 1; Ssh[w].hrn = hrn;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) Ssh[w].hp[i] = hp[i];
-        } else {
-            prep_sample(p, clamp != 0, g, Ssh[w]);
+    if ((threadIdx.x >> 5) < NS) {       // warp 0 (and warp 1 for the second SQ): the per-sample constants, fp64, spread over lanes
+        __shared__ double psh[NS][12];
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        double* p = psh[w];
+        const void* params = w == 0 ? params_a : params_b;
+        if (lane < 12)
+            p[lane] = dtype == SQ_F64 ? static_cast<const double*>(params)[12 * (size_t)b + lane]
+                                      : (double)static_cast<const float*>(params)[12 * (size_t)b + lane];
+        __syncwarp();
+        double hp_l = 0.0, hrn = 1.0;
+        if (heads) {     // rows are raw network-head outputs (sq_implicit_loss_heads): heads_forward(), one output per lane
+            double v = 0.0;
+            if (lane < 8) { hp_l = (double)(float)(1.0 / (1.0 + exp(-p[lane]))); v = hp_l; }
+            else if (lane < 12) {
+                hrn = 1.0 / sqrt(p[8] * p[8] + p[9] * p[9] + p[10] * p[10] + p[11] * p[11]);
+                v = (double)(float)(p[lane] * hrn);
+            }
+            __syncwarp();
+            if (lane < 12) p[lane] = v;
+            __syncwarp();
+        }
+        if (lane < 4) prep_part(p, clamp != 0, g, Ssh[w], lane);        // rows 0..2 of the scaled rotation; exponents
+        __syncwarp();
+        if (lane == 0) prep_finish(p, clamp != 0, g, Ssh[w]);
+        __syncwarp();
+        if (heads) {
+            if (lane < 8) Ssh[w].hp[lane] = hp_l;
+            if (lane == 8) { Ssh[w].heads = 1; Ssh[w].hrn = hrn; }
         }
         SQ_STAMP();
     }
@@ -343,24 +357,30 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (warp >= NS) {
             const int t = threadIdx.x - 32 * NS, T = kPlanThreads - 32 * NS, npix = g.n * g.n;
-            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+            double acc0 = 0.0, acc1 = 0.0;                    // fp64: an image of nearly equal depths rounds an fp32 sum one way
             const float* img = target + (size_t)b * tstride;
+            // pixel index -> (row, col): shift / mask when n is a power of two (the usual render sizes), else a division
+            const int sh = (g.n & (g.n - 1)) == 0 ? __ffs(g.n) - 1 : -1;
+            auto pixel = [&](int iu) {
+                const int r = sh >= 0 ? iu >> sh : iu / g.n, c = sh >= 0 ? iu & (g.n - 1) : iu - r * g.n;
+                return __ldg(img + row_off[r] + col_off[c]);
+            };
             int i = t;
             for (; i + 7 * T < npix; i += 8 * T) {         // eight independent loads in flight per thread (they miss to HBM)
                 float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const int iu = i + u * T; v[u] = __ldg(img + row_off[iu / g.n] + col_off[iu % g.n]); }
-                acc0 += fabsf(v[0]) + fabsf(v[4]); acc1 += fabsf(v[1]) + fabsf(v[5]);
-                acc2 += fabsf(v[2]) + fabsf(v[6]); acc3 += fabsf(v[3]) + fabsf(v[7]);
+                for (int u = 0; u < 8; ++u) v[u] = pixel(i + u * T);
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) { acc0 += (double)fabsf(v[u]); acc1 += (double)fabsf(v[u + 1]); }
             }
             {
                 float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const int iu = i + u * T; v[u] = iu < npix ? __ldg(img + row_off[iu / g.n] + col_off[iu % g.n]) : 0.f; }
-                acc0 += fabsf(v[0]) + fabsf(v[4]); acc1 += fabsf(v[1]) + fabsf(v[5]);
-                acc2 += fabsf(v[2]) + fabsf(v[6]); acc3 += fabsf(v[3]) + fabsf(v[7]);
+                for (int u = 0; u < 8; ++u) { const int iu = i + u * T; v[u] = iu < npix ? pixel(iu) : 0.f; }
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) { acc0 += (double)fabsf(v[u]); acc1 += (double)fabsf(v[u + 1]); }
             }
-            double d = (double)((acc0 + acc1) + (acc2 + acc3));
+            double d = acc0 + acc1;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
             if (lane == 0) tv_part[warp] = d;
@@ -447,14 +467,15 @@ __device__ __forceinline__ void array_to_acc(const float* v, Acc& a) {
 // per-thread Acc -> one row of kAccN floats per WARP, through the warp's own shared-memory tile: every lane writes
 // its 18 sums (5 vector stores), lane i < 18 adds up column i over the 32 lanes in a fixed order.  37 shared-memory
 // instructions and 32 adds per warp instead of the 90 shuffles + 90 adds of a butterfly per value.
-constexpr int kRedStride = 20;           // floats per lane in the tile (18 used; 80 bytes keeps float4 alignment)
+constexpr int kRedStride = 20;           // floats per lane in the tile (80 bytes keeps float4 alignment)
 constexpr int kRedFloats = 32 * kRedStride;
+static_assert(kRow == kRedStride, "a partial row is one reduced tile row");
 
-// lane i < 18 adds up column i of the warp's tile over the 32 lanes (fixed order) and stores the partial row
+// lane i < kRow adds up column i of the warp's tile over the 32 lanes (fixed order) and stores the partial row
 __device__ __forceinline__ void tile_reduce_store(const float* tile, float* row) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
-    if (lane < kAccN) {
+    if (lane < kRow) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int r = 0; r < 32; r += 4) {
@@ -482,7 +503,7 @@ __device__ __forceinline__ void tile_get(const float* tile, float* v /*[kRedStri
 __device__ __forceinline__ void warp_reduce_store(const Acc& a, float* tile, float* row, bool nonzero) {
     const int lane = threadIdx.x & 31;
     if (!__any_sync(0xffffffffu, nonzero)) {          // e.g. image-border patches: no object, no loss, no gradient
-        if (lane < kAccN) row[lane] = 0.f;
+        if (lane < kRow) row[lane] = 0.f;
         return;
     }
     float v[kRedStride];
@@ -503,11 +524,13 @@ __device__ __forceinline__ void block_reduce_store(const Acc& a, float (*red)[kA
         if (lane == 0) red[warp][i] = s;
     }
     __syncthreads();
-    if (threadIdx.x < kAccN) {
+    if (threadIdx.x < kRow) {
         float s = 0.f;
+        if (threadIdx.x < kAccN) {
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
-        row[threadIdx.x] = s;
+            for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+        }
+        row[threadIdx.x] = s;                          // slots 18, 19 (loss centring, ImplicitLoss only): 0
     }
 }
 
@@ -879,12 +902,16 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                                                    f2d(ci[2 * 32 + l_]) + f2d(ci[5 * 32 + l_]), tb);
                             }
                             __syncwarp();
+                            const float tau = P.tl * (float)kLn2;
+#ifdef SQ_DEPTH_SHIFT       // the refined occupancies' first-order effect on the rendered depth: measured below the loss's other
+                            // fp32 errors on every workload (profiles/tune_r02.txt) and 2 us per call -> off
+                            if (rmask) loss_sum = fmaf(wsg * tau * g.inv_n, queue_depth_shift(qlane, 0, rmask, U), loss_sum);
+#endif
 #ifndef SQ_EARLY_CLAIM
                             if (staged && wp.claim_finish()) pre.fetch(samples + L.sample_of(wp.next), lane);
 #endif
                             // 2. + 3. all entries, dealt out evenly: suffix weight (corrected for the refined entries of the
                             // entry's column), forward redone, backward; two rounds in flight (two independent MUFU chains)
-                            const float tau = P.tl * (float)kLn2;
                             auto dealt = [&](int j, Bwd& bq, float& cfq, float& dx_, float& dy_) {
                                 const bool has = j < total;
                                 const int m_ = has ? qmap_w[j] : 0, l_ = m_ >> 8, e_ = m_ & 255, at = e_ * 32 + l_;
@@ -943,16 +970,24 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 }
             }
             if (target) {
-                float* row = partials + ((size_t)b * L.rows_per_sample + chunk) * kAccN;
-                if (!__any_sync(0xffffffffu, loss_sum != 0.f || folded)) {
-                    if (lane < kAccN) row[lane] = 0.f;
+                float* row = partials + ((size_t)b * L.rows_per_sample + chunk) * kRow;
+                const unsigned nz = __ballot_sync(0xffffffffu, loss_sum != 0.f);
+                if (!nz && !__any_sync(0xffffffffu, folded)) {
+                    if (lane < kRow) row[lane] = 0.f;
                 } else {
                     if (!folded) {
                         float4* mine = reinterpret_cast<float4*>(tiles[warp] + lane * kRedStride);
 #pragma unroll
                         for (int q = 0; q < kRedStride / 4; ++q) mine[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    tiles[warp][lane * kRedStride + kAccN - 1] = loss_sum;
+                    // The lanes' loss terms |depth - t| - |t| are all close to -|t| when the object fills the patch, and
+                    // an fp32 sum of 32 nearly equal numbers rounds the same way 32 times (measured: +1e-7 on the loss of
+                    // every sample, 4e-5 of a loss of 3e-3).  So the row carries the terms relative to one of them
+                    // (slot 17: small numbers, summed exactly enough), that one (slot 18) and the count (slot 19);
+                    // finalize adds slot 17 + slot 18 x slot 19 in fp64.
+                    const float c = nz ? __shfl_sync(0xffffffffu, loss_sum, __ffs((int)nz) - 1) : 0.f;
+                    tiles[warp][lane * kRedStride + 17] = loss_sum != 0.f ? loss_sum - c : 0.f;
+                    if (lane == 0) { tiles[warp][18] = c; tiles[warp][19] = (float)__popc(nz); }
                     tile_reduce_store(tiles[warp], row);
                 }
             }
@@ -1026,7 +1061,7 @@ explicit_kernel(const SampleFull* __restrict__ tru, const SampleFull* __restrict
             }
             // claimed after the walk, not before it: see implicit_kernel
             if (wp.claim(lane)) { pre_t.fetch(tru + L.sample_of(wp.next), lane); pre_p.fetch(pred + L.sample_of(wp.next), lane); }
-            warp_reduce_store(acc, tiles[warp], partials + (size_t)item * kAccN, acc.loss != 0.f);
+            warp_reduce_store(acc, tiles[warp], partials + (size_t)item * kRow, acc.loss != 0.f);
             wp.rotate();
         }
     }
@@ -1129,7 +1164,7 @@ lsq_kernel(const SampleFull* __restrict__ samples, int R, int items_per_sample,
             acc.loss += lsq_point<BWD>(S, px, py, v[k], acc);
         }
     }
-    block_reduce_store(acc, red, partials + (size_t)item * kAccN);
+    block_reduce_store(acc, red, partials + (size_t)item * kRow);
 }
 
 // LeastSquares.energy_function on an explicit, compacted point list (classes.py:318-356): structure of arrays x[], y[],
@@ -1161,7 +1196,7 @@ lsq_points_kernel(const SampleFull* __restrict__ samples, int chunks_per_sample,
         for (int k = 0; k < 4; ++k)
             if (base + k >= lo && base + k < hi) acc.loss += lsq_point<BWD>(S, xs[k], ys[k], zs[k], acc);
     }
-    block_reduce_store(acc, red, partials + (size_t)item * kAccN);
+    block_reduce_store(acc, red, partials + (size_t)item * kRow);
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
@@ -1195,13 +1230,17 @@ finalize_kernel(const SampleFull* __restrict__ samples, Grid g, int batch, int i
         double s[kAccN];
 #pragma unroll
         for (int i = 0; i < kAccN; ++i) s[i] = 0.0;
-        const float* base = partials + (size_t)b * items_per_sample * kAccN;
+        const float* base = partials + (size_t)b * items_per_sample * kRow;
         for (int j = t; j < items_per_sample; j += kFinThreads) {
             // items the plan kernel proved empty were never processed: they have no row (and contribute nothing)
             if (item_class && item_class[(size_t)b * items_per_sample + j] == kClasses - 1) continue;
-            const float2* p = reinterpret_cast<const float2*>(base + (size_t)j * kAccN);     // rows are 72 bytes: 8-aligned
+            const float4* p = reinterpret_cast<const float4*>(base + (size_t)j * kRow);      // rows are 80 bytes: 16-aligned
+            float v[kRow];
 #pragma unroll
-            for (int i = 0; i < kAccN / 2; ++i) { const float2 v = __ldcg(p + i); s[2 * i] += (double)v.x; s[2 * i + 1] += (double)v.y; }
+            for (int i = 0; i < kRow / 4; ++i) { const float4 q = __ldcg(p + i); v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
+#pragma unroll
+            for (int i = 0; i < kAccN - 1; ++i) s[i] += (double)v[i];
+            s[17] += (double)v[17] + (double)v[18] * (double)v[19];      // loss: centred terms + constant x count (implicit_kernel)
         }
 #pragma unroll
         for (int i = 0; i < kAccN; ++i) {

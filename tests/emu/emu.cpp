@@ -67,6 +67,7 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
                     if (!g_emu_refine) rmask = 0u;
                     const double b0 = (double)bh[0] + (double)bl[0], b1 = (double)bh[1] + (double)bl[1], b2 = (double)bh[2] + (double)bl[2];
                     for (int e = 0; e < qn; ++e) if ((rmask >> e) & 1u) queue_refine_entry(S, g.step, P.kl, q, e, b0, b1, b2, default_tabs());
+                    a.loss += w * tau * g.inv_n * queue_depth_shift(q, 0, rmask, U);
                     for (int e = 0; e < qn; ++e) {
                         Bwd bq;
                         queue_entry_backward<true>(S, bh, bl, qcf[e], qx[e], queue_suffix_weight(q, 0, e, rmask, U, tau), w, true, bq);
