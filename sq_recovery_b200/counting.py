@@ -16,15 +16,18 @@ from .functional import nearest_offsets
 LIB_COUNT = os.path.join(_lib.HERE, "libsqloss_count.so")
 _h = None
 
-# MUFU-pipe (XU) warp instructions per counted event, read off csrc/sq_core.cuh / sqloss.cu:
+# MUFU-pipe (XU) warp instructions per counted event, read off csrc/sq_core.cuh / sqloss.cu (int <-> float and
+# fp64 <-> fp32 conversions share the pipe: profiles/peaks_r02.json D2F / I2F):
 #   plane step        3 lg2|s| + 2 (ex2 + lg2) + ex2 (F) + ex2, rcp (sigmoid) + ex2 (transmittance)              = 11
 #   on-the-spot bwd   5 rcp                                                                                      = 5
 #   deal-out round    point_forward 8 + point_backward 5 rcp                                                     = 13
-#   refinement round  ex2, rcp + 8 fp64<->fp32 conversions (they share the pipe: profiles/peaks_r01.json D2F)    = 10
-#   column group      sqrt (culling) + 11 conversions of the fp64 column base                                    = 12
-#   work item         sqrt per lane of groups that turn out empty                                                = 1
-XU_PER_EVENT = {"plane_steps": 11, "spot_backward_blocks": 5, "dealout_rounds": 13, "refine_rounds": 10,
-                "column_groups": 12, "items": 1}
+#   refinement round  ex2, rcp + 9 fp64<->fp32 conversions                                                       = 11
+#   column group      11 conversions of the fp64 column base + 2 int->double grid coordinates + 3 int->float     = 16
+#   work item         sqrt (culling) + 3 conversions of the range bounds + 2 int->float grid coordinates         = 6
+# Validated against ncu (sm__inst_executed_pipe_xu of the committed capture): the model is 6-10 % below the hardware
+# count (profiles/implicit_kernel_ncu_summary_r02.json), i.e. the reported fraction is slightly conservative.
+XU_PER_EVENT = {"plane_steps": 11, "spot_backward_blocks": 5, "dealout_rounds": 13, "refine_rounds": 11,
+                "column_groups": 16, "items": 6}
 NAMES = ("plane_steps", "spot_backward_blocks", "dealout_rounds", "refine_rounds", "items", "column_groups",
          "queued_points", "refined_points")
 

@@ -42,6 +42,9 @@ constexpr float kAbsFix = 1e-2f;          // |s| used when s == 0  (s^2 := 1e-4,
 #define SQ_KACTIVE 24.0f
 #endif
 constexpr float kActive = SQ_KACTIVE;     // |log2 of the sigmoid odds| beyond which o(1-o) < 2^-kActive is dropped
+// ExplicitLoss (k = 5) walks a wide soft shell: thousands of points per sample sit at 2^-24 .. 2^-32, and their sum shows
+// at 0.2x the gradient tolerance (measured) -- it keeps the wider cut
+constexpr float kActiveExplicit = 32.0f;
 
 // ---------------------------------------------------------------- MUFU primitives
 SQ_HD float ex2(float x) {
@@ -1154,7 +1157,7 @@ SQ_HD void explicit_step(const Sample& St, const Sample& Sp, float kl, float cf,
     const float d = ot - op;
     sq = fmaf(d, d, sq);
     if (BWD && HAS_P) {
-        const bool active = fabsf(xp) < kActive;
+        const bool active = fabsf(xp) < kActiveExplicit;
         if (SQ_ANY(active)) {
             // d/dF_p of (o_t - o_p)^2 = 2 d * k o_p (1 - o_p); constants 2, k applied in finalize
             const float W = active ? d * ep * op * op : 0.0f;

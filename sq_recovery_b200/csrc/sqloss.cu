@@ -685,7 +685,15 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
     __shared__ Sample Ssh[THREADS / 32];
-    __shared__ __align__(16) float tiles[THREADS / 32][kRedFloats];
+#if defined(SQ_TILE_ALIAS) && defined(SQ_BWD_COMPACT)
+    // experiment (5 blocks / SM): the fwd+bwd kernel's reduction tile lives in the warp's queue arrays, which are dead
+    // by the time the item's sums are put there (one column group per item only)
+    static_assert(!BWD || CPTMAX == 1, "SQ_TILE_ALIAS needs one column group per work item");
+    static_assert(4 * kBwdDepth * 32 >= kRedFloats, "queue arrays too small to hold the tile");
+    __shared__ __align__(16) float tiles_static[BWD ? 1 : THREADS / 32][kRedFloats];
+#else
+    __shared__ __align__(16) float tiles_static[THREADS / 32][kRedFloats];
+#endif
 #ifdef SQ_BWD_COMPACT       // per warp, in dynamic shared memory (BWD only; implicit_bwd_smem_bytes): the queued gradient-carrying
                             // points (BwdQueue arrays), per-column data for them, the deal-out list
     constexpr int kQN = kBwdDepth * 32;
@@ -693,6 +701,11 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
     float* const qbuf = reinterpret_cast<float*>(dyn_smem + (size_t)(threadIdx.x >> 5) * kImplicitBwdSmemPerWarp);      // [4][kQN]
     float* const colinfo_w = qbuf + 4 * kQN;                                                                         // [11][32]
     unsigned short* const qmap_w = reinterpret_cast<unsigned short*>(colinfo_w + 11 * 32);                            // [kQN]
+#endif
+#if defined(SQ_TILE_ALIAS) && defined(SQ_BWD_COMPACT)
+    float* const tile_w = BWD ? qbuf : tiles_static[threadIdx.x >> 5];
+#else
+    float* const tile_w = tiles_static[threadIdx.x >> 5];
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Sample& S = Ssh[warp];
@@ -856,7 +869,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     if (total > 0 || any_spill) {
                         Acc acc;
                         float v[kRedStride];
-                        if (folded) { tile_get(tiles[warp], v); array_to_acc(v, acc); } else acc_zero(acc);
+                        if (folded) { tile_get(tile_w, v); array_to_acc(v, acc); } else acc_zero(acc);
                         if (spilled && wsg != 0.f) implicit_fold(acc, cg, wsg, dxy[0], dxy[1]);      // handled on the spot
                         if (total > 0) {
                             float* ci = colinfo_w;
@@ -942,7 +955,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                         }
                         acc_to_array(acc, v);
                         v[18] = v[19] = 0.f;
-                        tile_put(tiles[warp], v);
+                        tile_put(tile_w, v);
                         folded = true;
                     }
                 } else
@@ -959,11 +972,11 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                         if (BWD && diff != 0.f) {
                             float v[kRedStride];
                             Acc acc;
-                            if (folded) { tile_get(tiles[warp], v); array_to_acc(v, acc); } else acc_zero(acc);
+                            if (folded) { tile_get(tile_w, v); array_to_acc(v, acc); } else acc_zero(acc);
                             implicit_fold(acc, cg, diff > 0.f ? 1.f : -1.f, dxy[0], dxy[1]);
                             acc_to_array(acc, v);
                             v[18] = v[19] = 0.f;
-                            tile_put(tiles[warp], v);
+                            tile_put(tile_w, v);
                             folded = true;
                         }
                     }
@@ -976,7 +989,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     if (lane < kRow) row[lane] = 0.f;
                 } else {
                     if (!folded) {
-                        float4* mine = reinterpret_cast<float4*>(tiles[warp] + lane * kRedStride);
+                        float4* mine = reinterpret_cast<float4*>(tile_w + lane * kRedStride);
 #pragma unroll
                         for (int q = 0; q < kRedStride / 4; ++q) mine[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
@@ -986,9 +999,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     // (slot 17: small numbers, summed exactly enough), that one (slot 18) and the count (slot 19);
                     // finalize adds slot 17 + slot 18 x slot 19 in fp64.
                     const float c = nz ? __shfl_sync(0xffffffffu, loss_sum, __ffs((int)nz) - 1) : 0.f;
-                    tiles[warp][lane * kRedStride + 17] = loss_sum != 0.f ? loss_sum - c : 0.f;
-                    if (lane == 0) { tiles[warp][18] = c; tiles[warp][19] = (float)__popc(nz); }
-                    tile_reduce_store(tiles[warp], row);
+                    tile_w[lane * kRedStride + 17] = loss_sum != 0.f ? loss_sum - c : 0.f;
+                    if (lane == 0) { tile_w[18] = c; tile_w[19] = (float)__popc(nz); }
+                    tile_reduce_store(tile_w, row);
                 }
             }
             wp.rotate();
@@ -1329,6 +1342,33 @@ gather_targets_kernel(const PIX* __restrict__ host_images, long long stride_b, c
         const int row = (int)(t % R);
         const size_t b = t / R;
         out[i] = (float)host_images[b * (size_t)stride_b + row_off[row] + col_off[col]] * scale;
+    }
+}
+
+// The same for the regular case (source width a multiple of the render size, rows 16-byte aligned): every thread pulls 16
+// contiguous bytes of a sampled row -- a warp 512 contiguous bytes -- so the reads arrive at the host as a few large PCIe
+// requests instead of many sector-sized ones (what limits eight GPUs reading from one host), and picks the sampled
+// pixels (every sx-th) out of them.
+template <typename PIX>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const PIX* __restrict__ host_images, long long stride_b, const int* __restrict__ row_off, int R, int W,
+                   int sx, int batch, float scale, float* __restrict__ out) {
+    constexpr int PER = 16 / (int)sizeof(PIX);              // pixels per 16-byte load
+    const int segs = W / PER;
+    const size_t total = (size_t)batch * R * segs;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int seg = (int)(i % segs);
+        const size_t t = i / segs;
+        const int row = (int)(t % R);
+        const size_t b = t / R;
+        const int c0 = seg * PER, first = (c0 + sx - 1) / sx * sx;      // first sampled source column at or after c0
+        if (first >= c0 + PER) continue;                                 // no sampled pixel in this segment
+        const uint4 v = *reinterpret_cast<const uint4*>(host_images + b * (size_t)stride_b + row_off[row] + c0);
+        const PIX* px = reinterpret_cast<const PIX*>(&v);
+        float* dst = out + (b * R + row) * (size_t)R;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+            if (c0 + k >= first && (c0 + k - first) % sx == 0) dst[(c0 + k) / sx] = (float)px[k] * scale;
     }
 }
 
@@ -1808,7 +1848,16 @@ int sq_implicit_loss_host_submit(sq_ctx* ctx, int slot, const float* pred_host, 
         src = d_raw;
     }
     const long long stride_b = (long long)height * width;
-    if (image_dtype == SQ_U8)
+    // regular sampling (F.interpolate's nearest rule picks column j * width / R when R divides the width) on 16-byte
+    // aligned rows: whole-row reads with 16-byte loads; otherwise pixel by pixel through the offset tables
+    const bool rows16 = width % R == 0 && ((size_t)width * px) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) % 16) == 0;
+    if (rows16 && image_dtype == SQ_U8)
+        gather_rows_kernel<unsigned char><<<1184, 256, 0, c->stream>>>(static_cast<const unsigned char*>(src), stride_b, d_off, R, width,
+                                                                      width / R, batch, image_scale, d_img);
+    else if (rows16)
+        gather_rows_kernel<float><<<1184, 256, 0, c->stream>>>(static_cast<const float*>(src), stride_b, d_off, R, width, width / R, batch,
+                                                              image_scale, d_img);
+    else if (image_dtype == SQ_U8)
         gather_targets_kernel<unsigned char><<<1184, 256, 0, c->stream>>>(static_cast<const unsigned char*>(src), stride_b, d_off, d_off + R,
                                                                          R, batch, image_scale, d_img);
     else

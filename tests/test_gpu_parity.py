@@ -780,3 +780,25 @@ def test_train_harness(dev, S, tmp_path):
     g2 = net.trunk.fc[2].weight.grad
     assert abs(l1.item() - l2.item()) <= 1e-5 * abs(l1.item())
     assert (g1 - g2).norm().item() <= 2e-2 * g1.norm().item()           # fp32 heads vs fp64-in-kernel heads at k = 260
+
+
+def test_objects_that_fill_the_grid(dev, S):
+    """bench.py's `dense` workload: sizes a ~ U(0.5, 1) -- every pixel is covered, columns graze faces for more planes than a
+    lane's backward queue holds, and with a prediction close to the target the loss (~3e-3) is a small difference of depths
+    near 1.  Round 2 found the loss 2e-5 off here (an fp32 sum of 32 nearly equal per-column terms rounds one way); the
+    partial rows now carry the terms relative to one of them."""
+    from sq_recovery_b200 import inputs
+    B, R = 4, 64
+    for seed in (302, 304):
+        true = inputs.random_params(B, seed, size_range=inputs.DENSE_SIZE_RANGE)
+        for pred in (inputs.random_params(B, seed + 1000, size_range=inputs.DENSE_SIZE_RANGE), inputs.perturbed_params(true, seed)):
+            with torch.no_grad():
+                img = O.ImplicitLoss(2 * R, "cpu", 1.5, 260).depth_projection(true).float().unsqueeze(1)
+            oc = O.ImplicitLoss(R, "cpu", 1.5, 260)
+            p = pred.clone().requires_grad_(True)
+            ref = oc(img, p); ref.backward()
+            l, gr = run(S.ImplicitLoss(R, dev, 1.5, 260), img, pred, dev)
+            check(l, gr, ref.item(), p.grad.double().numpy(), what=f"dense seed {seed}", keep=unambiguous(oc, img, pred))
+            with torch.no_grad():                                       # the forward-only kernel shares the bookkeeping
+                lf = S.ImplicitLoss(R, dev, 1.5, 260)(img.to(dev), pred.to(dev)).item()
+            assert abs(lf - ref.item()) <= LOSS_RTOL * abs(ref.item())
