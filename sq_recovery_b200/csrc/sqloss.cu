@@ -163,6 +163,7 @@ constexpr int kClasses = 8;
 #define SQ_PLAN_THREADS 512
 #endif
 constexpr int kPlanThreads = SQ_PLAN_THREADS;
+constexpr int kPlanThreadsSmall = 128;   // batches beyond one wave of kPlanThreads blocks (4 per SM)
 constexpr int kPlanMaxItems = 8192;      // items per sample the plan kernel can classify (more: index order)
 
 // First 256 bytes of every scratch buffer.  qcount and retired must be ZERO when a call starts: sq_scratch_init()
@@ -296,8 +297,10 @@ __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, flo
 
 // plan (column kernels): one block per sample.  Builds the Sample record(s) like prep, then estimates the cost of each
 // of the sample's work items and appends the item to the queue of its cost class.  NS = SQs per item (2: true + pred).
-template <int NS>
-__global__ void __launch_bounds__(kPlanThreads)
+// THREADS: kPlanThreads while the batch fits one wave of such blocks (shortest latency per sample: many threads per
+// pixel sum); kPlanThreadsSmall beyond (more samples resident per SM: the kernel is then a throughput problem).
+template <int NS, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, int heads, Grid g, Layout L, float bound,
             SampleFull* out_a, SampleFull* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap,
             unsigned char* item_class, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
@@ -305,7 +308,7 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
     __shared__ SampleFull Ssh[NS];
     __shared__ unsigned char cls[kPlanMaxItems];
     __shared__ unsigned int ccnt[kClasses], cbase[kClasses];
-    __shared__ double tv_part[kPlanThreads / 32];
+    __shared__ double tv_part[THREADS / 32];
     const int b = blockIdx.x;
 #ifdef SQ_TIMELINE
     unsigned long long ts[6]; int nts = 0;
@@ -356,7 +359,7 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
     if (tv_sum) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (warp >= NS) {
-            const int t = threadIdx.x - 32 * NS, T = kPlanThreads - 32 * NS, npix = g.n * g.n;
+            const int t = threadIdx.x - 32 * NS, T = THREADS - 32 * NS, npix = g.n * g.n;
             double acc0 = 0.0, acc1 = 0.0;                    // fp64: an image of nearly equal depths rounds an fp32 sum one way
             const float* img = target + (size_t)b * tstride;
             // pixel index -> (row, col): shift / mask when n is a power of two (the usual render sizes), else a division
@@ -391,17 +394,17 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
     SQ_STAMP();
     if (tv_sum && threadIdx.x == 0) {
         double d = 0.0;
-        for (int w = NS; w < kPlanThreads / 32; ++w) d += tv_part[w];
+        for (int w = NS; w < THREADS / 32; ++w) d += tv_part[w];
         tv_sum[b] = d;
     }
-    for (int w = threadIdx.x; w < NS * kFullWords; w += kPlanThreads) {
+    for (int w = threadIdx.x; w < NS * kFullWords; w += THREADS) {
         const int which = w / kFullWords, i = w - which * kFullWords;
         reinterpret_cast<uint32_t*>((which == 0 ? out_a : out_b) + b)[i] = reinterpret_cast<const uint32_t*>(&Ssh[which])[i];
     }
     if (!queue) return;
     const int J = L.rows_per_sample;
     const int max_cost = L.cpt * L.n * NS;
-    for (int j = threadIdx.x; j < J; j += kPlanThreads) {
+    for (int j = threadIdx.x; j < J; j += THREADS) {
         int cost = 0;
         for (int k = 0; k < L.cpt; ++k) {
             const int group = j + k * J;
@@ -423,7 +426,7 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
         ccnt[threadIdx.x] = 0u;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < J; j += kPlanThreads) {
+    for (int j = threadIdx.x; j < J; j += THREADS) {
         const int c = cls[j];
         const unsigned int r = atomicAdd(&ccnt[c], 1u);
 #ifdef SQ_DEBUG_BOUNDS
@@ -1407,8 +1410,7 @@ cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, size
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// blocks of a persistent column kernel: enough to fill every SM at the kernel's occupancy, no more than the work
-int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
+int device_sm_count() {
     static int sms[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1418,8 +1420,13 @@ int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
         sms[dev] = n;
     }
+    return sms[dev];
+}
+
+// blocks of a persistent column kernel: enough to fill every SM at the kernel's occupancy, no more than the work
+int persistent_blocks(int items, int warps_per_block, int min_blocks_per_sm) {
     const int need = (items + warps_per_block - 1) / warps_per_block;
-    const int fill = sms[dev] * min_blocks_per_sm;
+    const int fill = device_sm_count() * min_blocks_per_sm;
     return need < fill ? need : fill;
 }
 
@@ -1438,16 +1445,20 @@ int launch_plan(const void* params_a, const void* params_b, int dtype, int batch
                 const PlanTarget* pt, cudaStream_t st, bool heads = false) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
     int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
-    if (params_b)
-        plan_kernel<2><<<batch, kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, 0, g, L, bound, s.tru, s.pred,
-                                                       s.ctl, counts, queue, s.queue_cap, queue ? item_class : nullptr, nullptr, 0, nullptr, nullptr,
-                                                       nullptr);
-    else
-        plan_kernel<1><<<batch, kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, heads ? 1 : 0, g, L, bound, s.pred, nullptr,
-                                                       s.ctl, counts, queue, s.queue_cap, queue ? item_class : nullptr,
-                                                       pt ? pt->target : nullptr, pt ? pt->tstride : 0,
-                                                       pt ? pt->row_off : nullptr, pt ? pt->col_off : nullptr,
-                                                       pt ? s.tv_sum : nullptr);
+    const PlanTarget none{nullptr, 0, nullptr, nullptr};
+    const PlanTarget& t = pt ? *pt : none;
+    const bool small = batch > 4 * device_sm_count();      // more samples than one wave of the large blocks
+    if (params_b) {
+        auto k = small ? plan_kernel<2, kPlanThreadsSmall> : plan_kernel<2, kPlanThreads>;
+        k<<<batch, small ? kPlanThreadsSmall : kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, 0, g, L, bound, s.tru, s.pred,
+                                                                      s.ctl, counts, queue, s.queue_cap, queue ? item_class : nullptr,
+                                                                      nullptr, 0, nullptr, nullptr, nullptr);
+    } else {
+        auto k = small ? plan_kernel<1, kPlanThreadsSmall> : plan_kernel<1, kPlanThreads>;
+        k<<<batch, small ? kPlanThreadsSmall : kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, heads ? 1 : 0, g, L, bound, s.pred,
+                                                                      nullptr, s.ctl, counts, queue, s.queue_cap, queue ? item_class : nullptr,
+                                                                      t.target, t.tstride, t.row_off, t.col_off, pt ? s.tv_sum : nullptr);
+    }
     return (int)cudaGetLastError();
 }
 
