@@ -8,10 +8,16 @@ One "step" = one pass of the hot path over one batch: ``ImplicitLoss(64, dev, 1.
 (N > 1) every rank runs its own batch (the path shards by sample, no data-path collective: weak scaling) and the
 step time is the max over ranks.
 
-Printed line (rank 0), see the driver contract: ``value`` = Gpoints/s with inputs resident in HBM (CUDA events over
-the K steps); ``e2e`` = the same through the host-buffer C-ABI call with H2D/D2H inside the timed region;
-``roofline`` = the dominant kernel against the measured MUFU (SFU) peak of this GPU; ``cpu_baseline`` = the oracle
-port on the box's host cores on a bounded sample.  ``--impl reference`` times that CPU path alone.
+Printed line (rank 0), see the driver contract:
+  ``value``        Gpoints/s with inputs resident in HBM (CUDA events over exactly K graph-replayed steps)
+  ``dense``        the same call on a second workload, sizes a ~ U(0.5, 1): objects fill the grid, culling cannot help
+  ``e2e``          host buffers in, host results out, copies inside the timed region: 8-bit depth maps and fp32 parameters in
+                   pinned memory through sq_implicit_loss_host_submit / _wait, two batches in flight; H2D bytes counted and
+                   measured (NVML PCIe receive counter); round 1's blocking fp32-image call next to it
+  ``roofline``     the dominant kernel against the measured MUFU (SFU) peak of this GPU: issued MUFU-pipe ops from the counting
+                   build of the same sources, ``walked_fraction``, ``evaluated_gpoints_per_s``; DRAM traffic from the ncu capture
+  ``cpu_baseline`` the UNMODIFIED reference (staged under oracle/_ref) on the box's host cores on a bounded sample
+``--impl reference`` times that CPU path alone (same ``config``; ``--steps`` / ``--warmup`` honoured).
 """
 from __future__ import annotations
 
