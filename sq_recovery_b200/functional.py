@@ -17,6 +17,7 @@ from torch.autograd.function import once_differentiable
 from . import _lib
 
 _scratch: Dict[Tuple[int, int], torch.Tensor] = {}
+_retired: list = []          # outgrown workspaces, kept alive (see _get_scratch)
 _offsets: Dict[Tuple[int, int, int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
 
 
@@ -67,6 +68,8 @@ def _get_scratch(device: torch.device, batch: int, n: int, need: Optional[int] =
                 "the stream is being captured into a CUDA graph.  Run the same call once eagerly on the capture stream "
                 "first -- `s = torch.cuda.Stream(); with torch.cuda.stream(s): loss_fn(true, pred)` -- and capture with "
                 "`torch.cuda.graph(g, stream=s)`, or call sq_recovery_b200.functional.prepare_stream(device, batch, n, s).")
+        if buf is not None:
+            _retired.append(buf)             # a CUDA graph captured earlier may still hold pointers into the smaller buffer
         buf = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
         with torch.cuda.device(device):      # zero the control block once; every call leaves it zero (include/sqloss.h)
             _lib.check(_lib.lib().sq_scratch_init(ctypes.c_void_p(buf.data_ptr()), buf.numel(), _stream(device)),
