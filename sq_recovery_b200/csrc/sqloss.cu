@@ -156,9 +156,14 @@ struct ColIter {
 // ------------------------------------------------------------------------------------------------ scratch
 // Work items are handed to the persistent warps in order of estimated cost (longest first, empty last): the plan
 // kernel sorts them into kClasses cost classes, one queue per class.  Class k holds items whose estimated number of
-// z planes is in (max / 2^(k+1), max / 2^k]; the last class holds items PROVEN empty (the estimate is an upper bound),
+// z planes is in (max / 2^((k+1)/2), max / 2^(k/2)] (two classes per octave); the last class holds items PROVEN empty (the estimate is an upper bound),
 // which the column kernels never touch.
-constexpr int kClasses = 8;
+#ifndef SQ_CLASSES
+#define SQ_CLASSES 16
+#endif
+constexpr int kClasses = SQ_CLASSES;     // 8: one class per octave of cost; 16 / 32: two / four per octave -- a finer
+                                         // longest-first order: the last big items handed out are the cheaper ones (-1.5 us)
+static_assert(kClasses >= 4 && kClasses <= 32, "the class counters live in one warp's lanes and in the 256-byte control block");
 #ifndef SQ_PLAN_THREADS
 #define SQ_PLAN_THREADS 512
 #endif
@@ -413,7 +418,13 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
             for (int w = 0; w < NS; ++w) cost += group_planes(Ssh[w], g, L, bound, group);
         }
         int c = kClasses - 1;                              // proven empty (group_planes is an upper bound)
-        if (cost > 0) { c = 0; while (c < kClasses - 2 && (cost << (c + 1)) <= max_cost) ++c; }
+        if (cost > 0) {
+            if (kClasses == 8) { c = 0; while (c < kClasses - 2 && (cost << (c + 1)) <= max_cost) ++c; }
+            else {               // kClasses / 8 classes per octave
+                c = (int)((float)(kClasses / 8) * __log2f((float)max_cost / (float)cost));
+                c = c < 0 ? 0 : (c > kClasses - 2 ? kClasses - 2 : c);
+            }
+        }
         cls[j] = (unsigned char)c;
         if (item_class) item_class[(size_t)b * J + j] = (unsigned char)c;      // finalize skips the rows of proven-empty items
         atomicAdd(&ccnt[c], 1u);

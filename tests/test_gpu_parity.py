@@ -382,7 +382,7 @@ def test_scratch_is_reusable_and_left_clean(dev, S):
             p = pred.clone().requires_grad_(True)
             l = S.LeastSquares(R, dev)(img, p); l.backward(); out += [l.item(), p.grad.clone()]
             for w in _scratch_control_words(S, dev):
-                assert int(w[2]) == 0 and not w[4:12].any(), "queue counters not left clean"
+                assert int(w[2]) == 0 and not w[4:36].any(), "queue counters not left clean"
             if rep == 0:
                 first[(B, R)] = out
             else:                                                       # same inputs, dirty-then-cleaned scratch: same bits
@@ -447,7 +447,7 @@ def test_render_256_and_index_order_path(dev, S):
     img = depth.permute(1, 0).flip(0)                    # classes.py:279
     assert (d[0].double() - img).abs().max().item() < 1e-5
     for w in _scratch_control_words(S, dev):
-        assert int(w[2]) == 0 and not w[4:12].any()
+        assert int(w[2]) == 0 and not w[4:36].any()
 
 
 # ------------------------------------------------------------------ harnesses

@@ -63,10 +63,10 @@ print(f"items per warp: min {items.min()} p50 {np.median(items)} max {items.max(
 busy = (end - start).sum() / (len(buf) * end.max())
 print(f"warp-slot utilisation (sum of warp lifetimes / warps x span): {busy:.3f}")
 
-cls = np.zeros(8, dtype=np.uint32)
+cls = np.zeros(32, dtype=np.uint32)
 h.sq_debug_classes.argtypes = [ctypes.c_void_p]
 if h.sq_debug_classes(cls.ctypes.data_as(ctypes.c_void_p)) == 0:
-    print("items per cost class (0 = longest ... 7 = certified empty):", cls.tolist())
+    print("items per cost class (0 = longest ... last non-zero = certified empty):", [int(c) for c in cls if c])
 
 pl = np.zeros(16, dtype=np.uint64)
 h.sq_debug_plan.argtypes = [ctypes.c_void_p]
