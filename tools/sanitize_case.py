@@ -33,10 +33,24 @@ for B, R in ((3, 8), (5, 24), (2, 33), (7, 16), (300, 64), (1, 128)):
     S.IoUAccuracy(R, dev).ins_outs(pred)
     with torch.no_grad():
         S.ImplicitLoss(R, dev)(img, pred)
+# LeastSquares.energy_function on ragged explicit point lists (one empty, one of a single point, one long)
+pts = [torch.rand(3, m, device=dev) for m in (0, 1, 5000, 37)]
+pe = O.random_params(4, 6).to(dev).requires_grad_(True)
+S.LeastSquares(64, dev).energy_function(pts, pe).sum().backward()
+# objects that fill the grid: long queues, on-the-spot backward, many refinement rounds
+big = O.random_params(6, 7, size_range=O.DENSE_SIZE_RANGE).to(dev)
+img = S.ImplicitLoss(64, dev, 1.5, 260).depth_projection(big).unsqueeze(1)
+p = O.perturbed_params(big.cpu(), 8).to(dev).requires_grad_(True)
+S.ImplicitLoss(48, dev, 1.5, 260)(img, p).backward()
 ctx = HostContext(0)
 hi = torch.rand(4, 1, 40, 56).pin_memory()
 ctx.implicit_loss(O.random_params(4, 3).numpy(), hi.numpy(), 16, 1.5, 260.0)
 ctx.implicit_loss(O.random_params(4, 3).numpy(), torch.rand(4, 1, 40, 56).numpy(), 16, 1.5, 260.0)   # pageable
+import numpy as np                                    # two calls in flight: 8-bit pinned (row-wise gather) + 8-bit pageable, ragged width
+u8 = (torch.rand(4, 1, 64, 64) * 255).to(torch.uint8).pin_memory()
+ctx.submit_implicit(0, O.random_params(4, 3).numpy(), u8.numpy(), 16, 1.5, 260.0)
+ctx.submit_implicit(1, O.random_params(4, 5).numpy(), np.ascontiguousarray((np.random.rand(4, 1, 40, 56) * 255).astype(np.uint8)), 16, 1.5, 260.0)
+ctx.result(1); ctx.result(0)
 ctx.explicit_loss(O.random_params(4, 3).numpy(), O.random_params(4, 4).numpy(), 12)
 ctx.iou_counts(O.random_params(4, 3).numpy(), O.random_params(4, 4).numpy(), 12)
 ctx.close()
