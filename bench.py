@@ -219,7 +219,7 @@ class Workload:
     """Four independent input batches of one parameter distribution, the step on them (public class call + backward), its
     CUDA-graph captures, and the timing / counting of it."""
 
-    def __init__(self, name, size_range, S, O, dev, rank, side):
+    def __init__(self, name, size_range, S, O, dev, rank, side, side2):
         self.name, self.dev, self.S = name, dev, S
         self.crit = S.ImplicitLoss(R, dev, TAU, SHARP)
         render = S.ImplicitLoss(H, dev, TAU, SHARP)            # synthetic depth maps = soft renders of the true params
@@ -230,8 +230,8 @@ class Workload:
             img = render.depth_projection(true.to(dev)).unsqueeze(1).contiguous()
             self.sets.append((img, pred))
         torch.cuda.synchronize()
-        self.graphs, self.quad, self.quad_out = [], None, []
-        self.side = side
+        self.graphs, self.quad, self.quad_out, self.quad_seq = [], None, [], None
+        self.side, self.side2 = side, side2
 
     def eager_step(self, i):
         img, pred = self.sets[i % 4]
@@ -243,16 +243,21 @@ class Workload:
     def capture(self):
         """The same step captured once per input set (public API inside the capture: the class call and .backward());
         replaying it removes the ~100 us of Python/autograd launch overhead per step, which is longer than the kernels.
-        And the four steps back to back in ONE graph: a single launch then covers ~0.2 ms of GPU work, so the host's
-        launch rate cannot leave the GPU idle between steps.  Same kernels, same work per step.  Warm-up and capture run
-        on one side stream: the per-stream workspace must exist before a capture starts."""
-        dev, side = self.dev, self.side
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for k in range(4):
-                for _ in range(2):
-                    self.eager_step(k)
-        torch.cuda.current_stream(dev).wait_stream(side)
+        And the four steps (one per input set) in ONE graph: a single launch then covers ~0.2 ms of GPU work, so the host's
+        launch rate cannot leave the GPU idle between steps.  Same kernels, same work per step, same results (asserted).
+        Two versions of that graph: `quad_seq` runs the four steps one after the other; `quad` (what `value` times) puts
+        them alternately on two streams, i.e. TWO INDEPENDENT BATCHES IN FLIGHT: the plan / finalize kernels and the
+        end-game of one batch's persistent kernel (its last warps finishing) run under the other batch's kernel -- the
+        device-side counterpart of the two slots of the host-buffer API.  Warm-up and capture run on the side streams: the
+        per-stream workspace must exist before a capture starts."""
+        dev, side, side2 = self.dev, self.side, self.side2
+        for s_ in (side, side2):
+            s_.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s_):
+                for k in range(4):
+                    for _ in range(2):
+                        self.eager_step(k)
+            torch.cuda.current_stream(dev).wait_stream(s_)
         torch.cuda.synchronize()
         for k in range(4):
             gph = torch.cuda.CUDAGraph()
@@ -262,14 +267,29 @@ class Workload:
                 loss_k = self.crit(img, p)
                 loss_k.backward()
             self.graphs.append((gph, loss_k, p))
-        self.quad = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.quad, stream=side):
+        self.quad_seq, seq_out = torch.cuda.CUDAGraph(), []
+        with torch.cuda.graph(self.quad_seq, stream=side):
             for k in range(4):
                 img, pred = self.sets[k]
                 p = pred.detach().requires_grad_(True)
                 loss_k = self.crit(img, p)
                 loss_k.backward()
-                self.quad_out.append((loss_k, p))
+                seq_out.append((loss_k, p))
+        self.quad = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.quad, stream=side):
+            side2.wait_stream(side)
+            for k in range(4):
+                with torch.cuda.stream(side if k % 2 == 0 else side2):
+                    img, pred = self.sets[k]
+                    p = pred.detach().requires_grad_(True)
+                    loss_k = self.crit(img, p)
+                    loss_k.backward()
+                    self.quad_out.append((loss_k, p))
+            side.wait_stream(side2)
+        self.quad_seq.replay(); self.quad.replay()
+        torch.cuda.synchronize()
+        for (l0, p0), (l1, p1) in zip(seq_out, self.quad_out):      # two in flight or one after the other: the same bits
+            assert l0.item() == l1.item() and torch.equal(p0.grad, p1.grad)
 
     def step(self, i):
         if not self.graphs:
@@ -278,11 +298,11 @@ class Workload:
         gph.replay()
         return loss_k, p.grad
 
-    def run(self, steps):
+    def run(self, steps, sequential=False):
         """`steps` steps enqueued back to back (four per graph launch when captured); returns the last (loss, grad)."""
         if self.graphs:
             for _ in range(steps // 4):
-                self.quad.replay()
+                (self.quad_seq if sequential else self.quad).replay()
             out = (self.quad_out[3][0], self.quad_out[3][1].grad)
             for i in range(steps - steps % 4, steps):
                 out = self.step(i)
@@ -345,9 +365,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     steps, warmup = args.steps, max(args.warmup, 3)
-    side = torch.cuda.Stream(dev)
-    main = Workload("config2", O.SIZE_RANGE, S, O, dev, rank, side)
-    dense = Workload("dense", O.DENSE_SIZE_RANGE, S, O, dev, rank, side)
+    side, side2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    main = Workload("config2", O.SIZE_RANGE, S, O, dev, rank, side, side2)
+    dense = Workload("dense", O.DENSE_SIZE_RANGE, S, O, dev, rank, side, side2)
     if not args.eager:
         main.capture()
         dense.capture()
@@ -379,6 +399,14 @@ def run_gpu(args):
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     assert torch.isfinite(loss).item() and torch.isfinite(grad).all().item()
+    # the same K steps one batch at a time (no overlap between consecutive steps)
+    main.run(8, sequential=True)
+    barrier()
+    ev0.record()
+    main.run(steps, sequential=True)
+    ev1.record()
+    barrier()
+    seq_ms = ev0.elapsed_time(ev1)
     # the second workload: objects that fill the grid (a ~ U(0.5, 1)), where culling cannot help
     dsteps = max(4, min(steps, 80))
     dense.run(8)
@@ -398,10 +426,10 @@ def run_gpu(args):
             main.eager_step(i)
         ev1.record(); torch.cuda.synchronize()
         eager_ms = ev0.elapsed_time(ev1) / min(steps, 20)
-    t = torch.tensor([ms, dms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, dms, seq_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, dms = t[0].item(), t[1].item()
+    ms, dms, seq_ms = t[0].item(), t[1].item(), t[2].item()
 
     # ---- e2e: host buffers -> C-ABI host calls -> host results, copies inside the timed region.  Headline: 8-bit depth
     # images (what the reference's data are, torch/test.py:29-30) in pinned memory, two calls in flight on the context's
@@ -495,7 +523,10 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-            "launch": "CUDA graph replay, four steps (one per input set) per graph launch" if main.graphs else "eager",
+            "launch": ("CUDA graph replay, four steps (one per input set) per graph launch, TWO independent batches in flight "
+                       "(the steps alternate between two streams inside the graph)") if main.graphs else "eager",
+            "one_batch_at_a_time": {"value": world * pts * steps / (seq_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": seq_ms / steps,
+                                    "note": "the same K steps with consecutive steps serialised on one stream (round 1's protocol)"},
             "eager_ms_per_step": eager_ms,
             "walked_fraction": roof["walked_fraction"], "evaluated_gpoints_per_s": roof["evaluated_gpoints_per_s"],
             "clocks": clocks,
