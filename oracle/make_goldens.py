@@ -153,6 +153,39 @@ def edge_cases(rc):
           "n(R=24) =", int(out["explicit24_n"]))
 
 
+def zero_plane_cases(rc):
+    """Axis-aligned rotations with the position exactly on a grid plane ALONG Z (the walk direction of the kernels): the
+    reference's `s^2 == 0 -> 1e-4` fix-up (classes.py:171-173, 261-263) then fires on a whole plane.  Found by
+    tests/tools/parity_fuzz_other.py (q = identity, t_z clamped to 1 = the last coordinate of every grid)."""
+    R = 16
+    base = random_params(6, 31, torch.float64)
+    p = base.clone()
+    ident = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64)
+    p[0, 8:12] = ident; p[0, 5:8] = torch.tensor([0.41, 0.47, 1.4])             # t_z clamped to 1.0
+    p[0, 3:5] = torch.tensor([0.97, 0.5])                                        # e1 near 1: the zero plane's C = 1e-4^(1/e1) counts
+    p[1, 8:12] = ident; p[1, 5:8] = torch.tensor([0.5, 0.52, 9 / 15])            # on a linspace(0,1,16) plane
+    p[2, 8:12] = ident; p[2, 5:8] = torch.tensor([0.52, 0.5, 0.5])               # on an arange(0,1+1/16,1/16) plane
+    # half turns: M = diag(1,-1,-1), diag(-1,1,-1) -- every row has ONE non-zero entry, so the zeros do not depend on the
+    # summation order of the reference's einsum.  (Quarter turns need sqrt(1/2): their rows keep an entry of ~1e-16 and
+    # the reference's zeros then are rounding noise of its matmul -- not reproducible, see DESIGN.md section 4.)
+    p[3, 8:12] = torch.tensor([1.0, 0.0, 0.0, 0.0], dtype=torch.float64)
+    p[3, 5:8] = torch.tensor([0.45, 0.55, 1.0])
+    p[4, 8:12] = torch.tensor([0.0, 1.0, 0.0, 0.0], dtype=torch.float64)
+    p[4, 5:8] = torch.tensor([0.5, 0.5, 0.5]); p[4, 3:5] = torch.tensor([1.0, 1.0])
+    p[5, 8:12] = ident * 1.5; p[5, 5:8] = torch.tensor([0.48, 0.5, 1.0])         # non-unit but axis-aligned
+    true = random_params(6, 32, torch.float64)
+    img = synthetic_depth(rc, true.float(), 64, 0).double()
+    out = {"pred": p.numpy(), "true": true.numpy(), "img": img.numpy(), "R": np.array(R)}
+    out["implicit_loss"], out["implicit_grad"] = _grad(rc.ImplicitLoss(R, CPU, 1.5, 260), img.float(), p)
+    out["implicit_soft_loss"], out["implicit_soft_grad"] = _grad(rc.ImplicitLoss(R, CPU, 1.0, 20), img.float(), p)
+    out["explicit_loss"], out["explicit_grad"] = _grad(rc.ExplicitLoss(R, CPU), true, p)
+    out["explicit_swapped_loss"], out["explicit_swapped_grad"] = _grad(rc.ExplicitLoss(R, CPU), p, true)
+    out["implicit_per_sample"] = np.array([rc.ImplicitLoss(R, CPU, 1.5, 260)(img[i:i + 1].float(), p[i:i + 1]).item() for i in range(6)])
+    out["explicit_per_sample"] = np.array([rc.ExplicitLoss(R, CPU)(true[i:i + 1], p[i:i + 1]).item() for i in range(6)])
+    np.savez_compressed(os.path.join(OUT, "edge_zero_planes.npz"), **out)
+    print("zero planes: implicit", float(out["implicit_loss"]), "explicit", float(out["explicit_loss"]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -160,6 +193,7 @@ def main():
     fixtures(rc)
     random_cases(rc)
     edge_cases(rc)
+    zero_plane_cases(rc)
 
 
 if __name__ == "__main__":

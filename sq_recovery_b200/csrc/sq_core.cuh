@@ -146,7 +146,9 @@ struct Sample {
     // ellipsoid that contains every level set of F (column_range): w (sx^2 + sy^2) + sz^2 <= qB1 * F
     float wd[3];              // w_i * dh_i,  w = (qw, qw, 1)
     float qw, qa, qia, qB1;   // 2^(e2-1), sum w_i dh_i^2, its reciprocal, 2^(1-e1)
-    float pad_;
+    // Exact zeros along z (zero_planes()): 10 bits per coordinate i, the plane (>= 1) where s_i is EXACTLY 0 in the reference's
+    // fp64 arithmetic for every column, 0 = none.  Non-zero only for an axis-aligned rotation with t on a grid plane.
+    int zpack;
     // fp64 exponents for the refinement of gradient-carrying points (refined_point): 2/e2, 2/e1, e2/e1, e1
     double pxy64, pz64, e21_64, e1_64;
 };
@@ -229,6 +231,57 @@ SQ_HD void prep_part(const double* p, bool clamp, const Grid& g, SampleFull& S, 
         S.cf0 = (float)(g.z0 / g.step);
     }
 }
+// The reference replaces an EXACT zero of s_i^2 by 1e-4 (classes.py:171-173).  Along x and y such zeros come out of the
+// fp64 column base by themselves; along z the kernels evaluate s_i(c) = base_i + d_i c, which in general is never exactly
+// 0.  An exact zero on a whole plane happens in the reference when row i of M has exact zeros in its x and y entries (an
+// axis-aligned rotation: q = (0,0,0,1), half turns) and t_z sits exactly on a grid coordinate -- e.g. a position
+// clamped to 1 (classes.py:135), the last coordinate of every grid.  Then s_i = (M_i2 g_z - M_i2 t_z) / a_i for every column
+// (the reference's einsum adds exact zeros), and it vanishes where the two fp64 products agree.  Found by the fuzz
+// (tests/tools/parity_fuzz_other.py): a plane of |s| = 1e-2 instead of ~1e-17 moved an e1 gradient by 2x the tolerance.
+// Returns 10 bits per coordinate i: the plane c >= 1 where s_i is exactly 0, else 0.  (Plane 0 sits at 1e-4, classes.py:126,
+// which no clamp produces.  Rows with TWO non-zero entries -- quarter turns, whose matrix keeps a 1e-16 -- have zeros
+// that depend on the summation order of the reference's matmul: rounding noise, not reproduced.)
+SQ_HD int zero_planes(const SampleFull& S, const Grid& g) {
+    int pack = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (S.M[3 * i] != 0.0 || S.M[3 * i + 1] != 0.0 || S.M[3 * i + 2] == 0.0) continue;
+        const double m = S.M[3 * i + 2], target = m * S.t[2];
+        const int c0 = (int)(S.t[2] / g.step + 0.5);
+        for (int c = c0 - 1; c <= c0 + 1; ++c) {
+            if (c < 1 || c >= g.n || c > 1023) continue;
+            if (m * grid_coord(g, c) == target) pack |= c << (10 * i);
+        }
+    }
+    return pack;
+}
+// The kernels get these zeros for free: every one of them evaluates s_i = fma(cf, dh_i, bh_i) + fma(cf, dl_i, bl_i).  For
+// a row with a zero plane c*, d_i is re-split into two pieces of 13 significant bits (relative error 2^-26, better than
+// one float), so that c* dh_i and c* dl_i are exact in fp32, and column_base() hands out bh_i = -c* dh_i, bl_i = -c* dl_i
+// (the row does not depend on x, y): both FMAs return exactly 0 on plane c*, and d_i (c - c*) elsewhere.
+SQ_HD float round13(float v) {
+    int b;
+#if defined(__CUDA_ARCH__)
+    b = __float_as_int(v);
+#else
+    memcpy(&b, &v, 4);
+#endif
+    b = (b + 0x400) & ~0x7ff;
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(b);
+#else
+    float r; memcpy(&r, &b, 4); return r;
+#endif
+}
+SQ_HD void resplit_zero_rows(SampleFull& S, const Grid& g) {
+    for (int i = 0; i < 3; ++i) {
+        if (!((S.zpack >> (10 * i)) & 1023)) continue;
+        const double d = S.Ms[3 * i + 2] * g.step;
+        S.dh[i] = round13(d2f(d));
+        S.dl[i] = round13(d2f(d - f2d(S.dh[i])));
+        S.idh[i] = 1.0f / S.dh[i];
+    }
+}
+
 SQ_HD void prep_finish(const double* p, bool clamp, const Grid& g, SampleFull& S) {
     for (int i = 0; i < 8; ++i) {
         float m;
@@ -237,7 +290,8 @@ SQ_HD void prep_finish(const double* p, bool clamp, const Grid& g, SampleFull& S
         if (i < 3) S.a[i] = v; else if (i < 5) S.e[i - 3] = v; else S.t[i - 5] = v;
     }
     for (int i = 0; i < 4; ++i) S.q[i] = p[8 + i];
-    S.pad_ = 0.f;
+    S.zpack = zero_planes(S, g);
+    if (S.zpack) resplit_zero_rows(S, g);
     S.heads = 0; S.pad2_ = 0; S.hrn = 1.0;
     for (int i = 0; i < 8; ++i) S.hp[i] = 0.0;
     double al = 0.0;                                           // ellipsoid of column_range(): needs rows and qw
@@ -258,6 +312,11 @@ SQ_HD void column_base(const Sample& S, const Grid& g, int ia, int ib, float* bh
     const double dx = grid_coord(g, ia) - S.t[0], dy = grid_coord(g, ib) - S.t[1], dz = -S.t[2];
     for (int i = 0; i < 3; ++i)
         split2(S.Ms[3 * i] * dx + S.Ms[3 * i + 1] * dy + S.Ms[3 * i + 2] * dz, bh[i], bl[i]);
+    if (S.zpack)                                              // rows with a plane of exact zeros (zero_planes())
+        for (int i = 0; i < 3; ++i) {
+            const int cz = (S.zpack >> (10 * i)) & 1023;
+            if (cz) { bh[i] = -(float)cz * S.dh[i]; bl[i] = -(float)cz * S.dl[i]; }
+        }
     if (dxy) { dxy[0] = d2f(dx); dxy[1] = d2f(dy); }          // column position relative to t (for the M gradient)
 }
 
@@ -487,7 +546,13 @@ SQ_HD
 #endif
 float refined_x(const Sample& S, double step, float kl, double b0, double b1, double b2, float cf, const RefTabs& tb) {
     const double c = f2d(cf);
-    const double s0 = fma(c, S.Ms[2] * step, b0), s1 = fma(c, S.Ms[5] * step, b1), s2 = fma(c, S.Ms[8] * step, b2);
+    double s0 = fma(c, S.Ms[2] * step, b0), s1 = fma(c, S.Ms[5] * step, b1), s2 = fma(c, S.Ms[8] * step, b2);
+    if (S.zpack) {                                            // planes of exact zeros (zero_planes()): cf is an exact integer there
+        const int pc = cf < 1.0f ? -1 : (int)cf;          // plane 0 (cf = cf0 < 1) never is one
+        if ((S.zpack & 1023) == pc) s0 = 0.0;
+        if (((S.zpack >> 10) & 1023) == pc) s1 = 0.0;
+        if (((S.zpack >> 20) & 1023) == pc) s2 = 0.0;
+    }
     const double a0 = s0 == 0.0 ? 1e-2 : fabs(s0), a1 = s1 == 0.0 ? 1e-2 : fabs(s1), a2 = s2 == 0.0 ? 1e-2 : fabs(s2);
     const double lA = S.pxy64 * log2_acc(a0, tb), lB = S.pxy64 * log2_acc(a1, tb), lC = S.pz64 * log2_acc(a2, tb);
     const double t1 = exp2_acc(-fmin(fabs(lA - lB), 64.0), tb);
@@ -767,9 +832,9 @@ struct Plane { Fwd f; float x, eo, o, cf; };
 template <bool FIX>
 SQ_HD void plane_forward(const Sample& S, const ImplicitParams& P, const float* bh, const float* bl, float cf, Plane& p) {
     p.cf = cf;
-    const float sx = fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]);
-    const float sy = fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]);
-    const float sz = fmaf(cf, S.dh[2], bh[2]) + fmaf(cf, S.dl[2], bl[2]);
+    float sx = fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]);
+    float sy = fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]);
+    float sz = fmaf(cf, S.dh[2], bh[2]) + fmaf(cf, S.dl[2], bl[2]);
     point_forward<FIX>(S, sx, sy, sz, p.f);
     p.o = occupancy(p.f.F, P.kl, p.x, p.eo);
 }
@@ -955,8 +1020,9 @@ template <bool FIX>
 SQ_HD void queue_entry_backward(const Sample& S, const float* bh, const float* bl, float cf,
                                 float w, float Sw, float sign, bool has, Bwd& b) {
     Fwd f;
-    point_forward<FIX>(S, fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]), fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]),
-                       fmaf(cf, S.dh[2], bh[2]) + fmaf(cf, S.dl[2], bl[2]), f);
+    float sx = fmaf(cf, S.dh[0], bh[0]) + fmaf(cf, S.dl[0], bl[0]), sy = fmaf(cf, S.dh[1], bh[1]) + fmaf(cf, S.dl[1], bl[1]),
+          sz = fmaf(cf, S.dh[2], bh[2]) + fmaf(cf, S.dl[2], bl[2]);
+    point_forward<FIX>(S, sx, sy, sz, f);
     float W = w * Sw * sign;
     if (!has) { fwd_neutral(f); W = 0.f; }
     point_backward<FIX>(f, W, b);
@@ -1143,14 +1209,16 @@ SQ_HD void explicit_step(const Sample& St, const Sample& Sp, float kl, float cf,
     } else
 #endif
     {
-    if (HAS_T)
-        point_forward<true>(St, fmaf(cf, St.dh[0], bht[0]) + fmaf(cf, St.dl[0], blt[0]),
-                                fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
-                                fmaf(cf, St.dh[2], bht[2]) + fmaf(cf, St.dl[2], blt[2]), ft);
-    if (HAS_P)
-        point_forward<true>(Sp, fmaf(cf, Sp.dh[0], bhp[0]) + fmaf(cf, Sp.dl[0], blp[0]),
-                                fmaf(cf, Sp.dh[1], bhp[1]) + fmaf(cf, Sp.dl[1], blp[1]),
-                                fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]), fp);
+    if (HAS_T) {
+        float sx = fmaf(cf, St.dh[0], bht[0]) + fmaf(cf, St.dl[0], blt[0]), sy = fmaf(cf, St.dh[1], bht[1]) + fmaf(cf, St.dl[1], blt[1]),
+              sz = fmaf(cf, St.dh[2], bht[2]) + fmaf(cf, St.dl[2], blt[2]);
+        point_forward<true>(St, sx, sy, sz, ft);
+    }
+    if (HAS_P) {
+        float sx = fmaf(cf, Sp.dh[0], bhp[0]) + fmaf(cf, Sp.dl[0], blp[0]), sy = fmaf(cf, Sp.dh[1], bhp[1]) + fmaf(cf, Sp.dl[1], blp[1]),
+              sz = fmaf(cf, Sp.dh[2], bhp[2]) + fmaf(cf, Sp.dl[2], blp[2]);
+        point_forward<true>(Sp, sx, sy, sz, fp);
+    }
     if (HAS_T) { float xt, et; ot = occupancy(ft.F, kl, xt, et); }
     if (HAS_P) op = occupancy(fp.F, kl, xp, ep);
     }

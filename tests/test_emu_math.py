@@ -118,3 +118,25 @@ def test_proven_empty_groups_in_the_x_fastest_layout(kind, n):
         kl = 260 * log2e
         bad, empty, total = E.check_culling(p, n, 1 / (n - 1), 1e-4, 1, float(np.sqrt((1 + 40 / kl) * 1.002)), 1 + 40 / kl)
     assert bad == 0 and total > 0
+
+
+def test_emulated_zero_planes():
+    """Axis-aligned rotations with t_z exactly on a grid plane (tests/golden/edge_zero_planes.npz, frozen from the reference):
+    the reference's exact-zero fix-up fires on a whole z plane; the kernels' affine walk along z reproduces it through
+    Sample::zpack (zero_planes()).  Sample by sample, so that a single bad row is visible."""
+    g = load_golden("edge_zero_planes.npz")
+    R = int(g["R"])
+    tgt = F.interpolate(torch.tensor(g["img"]).float(), size=(R, R), mode="nearest")[:, 0].numpy()
+    for tau, k, name in ((1.5, 260.0, "implicit"), (1.0, 20.0, "implicit_soft")):
+        l, gr, _ = E.implicit(g["pred"], tgt, R, 1 / (R - 1), 1e-4, tau, k)
+        assert abs(l - g[f"{name}_loss"]) <= 1e-5 * g[f"{name}_loss"]
+        assert tol(gr, g[f"{name}_grad"]) <= 1.0, (name, np.abs(gr - g[f"{name}_grad"]).max(axis=1))
+    l, gr = E.explicit(g["true"], g["pred"], R + 1, 1 / R, 1e-4)
+    assert abs(l - g["explicit_loss"]) <= 1e-5 * g["explicit_loss"] and tol(gr, g["explicit_grad"]) <= 1.0
+    l, gr = E.explicit(g["pred"], g["true"], R + 1, 1 / R, 1e-4)
+    assert abs(l - g["explicit_swapped_loss"]) <= 1e-5 * g["explicit_swapped_loss"] and tol(gr, g["explicit_swapped_grad"]) <= 1.0
+    for i in range(len(g["pred"])):
+        l, _, _ = E.implicit(g["pred"][i:i + 1], tgt[i:i + 1], R, 1 / (R - 1), 1e-4, 1.5, 260.0, want_grad=False)
+        assert abs(l - g["implicit_per_sample"][i]) <= 1e-5 * g["implicit_per_sample"][i], i
+        l, _ = E.explicit(g["true"][i:i + 1], g["pred"][i:i + 1], R + 1, 1 / R, 1e-4, want_grad=False)
+        assert abs(l - g["explicit_per_sample"][i]) <= 1e-5 * g["explicit_per_sample"][i], i

@@ -802,3 +802,25 @@ def test_objects_that_fill_the_grid(dev, S):
             with torch.no_grad():                                       # the forward-only kernel shares the bookkeeping
                 lf = S.ImplicitLoss(R, dev, 1.5, 260)(img.to(dev), pred.to(dev)).item()
             assert abs(lf - ref.item()) <= LOSS_RTOL * abs(ref.item())
+
+
+def test_zero_planes(dev, S):
+    """Axis-aligned rotations with t_z exactly on a grid plane (e.g. a position clamped to 1): the reference's exact-zero
+    fix-up fires on a whole z plane -- the walk direction of the kernels (tests/golden/edge_zero_planes.npz, frozen from the
+    reference).  Found by tests/tools/parity_fuzz_other.py in round 2."""
+    g = load_golden("edge_zero_planes.npz")
+    R = int(g["R"])
+    img = torch.tensor(g["img"]).float()
+    l, gr = run(S.ImplicitLoss(R, dev, 1.5, 260), img, g["pred"], dev)
+    check(l, gr, g["implicit_loss"], g["implicit_grad"], what="zero planes implicit")
+    l, gr = run(S.ImplicitLoss(R, dev, 1.0, 20), img, g["pred"], dev)
+    check(l, gr, g["implicit_soft_loss"], g["implicit_soft_grad"], what="zero planes implicit soft")
+    l, gr = run(S.ExplicitLoss(R, dev), g["true"], g["pred"], dev)
+    check(l, gr, g["explicit_loss"], g["explicit_grad"], what="zero planes explicit")
+    l, gr = run(S.ExplicitLoss(R, dev), g["pred"], g["true"], dev)
+    check(l, gr, g["explicit_swapped_loss"], g["explicit_swapped_grad"], what="zero planes explicit swapped")
+    for i in range(len(g["pred"])):
+        t, p = torch.tensor(g["true"][i:i + 1]).to(dev), torch.tensor(g["pred"][i:i + 1]).to(dev)
+        with torch.no_grad():
+            assert abs(S.ImplicitLoss(R, dev, 1.5, 260)(img[i:i + 1].to(dev), p).item() - g["implicit_per_sample"][i]) <= LOSS_RTOL * g["implicit_per_sample"][i], i
+            assert abs(S.ExplicitLoss(R, dev)(t, p).item() - g["explicit_per_sample"][i]) <= LOSS_RTOL * g["explicit_per_sample"][i], i

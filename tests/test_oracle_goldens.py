@@ -118,6 +118,23 @@ def test_edge_cases(edge_golden):
     close(l, g["explicit24_loss"]); close(gr, g["explicit24_grad"], rtol=1e-9, atol=1e-12)
 
 
+def test_zero_plane_cases():
+    """Axis-aligned rotations with t_z exactly on a grid plane: the exact-zero fix-up on a whole z plane (frozen from
+    the reference by oracle/make_goldens.py:zero_plane_cases)."""
+    g = load_golden("edge_zero_planes.npz")
+    R = int(g["R"])
+    true, pred, img = torch.tensor(g["true"]), torch.tensor(g["pred"]), torch.tensor(g["img"]).float()
+    for form in ("batch", "loop"):
+        l, gr = grad_of(O.ImplicitLoss(R, "cpu", 1.5, 260, form=form), img, pred)
+        close(l, g["implicit_loss"]); close(gr, g["implicit_grad"], rtol=1e-9, atol=1e-12)
+        l, gr = grad_of(O.ExplicitLoss(R, "cpu", form=form), true, pred)
+        close(l, g["explicit_loss"]); close(gr, g["explicit_grad"], rtol=1e-9, atol=1e-12)
+    l, gr = grad_of(O.ImplicitLoss(R, "cpu", 1.0, 20), img, pred)
+    close(l, g["implicit_soft_loss"]); close(gr, g["implicit_soft_grad"], rtol=1e-9, atol=1e-12)
+    close(O.ExplicitLoss(R, "cpu").per_sample(true, pred).numpy(), g["explicit_per_sample"])
+    close(O.ImplicitLoss(R, "cpu", 1.5, 260).per_sample(img, pred).numpy(), g["implicit_per_sample"])
+
+
 def test_quaternion_helpers():
     q = torch.tensor([0.699625, 0.378123, -0.090419, -0.599476], dtype=torch.float64)
     assert torch.equal(O.conjugate(q), torch.tensor([-0.699625, -0.378123, 0.090419, -0.599476], dtype=torch.float64))
