@@ -12,7 +12,7 @@ Printed line (rank 0), see the driver contract:
   ``value``        Gpoints/s with inputs resident in HBM (CUDA events over exactly K graph-replayed steps)
   ``dense``        the same call on a second workload, sizes a ~ U(0.5, 1): objects fill the grid, culling cannot help
   ``e2e``          host buffers in, host results out, copies inside the timed region: 8-bit depth maps and fp32 parameters in
-                   pinned memory through sq_implicit_loss_host_submit / _wait, two batches in flight; H2D bytes counted and
+                   pinned memory through sq_implicit_loss_host_submit / _wait, several batches in flight; H2D bytes counted and
                    measured (NVML PCIe receive counter); round 1's blocking fp32-image call next to it
   ``roofline``     the dominant kernel against the measured MUFU (SFU) peak of this GPU: issued MUFU-pipe ops from the counting
                    build of the same sources, ``walked_fraction``, ``evaluated_gpoints_per_s``; DRAM traffic from the ncu capture
@@ -432,8 +432,8 @@ def run_gpu(args):
     ms, dms, seq_ms = t[0].item(), t[1].item(), t[2].item()
 
     # ---- e2e: host buffers -> C-ABI host calls -> host results, copies inside the timed region.  Headline: 8-bit depth
-    # images (what the reference's data are, torch/test.py:29-30) in pinned memory, two calls in flight on the context's
-    # two slots (sq_implicit_loss_host_submit / _wait): while one batch is being computed the next one crosses PCIe.
+    # images (what the reference's data are, torch/test.py:29-30) in pinned memory, several calls in flight on the context's
+    # slots (sq_implicit_loss_host_submit / _wait): while one batch is being computed the next ones cross PCIe.
     # Also reported: the blocking fp32-image call of round 1.
     ctx = HostContext(local)
     h_sets = []
@@ -447,17 +447,25 @@ def run_gpu(args):
         hs = torch.empty(small.shape, dtype=torch.uint8).pin_memory(); hs.copy_((small * 255.0).round().clamp(0, 255).to(torch.uint8))
         h_sets.append((hu.numpy(), hf.numpy(), hp.numpy(), hs.numpy()))
 
-    def pipelined(n, which=0):
-        """n steps, two in flight; every step: pinned inputs in, loss + gradient out to host memory."""
-        ctx.submit_implicit(0, h_sets[0][2], h_sets[0][which], R, TAU, SHARP)
+    # calls in flight (the context has SQ_HOST_SLOTS = 8 slots).  Measured on config 2 (profiles/e2e_depth_r02.txt): 2 -> 105 us per
+    # step, 4..6 -> 83 us (the strided copy-engine transfer of the sampled rows alone is 80 us, tools/pcie_probe.cu: the bus is
+    # busy all the time), 8 -> 91 us; with pre-resized images (1/16 of the bytes) 8 in flight reach the device-resident pace
+    DEPTH = int(os.environ.get("SQ_E2E_DEPTH", 5))
+    DEPTH_SMALL = int(os.environ.get("SQ_E2E_DEPTH_SMALL", 8))
+
+    def pipelined(n, which=0, depth=DEPTH):
+        """n steps, `depth` in flight; every step: pinned inputs in, loss + gradient out to host memory."""
+        for j in range(min(depth - 1, n)):
+            ctx.submit_implicit(j % depth, h_sets[j % 4][2], h_sets[j % 4][which], R, TAU, SHARP)
         out = None
         for i in range(n):
-            if i + 1 < n:
-                ctx.submit_implicit((i + 1) % 2, h_sets[(i + 1) % 4][2], h_sets[(i + 1) % 4][which], R, TAU, SHARP)
-            out = ctx.result(i % 2)
+            j = i + depth - 1
+            if j < n:
+                ctx.submit_implicit(j % depth, h_sets[j % 4][2], h_sets[j % 4][which], R, TAU, SHARP)
+            out = ctx.result(i % depth)
         return out
 
-    pipelined(6)
+    pipelined(12)
     for i in range(3):
         ctx.implicit_loss(h_sets[i % 4][2], h_sets[i % 4][1], R, TAU, SHARP)
     barrier()
@@ -471,10 +479,10 @@ def run_gpu(args):
     for i in range(f32_steps):
         l_f, g_f = ctx.implicit_loss(h_sets[i % 4][2], h_sets[i % 4][1], R, TAU, SHARP)
     f32_s = time.perf_counter() - t0
-    pipelined(6, which=3)
+    pipelined(12, which=3, depth=DEPTH_SMALL)
     barrier()
     t0 = time.perf_counter()
-    l_s, g_s = pipelined(e2e_steps, which=3)
+    l_s, g_s = pipelined(e2e_steps, which=3, depth=DEPTH_SMALL)
     small_s = time.perf_counter() - t0
     assert abs(l_s - l_h) <= 1e-12 * abs(l_h) and np.array_equal(g_s, g_h)     # same pixels, same bits
     te = torch.tensor([e2e_s, f32_s, small_s], dtype=torch.float64, device=dev)
@@ -528,7 +536,7 @@ def run_gpu(args):
         roof["peak_source"] = (f"{peak['source']}: {peak['mufu_per_clk_sm']:.2f} MUFU/clk/SM x {peak['sms']} SMs x "
                                f"{peak['sm_mhz']:.0f} MHz (measured)")
         droof = roofline_block(dkms, c_dense, peak, None, pts, clock)
-        h2d_u8 = B * R * min(W, R * 32) + B * 12 * 4 + 4 * R * 4       # sectors of the sampled rows + parameters + offset tables
+        h2d_u8 = B * R * W + B * 12 * 4        # the sampled rows + parameters (the offset tables stay on the device)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -541,15 +549,16 @@ def run_gpu(args):
             "walked_fraction": roof["walked_fraction"], "evaluated_gpoints_per_s": roof["evaluated_gpoints_per_s"],
             "clocks": clocks,
             "e2e": {"value": world * pts * e2e_steps / e2e_s / 1e9, "unit": UNIT,
-                    # the pinned 8-bit depth maps are sampled in place over PCIe: the 32-byte sectors of the sampled rows
-                    # cross the bus (every 4th row of a 256 x 256 image, all of its 256 bytes)
+                    # of the pinned 8-bit depth maps only the sampled rows cross the bus (every 4th row of a 256 x 256 image, all of
+                    # its 256 bytes), as one strided copy-engine transfer per call
                     "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": 8 + B * 12 * 4,
                     "h2d_bytes_per_step_measured": pcie["bytes_per_step"] if pcie else None, "pcie": pcie,
                     "host_image_bytes": B * H * W, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "api": "sq_implicit_loss_host_submit / _wait (include/sqloss.h): uint8 depth images and fp32 parameters in "
-                           "pinned host memory, loss + gradient back to host memory every step, two calls in flight",
+                           f"pinned host memory, loss + gradient back to host memory every step, {DEPTH} calls in flight",
+                    "calls_in_flight": DEPTH,
                     "pre_resized_u8_images": {"value": world * pts * e2e_steps / small_s / 1e9, "ms_per_step": small_s / e2e_steps * 1e3,
-                                              "h2d_bytes_per_step": B * R * R + B * 12 * 4 + 4 * R * 4,
+                                              "h2d_bytes_per_step": B * R * R + B * 12 * 4, "calls_in_flight": DEPTH_SMALL,
                                               "note": f"the same call on depth maps stored at the render size ({R}x{R} uint8: the pixels the "
                                                       "nearest resize would pick): 1/16 of the bytes, the step is then bound by the kernels"},
                     "blocking_f32_images": {"value": world * pts * f32_steps / f32_s / 1e9, "ms_per_step": f32_s / f32_steps * 1e3,

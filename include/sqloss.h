@@ -140,16 +140,20 @@ int sq_implicit_loss_host(sq_ctx* ctx, const float* pred_host, int batch, int re
                           const float* images_host, int height, int width, float tau, float sharpness,
                           double* loss_host, float* grad_host);
 
-/* The same in two halves, on one of the context's two slots (0 or 1), so that a caller can keep two batches in flight:
- * while one slot's kernels run, the other slot's images cross PCIe.
+/* The same in two halves, on one of the context's SQ_HOST_SLOTS slots (0 ... SQ_HOST_SLOTS-1), so that a caller can keep
+ * several batches in flight: while one slot's kernels run, the next slots' images cross PCIe (three in flight keep the
+ * bus busy all the time on BASELINE config 2).
  *   submit  enqueues the copies and kernels of one ImplicitLoss call on the slot's stream and returns at once.
  *           images_host [batch,H,W] of image_dtype SQ_F32, or SQ_U8 for 8-bit depth images -- the reference's data are
  *           8-bit BMPs divided by 255 (torch/test.py:29-30, torch/classes.py:82-88); every sampled pixel is multiplied by
- *           image_scale (1/255 for such images, 1 for fp32 depth in [0,1]).  Pinned (or registered) images are sampled
- *           in place over PCIe: only the sectors holding sampled pixels cross the bus.  pred_host and images_host must
- *           stay valid and unchanged until the matching wait.  cudaErrorNotReady if the slot still holds a result.
+ *           image_scale (1/255 for such images, 1 for fp32 depth in [0,1]).  Of pinned (or registered) images only the
+ *           sampled rows cross the bus: as one strided copy-engine transfer when H and W are multiples of render_size,
+ *           else read in place by a kernel; pageable images are copied whole.  pred_host is copied before submit returns;
+ *           images_host must stay valid and unchanged until the matching wait.  cudaErrorNotReady if the slot still
+ *           holds a result.
  *   wait    blocks until that call has finished and copies loss (and the gradient if it was asked for) out.
  */
+#define SQ_HOST_SLOTS 8
 int sq_implicit_loss_host_submit(sq_ctx* ctx, int slot, const float* pred_host, int batch, int render_size,
                                  const void* images_host, int image_dtype, int height, int width, float image_scale,
                                  float tau, float sharpness, int want_grad);

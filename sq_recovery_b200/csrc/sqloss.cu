@@ -1748,12 +1748,13 @@ int sq_field(const void* params, int params_dtype, int batch, int n, double step
 // whose Control block is zeroed when the arena is allocated, always sits at its start) and pinned staging.  The blocking
 // calls use slot 0.  sq_implicit_loss_host_submit / _wait expose the slots: while slot A's kernels run, slot B's inputs
 // cross PCIe.
-constexpr int kSlots = 2;
+constexpr int kSlots = SQ_HOST_SLOTS;
 struct sq_slot {
     cudaStream_t stream;
     char* dev; size_t dev_bytes;
     char* pin; size_t pin_bytes;
     size_t out_off, out_bytes;           // where the pending call's results sit in `pin`
+    const int* tab_dev; int tab_r, tab_h, tab_w;    // the resize offset tables now on the device (sq_implicit_loss_host_submit)
     int pending_batch; bool pending, pending_grad;
 };
 struct sq_ctx {
@@ -1764,7 +1765,7 @@ struct sq_ctx {
 static int slot_reserve(sq_slot* c, size_t dev_bytes, size_t pin_bytes) {
     if (dev_bytes > c->dev_bytes) {
         if (c->dev) { SQ_TRY(cudaStreamSynchronize(c->stream)); SQ_TRY(cudaFree(c->dev)); }
-        c->dev = nullptr; c->dev_bytes = 0;
+        c->dev = nullptr; c->dev_bytes = 0; c->tab_dev = nullptr;
         SQ_TRY(cudaMalloc(&c->dev, dev_bytes));
         c->dev_bytes = dev_bytes;
         SQ_TRY(cudaMemsetAsync(c->dev, 0, sizeof(Control), c->stream));
@@ -1788,6 +1789,7 @@ int sq_ctx_create(int device, sq_ctx** out) {
         sq_slot& sl = c->slot[i];
         sl.stream = nullptr; sl.dev = nullptr; sl.dev_bytes = 0; sl.pin = nullptr; sl.pin_bytes = 0;
         sl.out_off = sl.out_bytes = 0; sl.pending_batch = 0; sl.pending = sl.pending_grad = false;
+        sl.tab_dev = nullptr; sl.tab_r = sl.tab_h = sl.tab_w = 0;
     }
     for (int i = 0; i < kSlots; ++i) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking);
@@ -1835,50 +1837,76 @@ int sq_implicit_loss_host_submit(sq_ctx* ctx, int slot, const float* pred_host, 
     if (c->pending) return (int)cudaErrorNotReady;          // the previous submit on this slot has not been waited for
     const int R = render_size;
     const size_t px = image_dtype == SQ_U8 ? 1 : sizeof(float);
-    // images in pinned (or registered) host memory are sampled in place over PCIe; pageable memory is copied whole
+    // How the pixels cross PCIe.  Images in pinned (or registered) host memory:
+    //   kRowsDma     the nearest resize picks every (height/R)-th row and every (width/R)-th pixel of it: the rows are one
+    //                strided copy-engine transfer (cudaMemcpy2DAsync) -- it runs beside the kernels of the other slot, which a
+    //                zero-copy kernel cannot (the persistent column kernel fills every SM's registers, so a gather kernel
+    //                waits for it to retire: 139 us -> 8x us per pipelined config-2 step, tools/pcie_probe.cu);
+    //   kRowsMapped  irregular rows but regular columns: whole rows read in place with 16-byte loads;
+    //   kPixels      anything else: pixel by pixel through the offset tables.
+    // Pageable memory is copied whole first and then sampled on the device (kRowsMapped / kPixels on the copy).
     cudaPointerAttributes attr;
     const void* mapped = nullptr;
     if (cudaPointerGetAttributes(&attr, images_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
         mapped = attr.devicePointer;
     else
         cudaGetLastError();
+    const bool regular = width % R == 0 && ((size_t)width * px) % 16 == 0;
+    const bool rows_dma = mapped && regular && height % R == 0;
+    const bool rows16 = regular && (rows_dma || !mapped || reinterpret_cast<uintptr_t>(mapped) % 16 == 0);
+    const size_t b_off = align_up(sizeof(int) * 5 * (size_t)R, 256);
     const size_t b_pred = align_up(sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_img = align_up(sizeof(float) * (size_t)batch * R * R, 256);                 // the compact [batch, R, R] fp32 target
-    const size_t b_raw = mapped ? 0 : align_up(px * (size_t)batch * height * width, 256);       // pageable images, copied whole
-    const size_t b_off = align_up(sizeof(int) * 4 * (size_t)R, 256);
+    const size_t b_raw = rows_dma ? align_up(px * (size_t)batch * R * width, 256)               // the sampled rows
+                       : mapped ? 0 : align_up(px * (size_t)batch * height * width, 256);       // pageable images, copied whole
     const size_t b_out = align_up(sizeof(double) + sizeof(float) * 12 * (size_t)batch, 256);
     const size_t b_scr = sq_scratch_bytes(batch, R);
-    int rc = slot_reserve(c, align_up(b_scr, 256) + b_pred + b_img + b_raw + b_off + b_out, b_off + b_out);
+    int rc = slot_reserve(c, align_up(b_scr, 256) + b_off + b_pred + b_img + b_raw + b_out, b_off + b_pred + b_out);
     if (rc) return rc;
     char* d = c->dev;
     void* d_scr = d; d += align_up(b_scr, 256);
+    int* d_off = reinterpret_cast<int*>(d); d += b_off;                                         // [off | pred]: one upload
     float* d_pred = reinterpret_cast<float*>(d); d += b_pred;
     float* d_img = reinterpret_cast<float*>(d); d += b_img;
     void* d_raw = d; d += b_raw;
-    int* d_off = reinterpret_cast<int*>(d); d += b_off;
     double* d_loss = reinterpret_cast<double*>(d);
     float* d_grad = reinterpret_cast<float*>(d + sizeof(double)); d += b_out;
+    // offset tables (kept on the device while the shape stays the same) and parameters, staged in pinned memory
     int* h_off = reinterpret_cast<int*>(c->pin);
-    nearest_offsets(height, R, width, h_off);
-    nearest_offsets(width, R, 1, h_off + R);
-    for (int i = 0; i < R; ++i) { h_off[2 * R + i] = i * R; h_off[3 * R + i] = i; }             // identity tables of the compact target
-    SQ_TRY(cudaMemcpyAsync(d_pred, pred_host, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
-    SQ_TRY(cudaMemcpyAsync(d_off, h_off, sizeof(int) * 4 * (size_t)R, cudaMemcpyHostToDevice, c->stream));
+    const bool same_tables = c->tab_dev == d_off && c->tab_r == R && c->tab_h == height && c->tab_w == width;
+    if (!same_tables) {
+        nearest_offsets(height, R, width, h_off);
+        nearest_offsets(width, R, 1, h_off + R);
+        for (int i = 0; i < R; ++i) {
+            h_off[2 * R + i] = i * R; h_off[3 * R + i] = i;                                     // identity tables of the compact target
+            h_off[4 * R + i] = i * width;                                                       // rows of the kRowsDma staging
+        }
+    }
+    memcpy(c->pin + b_off, pred_host, sizeof(float) * 12 * (size_t)batch);
+    if (same_tables) {
+        SQ_TRY(cudaMemcpyAsync(d_pred, c->pin + b_off, sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        SQ_TRY(cudaMemcpyAsync(d_off, c->pin, b_off + sizeof(float) * 12 * (size_t)batch, cudaMemcpyHostToDevice, c->stream));
+        c->tab_dev = d_off; c->tab_r = R; c->tab_h = height; c->tab_w = width;
+    }
     const void* src = mapped;
-    if (!mapped) {
+    long long stride_b = (long long)height * width;
+    const int* rows_off = d_off;
+    if (rows_dma) {
+        SQ_TRY(cudaMemcpy2DAsync(d_raw, (size_t)width * px, images_host, (size_t)(height / R) * width * px, (size_t)width * px,
+                                 (size_t)batch * R, cudaMemcpyHostToDevice, c->stream));
+        src = d_raw; stride_b = (long long)R * width; rows_off = d_off + 4 * R;
+    } else if (!mapped) {
         SQ_TRY(cudaMemcpyAsync(d_raw, images_host, px * (size_t)batch * height * width, cudaMemcpyHostToDevice, c->stream));
         src = d_raw;
     }
-    const long long stride_b = (long long)height * width;
-    // regular sampling (F.interpolate's nearest rule picks column j * width / R when R divides the width) on 16-byte
-    // aligned rows: whole-row reads with 16-byte loads; otherwise pixel by pixel through the offset tables
-    const bool rows16 = width % R == 0 && ((size_t)width * px) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) % 16) == 0;
+    const int gblocks = rows_dma ? 592 : 1184;
     if (rows16 && image_dtype == SQ_U8)
-        gather_rows_kernel<unsigned char><<<1184, 256, 0, c->stream>>>(static_cast<const unsigned char*>(src), stride_b, d_off, R, width,
-                                                                      width / R, batch, image_scale, d_img);
+        gather_rows_kernel<unsigned char><<<gblocks, 256, 0, c->stream>>>(static_cast<const unsigned char*>(src), stride_b, rows_off, R,
+                                                                         width, width / R, batch, image_scale, d_img);
     else if (rows16)
-        gather_rows_kernel<float><<<1184, 256, 0, c->stream>>>(static_cast<const float*>(src), stride_b, d_off, R, width, width / R, batch,
-                                                              image_scale, d_img);
+        gather_rows_kernel<float><<<gblocks, 256, 0, c->stream>>>(static_cast<const float*>(src), stride_b, rows_off, R, width, width / R,
+                                                                 batch, image_scale, d_img);
     else if (image_dtype == SQ_U8)
         gather_targets_kernel<unsigned char><<<1184, 256, 0, c->stream>>>(static_cast<const unsigned char*>(src), stride_b, d_off, d_off + R,
                                                                          R, batch, image_scale, d_img);
@@ -1890,7 +1918,7 @@ int sq_implicit_loss_host_submit(sq_ctx* ctx, int slot, const float* pred_host, 
                           d_off + 2 * R, d_off + 3 * R, tau, sharpness, d_loss, nullptr, want_grad ? d_grad : nullptr, nullptr,
                           d_scr, b_scr, c->stream);
     if (rc) return rc;
-    c->out_off = b_off;
+    c->out_off = b_off + b_pred;
     c->out_bytes = sizeof(double) + (want_grad ? sizeof(float) * 12 * (size_t)batch : 0);
     SQ_TRY(cudaMemcpyAsync(c->pin + c->out_off, d_loss, c->out_bytes, cudaMemcpyDeviceToHost, c->stream));
     c->pending = true; c->pending_grad = want_grad != 0; c->pending_batch = batch;
@@ -1933,6 +1961,7 @@ int sq_explicit_loss_host(sq_ctx* ctx, const float* true_host, const float* pred
     const size_t b_scr = sq_scratch_bytes(batch, n);
     int rc = slot_reserve(c, align_up(b_scr, 256) + 2 * b_par + b_out, b_out);
     if (rc) return rc;
+    c->tab_dev = nullptr;                                    // this call's arena layout overwrites the resize tables
     char* d = c->dev;
     void* d_scr = d; d += align_up(b_scr, 256);
     float* d_true = reinterpret_cast<float*>(d); d += b_par;
@@ -1965,6 +1994,7 @@ int sq_iou_counts_host(sq_ctx* ctx, const float* true_host, const float* pred_ho
     const size_t b_scr = sq_scratch_bytes(batch, n);
     int rc = slot_reserve(c, align_up(b_scr, 256) + 2 * b_par + b_out, b_out);
     if (rc) return rc;
+    c->tab_dev = nullptr;                                    // this call's arena layout overwrites the resize tables
     char* d = c->dev;
     void* d_scr = d; d += align_up(b_scr, 256);
     float* d_true = reinterpret_cast<float*>(d); d += b_par;

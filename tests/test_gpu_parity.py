@@ -355,6 +355,35 @@ def test_host_entry_points(dev, S):
     ctx.close()
 
 
+def test_host_image_transfer_modes(dev, S):
+    """sq_implicit_loss_host_submit picks how the pixels cross PCIe from the image shape (copy-engine rows / rows read in
+    place / single pixels / pageable copy): every mode must give the bits of the class path on the same pixels, also when
+    shapes, batch sizes and slots alternate (the resize tables are kept on the device while the shape stays the same) and
+    when another host call reuses the slot's arena in between."""
+    from sq_recovery_b200.functional import HostContext
+    ctx = HostContext(0)
+    rs = np.random.RandomState(3)
+    seq = [(8, 16, 64, 64), (8, 16, 64, 64), (8, 16, 40, 64), (8, 16, 40, 56), (3, 16, 64, 64), (8, 16, 64, 64),
+           (5, 32, 128, 96), (8, 16, 64, 64), (8, 24, 48, 96)]
+    for n, (B, R, H, W) in enumerate(seq):
+        pred = O.random_params(B, 40 + n)
+        for dtype in (torch.uint8, torch.float32):
+            raw = torch.from_numpy(rs.randint(0, 256, size=(B, 1, H, W)).astype(np.uint8))
+            host = raw if dtype == torch.uint8 else raw.float() / 255.0
+            as_f32 = raw.float() * np.float32(1.0 / 255.0) if dtype == torch.uint8 else host
+            want = run(S.ImplicitLoss(R, dev, 1.5, 260), as_f32, pred, dev)
+            pin = torch.empty(host.shape, dtype=dtype).pin_memory(); pin.copy_(host)
+            slot = n & 1
+            ctx.submit_implicit(slot, pred.numpy(), pin.numpy(), R, 1.5, 260.0)
+            ctx.submit_implicit(1 - slot, pred.numpy(), host.numpy(), R, 1.5, 260.0)          # pageable
+            for sl in (slot, 1 - slot):
+                l, g = ctx.result(sl)
+                assert l == want[0] and np.array_equal(g.astype(np.float64), want[1]), (n, dtype, sl)
+        if n == 4:
+            ctx.explicit_loss(O.random_params(4, 1).numpy(), O.random_params(4, 2).numpy(), 12)
+    ctx.close()
+
+
 # ------------------------------------------------------------------ work queues, scratch contract, culling corner cases
 def _scratch_control_words(S, dev):
     from sq_recovery_b200 import functional as Fn
