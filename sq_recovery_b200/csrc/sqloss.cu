@@ -653,13 +653,17 @@ struct WorkPipe {
     // The same claim in three stages, so that its two dependent L2 round trips (cursor, queue) are spent under other work
     // of the warp instead of stalling it: issue the cursor atomic; later turn its result into a queue lookup; later use
     // the item (the caller then fetches its Sample).
-    int pend_pos;
+    // (ptxas turns an atomic add of a warp-uniform value -- atomicAdd(), atom.add or atom.inc in inline PTX alike -- into its
+    // warp-aggregated form, whose broadcast shuffle sits right behind the ATOMG and waits out the whole round trip on the
+    // spot.  An increment it cannot prove uniform -- 1 + a shuffled 0 -- keeps the atomic a plain fire-and-forget one.)
+    unsigned int pend_pos;
     __device__ __forceinline__ void claim_issue(int lane) {
-        pend_pos = 0;
-        if (lane == 0) pend_pos = (int)(atomicAdd(cursor, 1u) + gridDim.x * (blockDim.x >> 5));
+        const unsigned int one = 1u + __shfl_sync(0xffffffffu, 0u, lane);
+        pend_pos = 0u;
+        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pend_pos) : "l"(cursor), "r"(one) : "memory");
     }
     __device__ __forceinline__ void claim_lookup(int lane) {
-        next_pos = __shfl_sync(0xffffffffu, pend_pos, 0);
+        next_pos = (int)(__shfl_sync(0xffffffffu, pend_pos, 0) + gridDim.x * (blockDim.x >> 5));
         next = next_pos < total ? wm.item(queue, cap, next_pos, lane) : -1;
     }
     // decided on the position alone: the looked-up item id is not touched before the caller forms the Sample address
@@ -687,7 +691,19 @@ __device__ __forceinline__ void retire(Control* ctl, bool joined, int total_item
 __device__ unsigned long long g_timeline[3 * 8192];
 __device__ unsigned int g_classes[kClasses];
 #endif
+#ifdef SQ_PHASES       // tools/timeline.py SQ_PHASES: SM cycles of every warp of the fwd+bwd kernel, summed per phase
+// 0 item set-up (sample, pixel loads, fp32 base, ranges)  1 exact base + z walk  2 claim issue, signs, counts scan, queue look-up
+// 3 fp64 refinement  4 deal-out backward  5 column values + deal-out list to shared memory, folding into the tile
+// 6 item epilogue (reduction, partial row)  7 waiting for the next item (claim, sample) and loop ends
+__device__ unsigned long long g_phase[8];
+#define SQ_PH(i) do { const long long n_ = clock64(); ph[i] += n_ - ph_t; ph_t = n_; } while (0)
+#else
+#define SQ_PH(i) do { } while (0)
+#endif
 
+#ifndef SQ_EARLY_MARGIN      // measured (profiles/tune_r02.txt run k): margins 1..3 are 1-2 us SLOWER per call than none -> off
+#define SQ_EARLY_MARGIN 0
+#endif
 // dynamic shared memory of the fwd+bwd kernel, per warp: 4 queue arrays + 11 x 32 column values + the deal-out list
 constexpr size_t kImplicitBwdSmemPerWarp = (size_t)kBwdDepth * 32 * (4 * sizeof(float) + sizeof(unsigned short)) + 11 * 32 * sizeof(float);
 static_assert(kImplicitBwdSmemPerWarp % 16 == 0, "per-warp regions stay 16-byte aligned");
@@ -753,6 +769,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #endif
     WorkPipe wp;
     wp.start(ctl, queue, cap, total_items, true, lane);
+#ifdef SQ_PHASES
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph_t = clock64();
+#endif
     {
         SampleFetch pre;
         if (wp.item >= 0) pre.fetch(samples + L.sample_of(wp.item), lane);
@@ -769,6 +788,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #endif
             int b, chunk;
             L.split(wp.item, b, chunk);
+            SQ_PH(7);
             pre.commit(&S, lane);
             SQ_COUNT_HOOK(4, 1);
 
@@ -816,6 +836,17 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     continue;
                 }
                 SQ_COUNT_HOOK(5, 1);
+                SQ_PH(0);
+#if defined(SQ_BWD_COMPACT) && !defined(SQ_NO_STAGED_CLAIM) && !defined(SQ_EARLY_CLAIM) && SQ_EARLY_MARGIN > 0
+                // Far from the end of the queue the cursor atomic goes out BEFORE the walk (its L2 round trip then costs
+                // nothing); in the end-game -- fewer than SQ_EARLY_MARGIN items per warp left -- an item claimed before a
+                // long walk would be work no idle warp can take, so the claim waits until after the walk (see below).
+                const bool early = BWD && k == L.cpt - 1 &&
+                                   wp.item_pos + SQ_EARLY_MARGIN * (int)(gridDim.x * (THREADS / 32)) < wp.total;
+                if (early) wp.claim_issue(lane);
+#else
+                const bool early = false;
+#endif
                 float bh[3], bl[3], cg[11], dxy[2];
                 column_base(S, g, valid ? ia : 0, valid ? ib : 0, bh, bl, dxy);
                 float depth;
@@ -834,6 +865,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 else
                     depth = implicit_column<BWD, false>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg);
 #endif
+                SQ_PH(1);
 #ifndef SQ_EARLY_CLAIM
                 // Claim the next item only now, after the walk: the cursor -> queue -> Sample chain then stalls this warp
                 // for ~1300 cycles, but the kernel is bound by instruction dispatch and the other warps of the scheduler
@@ -841,7 +873,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 // take -- during the end-game that was the tail of the kernel.
 #if defined(SQ_BWD_COMPACT) && !defined(SQ_NO_STAGED_CLAIM)
                 const bool staged = BWD && k == L.cpt - 1;     // fwd+bwd: the claim is spread over the backward passes
-                if (staged) wp.claim_issue(lane);
+                if (staged) { if (!early) wp.claim_issue(lane); }
                 else
 #else
                 const bool staged = false;
@@ -880,6 +912,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                         if (total == 0 && wp.claim_finish()) pre.fetch(samples + L.sample_of(wp.next), lane);
                     }
 #endif
+                    SQ_PH(2);
                     if (total > 0 || any_spill) {
                         Acc acc;
                         float v[kRedStride];
@@ -902,6 +935,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                             const BwdQueue qwarp{qbuf, qbuf + kQN, qbuf + 2 * kQN, qbuf + 3 * kQN, 32};
                             SQ_COUNT_HOOK(6, total); SQ_COUNT_HOOK(7, total_r);
                             SQ_COUNT_HOOK(3, (total_r + 31) / 32); SQ_COUNT_HOOK(2, (total + 31) / 32);
+                            SQ_PH(5);
                             // 1. the entries near the surface, dealt out evenly: x in fp64 (sq_core.cuh "fp64 refinement")
                             // (SQ_REFINE_ILP2: two rounds in flight where there are that many -- measured 6 us SLOWER per call,
                             // profiles/tune_r02.txt: the second chain's registers cost the walk its allocation)
@@ -929,6 +963,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                                                    f2d(ci[2 * 32 + l_]) + f2d(ci[5 * 32 + l_]), tb);
                             }
                             __syncwarp();
+                            SQ_PH(3);
                             const float tau = P.tl * (float)kLn2;
 #ifdef SQ_DEPTH_SHIFT       // the refined occupancies' first-order effect on the rendered depth: measured below the loss's other
                             // fp32 errors on every workload (profiles/tune_r02.txt) and 2 us per call -> off
@@ -966,11 +1001,13 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                                 acc_add_point(acc, b0, c0, x0, y0);
                             }
                             __syncwarp();
+                            SQ_PH(4);
                         }
                         acc_to_array(acc, v);
                         v[18] = v[19] = 0.f;
                         tile_put(tile_w, v);
                         folded = true;
+                        SQ_PH(5);
                     }
                 } else
 #endif
@@ -996,6 +1033,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     }
                 }
             }
+            SQ_PH(7);
             if (target) {
                 float* row = partials + ((size_t)b * L.rows_per_sample + chunk) * kRow;
                 const unsigned nz = __ballot_sync(0xffffffffu, loss_sum != 0.f);
@@ -1018,10 +1056,15 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     tile_reduce_store(tile_w, row);
                 }
             }
+            SQ_PH(6);
             wp.rotate();
         }
     }
     retire(ctl, wp.joined, total_items, lane);
+#ifdef SQ_PHASES
+    if (BWD && lane == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_phase[i], (unsigned long long)ph[i]);
+#endif
 #ifdef SQ_TIMELINE
     if (BWD && lane == 0) {
         const int w = first_position();
@@ -1497,6 +1540,13 @@ int sq_debug_counters(unsigned long long* host_out, int reset) {
 }
 #endif
 
+#ifdef SQ_PHASES
+int sq_debug_phases(unsigned long long* host_out, int reset) {
+    int rc = (int)cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 8);
+    if (!rc && reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; rc = (int)cudaMemcpyToSymbol(g_phase, z, sizeof z); }
+    return rc;
+}
+#endif
 #ifdef SQ_TIMELINE
 int sq_debug_timeline(unsigned long long* host_out, int n) {
     return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * 3 * (size_t)n);

@@ -79,3 +79,21 @@ bw = np.zeros(2, dtype=np.uint64)
 h.sq_debug_bwd.argtypes = [ctypes.c_void_p]
 if h.sq_debug_bwd(bw.ctypes.data_as(ctypes.c_void_p)) == 0 and bw[0]:
     print(f"backward blocks executed (all calls so far): {int(bw[0])} warp-steps, {bw[1] / bw[0]:.1f} of 32 lanes carrying gradient on average")
+
+if "SQ_PHASES" in sys.argv[1:]:       # python tools/timeline.py SQ_PHASES: SM cycles of all warps per phase (the stamps cost ~3 %)
+    ph = np.zeros(8, dtype=np.uint64)
+    h.sq_debug_phases.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    assert h.sq_debug_phases(ph.ctypes.data_as(ctypes.c_void_p), 1) == 0          # discard the warm-up calls
+    reps = 4
+    for _ in range(reps):
+        assert h.sq_implicit_loss(P(pred), 0, B, R, 1.0 / (R - 1), 1e-4, P(img), 256 * 256, P(row_off), P(col_off), 1.5, 260.0,
+                                  P(loss), None, P(grad), None, P(scratch), nb, torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    assert h.sq_debug_phases(ph.ctypes.data_as(ctypes.c_void_p), 0) == 0
+    names = ["item set-up (sample, pixels, fp32 base, ranges)", "exact base + z walk", "claim issue, signs, counts scan, queue look-up",
+             "fp64 refinement", "deal-out backward", "column values + deal-out list, folding into the tile",
+             "item epilogue (reduction, partial row)", "waiting for the next item (claim, sample), loop ends"]
+    tot = float(ph.sum())
+    print(f"warp cycles per launch, all {len(buf)} warps: {tot / reps / 1e6:.2f} M  ({tot / reps / len(buf) / 1e3:.1f} k per warp)")
+    for nme, c in zip(names, ph):
+        print(f"  {nme:52s} {100.0 * float(c) / tot:5.1f} %")
