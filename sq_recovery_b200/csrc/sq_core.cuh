@@ -822,7 +822,7 @@ struct ColState {
 #define SQ_BWD_COMPACT 1
 #endif
 #ifndef SQ_BWD_DEPTH
-#define SQ_BWD_DEPTH 16
+#define SQ_BWD_DEPTH 15       // 15 (not 16): five blocks' queues fit one SM's shared memory (sqloss.cu SQ_IMPB_MINB)
 #endif
 constexpr int kBwdDepth = SQ_BWD_DEPTH;
 

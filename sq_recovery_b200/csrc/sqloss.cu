@@ -49,7 +49,19 @@ namespace {
 #define SQ_IMPB_THREADS 128              // implicit fwd+bwd
 #endif
 #ifndef SQ_IMPB_MINB
-#define SQ_IMPB_MINB 4
+// 5 blocks = 20 warps per SM at 96 registers (60 bytes of spill on cold paths): the phases of an item outside the z walk
+// are dependent chains (profiles/phases_r02.txt), and a fifth warp per scheduler hides more of them than the 26 registers
+// were worth -- 48.0 vs 49.2-50.1 us per call (profiles/tune_r02.txt run l).  It takes the three settings below with it:
+// the reduction tile aliased onto the queue arrays and a 15-deep queue (shared memory for 5 blocks), one deal-out chain
+// in flight instead of two (registers).  The round's earlier shape: -DSQ_IMPB_MINB=4 -DSQ_BWD_DEPTH=16 -DSQ_TILE_ALIAS=0
+// -DSQ_DENSE_ILP=2.
+#define SQ_IMPB_MINB 5
+#endif
+#ifndef SQ_TILE_ALIAS
+#define SQ_TILE_ALIAS 1
+#endif
+#ifndef SQ_DENSE_ILP
+#define SQ_DENSE_ILP 1
 #endif
 #ifndef SQ_IMPB_CPT
 #define SQ_IMPB_CPT 1
@@ -715,9 +727,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
     __shared__ Sample Ssh[THREADS / 32];
-#if defined(SQ_TILE_ALIAS) && defined(SQ_BWD_COMPACT)
-    // experiment (5 blocks / SM): the fwd+bwd kernel's reduction tile lives in the warp's queue arrays, which are dead
-    // by the time the item's sums are put there (one column group per item only)
+#if SQ_TILE_ALIAS && defined(SQ_BWD_COMPACT)
+    // the fwd+bwd kernel's reduction tile lives in the warp's queue arrays, which are dead by the time the item's sums
+    // are put there (one column group per item only): shared memory for 5 blocks per SM
     static_assert(!BWD || CPTMAX == 1, "SQ_TILE_ALIAS needs one column group per work item");
     static_assert(4 * kBwdDepth * 32 >= kRedFloats, "queue arrays too small to hold the tile");
     __shared__ __align__(16) float tiles_static[BWD ? 1 : THREADS / 32][kRedFloats];
@@ -732,7 +744,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
     float* const colinfo_w = qbuf + 4 * kQN;                                                                         // [11][32]
     unsigned short* const qmap_w = reinterpret_cast<unsigned short*>(colinfo_w + 11 * 32);                            // [kQN]
 #endif
-#if defined(SQ_TILE_ALIAS) && defined(SQ_BWD_COMPACT)
+#if SQ_TILE_ALIAS && defined(SQ_BWD_COMPACT)
     float* const tile_w = BWD ? qbuf : tiles_static[threadIdx.x >> 5];
 #else
     float* const tile_w = tiles_static[threadIdx.x >> 5];
@@ -986,7 +998,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                                 cfq = cf_; dx_ = ci[7 * 32 + l_]; dy_ = ci[8 * 32 + l_];
                             };
                             int j = lane;
-#ifndef SQ_DENSE_ILP1
+#if SQ_DENSE_ILP == 2
                             for (; j - lane + 32 < total; j += 64) {
                                 Bwd b0, b1; float c0, c1, x0, x1, y0, y1;
                                 dealt(j, b0, c0, x0, y0);
