@@ -27,6 +27,10 @@ __device__ unsigned long long g_bwd_stats[2];
 #define SQ_BWD_HOOK(a) do { const unsigned m_ = __ballot_sync(0xffffffffu, (a)); if ((threadIdx.x & 31) == 0) { \
     atomicAdd(&g_bwd_stats[0], 1ull); atomicAdd(&g_bwd_stats[1], (unsigned long long)__popc(m_)); } } while (0)
 #endif
+#ifdef SQ_ITEMLOG      // tools/item_costs.py: per work item, what the plan kernel estimated and what the column kernel spent
+__device__ float g_planlog[4 * 65536];       // cost class, estimated planes, -, -
+__device__ int g_itemlog[4 * 65536];         // cycles of the item, cycles of its z walk, queued points, refined points
+#endif
 #ifdef SQ_COUNT         // counting build (libsqloss_count.so, bench.py): what the implicit column kernel did, per launch
 // [0] warp plane steps of the z walk (32 point evaluations each)   [1] on-the-spot backward blocks (queue full)
 // [2] deal-out rounds of the compacted backward (all entries)       [3] deal-out rounds of the fp64 refinement
@@ -422,6 +426,7 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
     const int J = L.rows_per_sample;
     const int max_cost = L.cpt * L.n * NS;
     for (int j = threadIdx.x; j < J; j += THREADS) {
+        int c = kClasses - 1;                              // proven empty (group_planes is an upper bound)
         int cost = 0;
         for (int k = 0; k < L.cpt; ++k) {
             const int group = j + k * J;
@@ -429,7 +434,6 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
 #pragma unroll
             for (int w = 0; w < NS; ++w) cost += group_planes(Ssh[w], g, L, bound, group);
         }
-        int c = kClasses - 1;                              // proven empty (group_planes is an upper bound)
         if (cost > 0) {
             if (kClasses == 8) { c = 0; while (c < kClasses - 2 && (cost << (c + 1)) <= max_cost) ++c; }
             else {               // kClasses / 8 classes per octave
@@ -437,6 +441,9 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
                 c = c < 0 ? 0 : (c > kClasses - 2 ? kClasses - 2 : c);
             }
         }
+#ifdef SQ_ITEMLOG
+        if (NS == 1 && b * J + j < 65536) { float* lg = g_planlog + 4 * (b * J + j); lg[0] = (float)c; lg[1] = (float)cost; lg[2] = lg[3] = 0.f; }
+#endif
         cls[j] = (unsigned char)c;
         if (item_class) item_class[(size_t)b * J + j] = (unsigned char)c;      // finalize skips the rows of proven-empty items
         atomicAdd(&ccnt[c], 1u);
@@ -800,6 +807,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #endif
             int b, chunk;
             L.split(wp.item, b, chunk);
+#ifdef SQ_ITEMLOG
+            const long long il_t0 = clock64(); long long il_walk = 0; int il_q = 0, il_qr = 0;
+#endif
             SQ_PH(7);
             pre.commit(&S, lane);
             SQ_COUNT_HOOK(4, 1);
@@ -849,6 +859,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 }
                 SQ_COUNT_HOOK(5, 1);
                 SQ_PH(0);
+#ifdef SQ_ITEMLOG
+                const long long il_w0 = clock64();
+#endif
 #if defined(SQ_BWD_COMPACT) && !defined(SQ_NO_STAGED_CLAIM) && !defined(SQ_EARLY_CLAIM) && SQ_EARLY_MARGIN > 0
                 // Far from the end of the queue the cursor atomic goes out BEFORE the walk (its L2 round trip then costs
                 // nothing); in the end-game -- fewer than SQ_EARLY_MARGIN items per warp left -- an item claimed before a
@@ -878,6 +891,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     depth = implicit_column<BWD, false>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg);
 #endif
                 SQ_PH(1);
+#ifdef SQ_ITEMLOG
+                il_walk += clock64() - il_w0;
+#endif
 #ifndef SQ_EARLY_CLAIM
                 // Claim the next item only now, after the walk: the cursor -> queue -> Sample chain then stalls this warp
                 // for ~1300 cycles, but the kernel is bound by instruction dispatch and the other warps of the scheduler
@@ -918,6 +934,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                     const int last = __shfl_sync(0xffffffffu, incl, 31);
                     const int total_r = last >> 16, total = total_r + (last & 0xffff);
                     const bool any_spill = __any_sync(0xffffffffu, spilled && wsg != 0.f);
+#ifdef SQ_ITEMLOG
+                    il_q += total + (any_spill ? 1000 : 0); il_qr += total_r;
+#endif
 #ifndef SQ_EARLY_CLAIM
                     if (staged) {
                         wp.claim_lookup(lane);
@@ -1069,6 +1088,12 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 }
             }
             SQ_PH(6);
+#ifdef SQ_ITEMLOG
+            if (BWD && lane == 0 && wp.item < 65536) {
+                int* lg = g_itemlog + 4 * wp.item;
+                lg[0] = (int)(clock64() - il_t0); lg[1] = (int)il_walk; lg[2] = il_q; lg[3] = il_qr;
+            }
+#endif
             wp.rotate();
         }
     }
@@ -1552,6 +1577,13 @@ int sq_debug_counters(unsigned long long* host_out, int reset) {
 }
 #endif
 
+#ifdef SQ_ITEMLOG
+int sq_debug_itemlog(float* plan_out, int* item_out, int n) {
+    int rc = (int)cudaMemcpyFromSymbol(plan_out, g_planlog, sizeof(float) * 4 * (size_t)n);
+    if (!rc) rc = (int)cudaMemcpyFromSymbol(item_out, g_itemlog, sizeof(int) * 4 * (size_t)n);
+    return rc;
+}
+#endif
 #ifdef SQ_PHASES
 int sq_debug_phases(unsigned long long* host_out, int reset) {
     int rc = (int)cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 8);
