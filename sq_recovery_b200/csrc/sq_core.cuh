@@ -693,7 +693,7 @@ SQ_HD void column_range(const Sample& S, const Grid& g, float bound, const float
 // footprint (so a thin object that slips between probe columns is never taken for empty).  0 is a PROOF that every
 // column of the footprint has an empty range -- the plan kernel relies on it to drop work items for good
 // (tests/test_emu_math.py checks the claim against the fp64 F).
-SQ_HD int footprint_planes(const Sample& S, const Grid& g, float bound, float cx, float cy, float hx, float hy) {
+SQ_HD int footprint_planes(const Sample& S, const Grid& g, float bound, float cx, float cy, float hx, float hy, int* range_lo = nullptr) {
     const float gx = cx * g.stepf, gy = cy * g.stepf;
     float lo = -1e30f, hi = 1e30f, he2 = 0.f, bc[3];
     for (int i = 0; i < 3; ++i) {
@@ -720,7 +720,43 @@ SQ_HD int footprint_planes(const Sample& S, const Grid& g, float bound, float cx
     lo = fminf(fmaxf(lo - 1.0f, 0.0f), nf);
     hi = fmaxf(fminf(hi + 1.0f, nf - 1.0f), -1.0f);
     const int c_lo = (int)ceilf(lo), c_hi = (int)floorf(hi);
+    if (range_lo) *range_lo = c_lo;
     return c_hi >= c_lo ? c_hi - c_lo + 1 : 0;
+}
+
+// How many of those planes an ImplicitLoss walk really visits.  The walk comes from high z and a lane is finished once its
+// transmittance is below 2^-32, i.e. `die` = 32 / (tau log2 e) planes of full occupancy after it entered the object; the
+// warp stops when its last lane has.  The unit ball |s|_2 <= 1 lies inside every superquadric with exponents 2/e >= 2
+// (|.|_p <= |.|_2), so a column whose chord through the ball |s|^2 <= 0.97 (occupancy > 0.99 at any sharpness >= 200; an
+// estimate, like everything here) is at least `die` planes long is finished `die` planes behind the chord's near end.
+// Chord length and near end are concave over the footprint (a convex body), so the four corner columns decide: if all
+// of them go opaque, every column between them does, and the walk ends at the lowest of their stopping planes; a group
+// on the silhouette keeps walking to the end of its range.  Objects that fill the grid (bench.py's `dense` workload) have
+// the same plane count in nearly every group, but real walks from 15 planes (interior) to all of them (silhouette): by plane
+// count alone the order was random there and the end-game 30 % of the launch (profiles/item_costs_r02.txt).
+SQ_HD int footprint_walk(const Sample& S, const Grid& g, float bound, float die, float cx, float cy, float hx, float hy) {
+    int c_lo = 0;
+    const int planes = footprint_planes(S, g, bound, cx, cy, hx, hy, &c_lo);
+    if (planes <= 0 || !(die > 0.f)) return planes;
+    const float a = fmaf(S.dh[0], S.dh[0], fmaf(S.dh[1], S.dh[1], S.dh[2] * S.dh[2])), ia = 1.0f / a, nf = (float)(g.n - 1);
+    float stop = 1e30f;
+    for (int k = 0; k < 4; ++k) {
+        const float gx = (cx + ((k & 1) ? hx : -hx)) * g.stepf, gy = (cy + ((k & 2) ? hy : -hy)) * g.stepf;
+        float b[3];
+        for (int i = 0; i < 3; ++i) b[i] = fmaf(S.mf[2 * i], gx, fmaf(S.mf[2 * i + 1], gy, S.of[i]));
+        const float beta = fmaf(S.dh[0], b[0], fmaf(S.dh[1], b[1], S.dh[2] * b[2]));
+        const float gamma = fmaf(b[0], b[0], fmaf(b[1], b[1], fmaf(b[2], b[2], -0.97f)));
+        const float disc = fmaf(beta, beta, -a * gamma);
+        float s = (float)c_lo;                                        // not opaque: walks to the end of the range
+        if (disc > 0.f) {
+            const float sq = sqrtf(disc);
+            const float far_ = fmaxf((-beta - sq) * ia, 0.f), near_ = fminf((sq - beta) * ia, nf);
+            if (near_ - far_ >= die) s = fmaxf(near_ - die - 1.0f, (float)c_lo);
+        }
+        stop = fminf(stop, s);
+    }
+    const int cut = (int)(stop - (float)c_lo);
+    return cut > 0 ? (planes - cut > 1 ? planes - cut : 1) : planes;
 }
 
 // Footprint (centre and half extents, in grid steps) of the 32-slot column group `group` in the x-fastest layout used

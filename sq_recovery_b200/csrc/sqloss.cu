@@ -64,6 +64,9 @@ namespace {
 #ifndef SQ_TILE_ALIAS
 #define SQ_TILE_ALIAS 1
 #endif
+#ifndef SQ_WALK_ESTIMATE     // cost classes of the implicit kernels from the planes a walk really visits (sq_core.cuh footprint_walk)
+#define SQ_WALK_ESTIMATE 1
+#endif
 #ifndef SQ_DENSE_ILP
 #define SQ_DENSE_ILP 1
 #endif
@@ -172,10 +175,11 @@ struct ColIter {
 // ------------------------------------------------------------------------------------------------ scratch
 // Work items are handed to the persistent warps in order of estimated cost (longest first, empty last): the plan
 // kernel sorts them into kClasses cost classes, one queue per class.  Class k holds items whose estimated number of
-// z planes is in (max / 2^((k+1)/2), max / 2^(k/2)] (two classes per octave); the last class holds items PROVEN empty (the estimate is an upper bound),
-// which the column kernels never touch.
+// z planes is in (max / 2^((k+1)/4), max / 2^(k/4)] (four classes per octave); the last class holds items PROVEN empty (the
+// plane count is an upper bound), which the column kernels never touch.  For the implicit kernels the estimate is the
+// planes a walk really visits (sq_core.cuh footprint_walk): the early exit cuts interior groups short.
 #ifndef SQ_CLASSES
-#define SQ_CLASSES 16
+#define SQ_CLASSES 32
 #endif
 constexpr int kClasses = SQ_CLASSES;     // 8: one class per octave of cost; 16 / 32: two / four per octave -- a finer
                                          // longest-first order: the last big items handed out are the cheaper ones (-1.5 us)
@@ -305,7 +309,7 @@ prep_kernel(const void* params, int dtype, int batch, int clamp, Grid g, SampleF
 // once at the centre of the group's footprint, widened by how far s can move across the footprint (so a thin object
 // that slips between probe columns is never taken for empty).  Only the ORDER in which work is handed out depends on
 // this, never a result.
-__device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, float bound, int group) {
+__device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, float bound, int group, float die = 0.f) {
     float cx, cy, hx, hy;                                  // centre and half extent of the footprint, in grid steps
     if (L.patched) {
         const int pw = L.n >> 3, pb = group / pw, pa = group - pb * pw;
@@ -313,7 +317,7 @@ __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, flo
     } else {
         xfast_group_footprint(L.n, group, cx, cy, hx, hy);
     }
-    return footprint_planes(S, g, bound, cx, cy, hx, hy);
+    return die > 0.f ? footprint_walk(S, g, bound, die, cx, cy, hx, hy) : footprint_planes(S, g, bound, cx, cy, hx, hy);
 }
 
 // plan (column kernels): one block per sample.  Builds the Sample record(s) like prep, then estimates the cost of each
@@ -322,7 +326,7 @@ __device__ int group_planes(const Sample& S, const Grid& g, const Layout& L, flo
 // pixel sum); kPlanThreadsSmall beyond (more samples resident per SM: the kernel is then a throughput problem).
 template <int NS, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, int heads, Grid g, Layout L, float bound,
+plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, int heads, Grid g, Layout L, float bound, float die,
             SampleFull* out_a, SampleFull* out_b, Control* ctl, unsigned long long* counts, int* queue, int cap,
             unsigned char* item_class, const float* __restrict__ target, long long tstride, const int* __restrict__ row_off,
             const int* __restrict__ col_off, double* tv_sum) {
@@ -432,7 +436,7 @@ plan_kernel(const void* params_a, const void* params_b, int dtype, int clamp, in
             const int group = j + k * J;
             if (group * 32 >= L.slots) break;
 #pragma unroll
-            for (int w = 0; w < NS; ++w) cost += group_planes(Ssh[w], g, L, bound, group);
+            for (int w = 0; w < NS; ++w) cost += group_planes(Ssh[w], g, L, bound, group, NS == 1 ? die : 0.f);
         }
         if (cost > 0) {
             if (kClasses == 8) { c = 0; while (c < kClasses - 2 && (cost << (c + 1)) <= max_cost) ++c; }
@@ -1533,7 +1537,7 @@ struct PlanTarget { const float* target; long long tstride; const int* row_off; 
 
 int launch_plan(const void* params_a, const void* params_b, int dtype, int batch, bool clamp, const Grid& g,
                 const Layout& L, float bound, const Scratch& s, unsigned long long* counts, unsigned char* item_class,
-                const PlanTarget* pt, cudaStream_t st, bool heads = false) {
+                const PlanTarget* pt, cudaStream_t st, bool heads = false, float die = 0.f) {
     if (dtype != SQ_F32 && dtype != SQ_F64) return (int)cudaErrorInvalidValue;
     int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;
     const PlanTarget none{nullptr, 0, nullptr, nullptr};
@@ -1541,12 +1545,12 @@ int launch_plan(const void* params_a, const void* params_b, int dtype, int batch
     const bool small = batch > 4 * device_sm_count();      // more samples than one wave of the large blocks
     if (params_b) {
         auto k = small ? plan_kernel<2, kPlanThreadsSmall> : plan_kernel<2, kPlanThreads>;
-        k<<<batch, small ? kPlanThreadsSmall : kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, 0, g, L, bound, s.tru, s.pred,
+        k<<<batch, small ? kPlanThreadsSmall : kPlanThreads, 0, st>>>(params_a, params_b, dtype, clamp ? 1 : 0, 0, g, L, bound, 0.f, s.tru, s.pred,
                                                                       s.ctl, counts, queue, s.queue_cap, queue ? item_class : nullptr,
                                                                       nullptr, 0, nullptr, nullptr, nullptr);
     } else {
         auto k = small ? plan_kernel<1, kPlanThreadsSmall> : plan_kernel<1, kPlanThreads>;
-        k<<<batch, small ? kPlanThreadsSmall : kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, heads ? 1 : 0, g, L, bound, s.pred,
+        k<<<batch, small ? kPlanThreadsSmall : kPlanThreads, 0, st>>>(params_a, nullptr, dtype, clamp ? 1 : 0, heads ? 1 : 0, g, L, bound, die, s.pred,
                                                                       nullptr, s.ctl, counts, queue, s.queue_cap, queue ? item_class : nullptr,
                                                                       t.target, t.tstride, t.row_off, t.col_off, pt ? s.tv_sum : nullptr);
     }
@@ -1641,7 +1645,7 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
 #endif
     const PlanTarget pt{target, target_stride_b, row_off, col_off};
     rc = launch_plan(pred, nullptr, pred_dtype, batch, true, g, L, P.bound, s, nullptr, target ? s.item_class : nullptr,
-                     target ? &pt : nullptr, st, heads);
+                     target ? &pt : nullptr, st, heads, SQ_WALK_ESTIMATE ? 32.0f / P.tl : 0.f);
     if (rc) return rc;
     const int items = batch * L.rows_per_sample;
     const int* queue = L.rows_per_sample <= kPlanMaxItems ? s.queue : nullptr;

@@ -27,7 +27,8 @@ for name, (res, args) in L0._PROTOS.items():
     fn = getattr(h, name); fn.restype, fn.argtypes = res, args
 B, R = 256, 64
 dev = torch.device("cuda:0")
-true = O.random_params(B, 0)
+dense = bool(os.environ.get("SQ_DENSE"))           # objects that fill the grid (bench.py's second workload)
+true = O.random_params(B, 0, size_range=O.DENSE_SIZE_RANGE) if dense else O.random_params(B, 0)
 pred = O.perturbed_params(true, 7).to(dev)
 true = true.to(dev)
 img = S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(true).unsqueeze(1).contiguous()
@@ -44,7 +45,7 @@ plan = np.zeros((n, 4), dtype=np.float32); item = np.zeros((n, 4), dtype=np.int3
 h.sq_debug_itemlog.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 assert h.sq_debug_itemlog(plan.ctypes.data_as(ctypes.c_void_p), item.ctypes.data_as(ctypes.c_void_p), n) == 0
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-np.savez_compressed(os.path.join(ROOT, "gpurun_out", "item_costs.npz"), plan=plan, item=item)
+np.savez_compressed(os.path.join(ROOT, "gpurun_out", "item_costs_dense.npz" if dense else "item_costs.npz"), plan=plan, item=item)
 live = item[:, 0] > 0
 cyc = item[live, 0].astype(np.float64)
 print(f"items with work {live.sum()} of {n}; cycles per item: mean {cyc.mean():.0f} p50 {np.median(cyc):.0f} p90 {np.percentile(cyc, 90):.0f} max {cyc.max():.0f}")

@@ -28,7 +28,7 @@ for name, (res, args) in L0._PROTOS.items():
     fn = getattr(h, name); fn.restype, fn.argtypes = res, args
 B, R = int(os.environ.get("SQ_B", 256)), 64
 dev = torch.device("cuda:0")
-true = O.random_params(B, 0)
+true = O.random_params(B, 0, size_range=O.DENSE_SIZE_RANGE) if os.environ.get("SQ_DENSE") else O.random_params(B, 0)
 pred = O.perturbed_params(true, 7)
 if os.environ.get("SQ_SORT"):
     vol = pred[:, 0].clamp(0.05, 1) * pred[:, 1].clamp(0.05, 1) * pred[:, 2].clamp(0.05, 1)
