@@ -222,5 +222,29 @@ long long emu_check_culling(const double* params, int B, int n, double step, dou
     return bad;
 }
 
-}  // extern "C"
+// The plan kernel's walk estimate (footprint_walk) only orders the work, but an estimate of 0 planes means "proven empty" and
+// the item is never processed: it must be 0 exactly where the plane count is, and never exceed it.  Returns the violations;
+// *cut_groups counts the groups whose estimate the early exit shortened.
+long long emu_check_walk_estimate(const double* params, int B, int n, double step, double z0, float bound, float die,
+                                  long long* cut_groups, long long* live_groups) {
+    Grid g = make_grid(n, step, z0);
+    long long bad = 0, cut = 0, live = 0;
+    for (int b = 0; b < B; ++b) {
+        double p[12]; for (int i = 0; i < 12; ++i) p[i] = params[12 * b + i];
+        SampleFull S; prep_sample(p, true, g, S);
+        const int groups = n % 8 == 0 ? (n / 8) * (n / 4) : (n * n + 31) / 32;
+        for (int group = 0; group < groups; ++group) {
+            float cx, cy, hx, hy;
+            if (n % 8 == 0) { const int pw = n >> 3, pb = group / pw, pa = group - pb * pw; cx = 8 * pa + 3.5f; cy = 4 * pb + 1.5f; hx = 3.5f; hy = 1.5f; }
+            else xfast_group_footprint(n, group, cx, cy, hx, hy);
+            const int planes = footprint_planes(S, g, bound, cx, cy, hx, hy);
+            const int walk = footprint_walk(S, g, bound, die, cx, cy, hx, hy);
+            if ((planes == 0) != (walk == 0) || walk > planes || walk < 0) ++bad;
+            if (planes > 0) { ++live; if (walk < planes) ++cut; }
+        }
+    }
+    *cut_groups = cut; *live_groups = live;
+    return bad;
+}
 
+}  // extern "C"

@@ -88,3 +88,14 @@ def check_culling(params, n, step, z0, clamp, bound, f_min):
     bad = fn(_ptr(params, ctypes.c_double), B, n, ctypes.c_double(step), ctypes.c_double(z0), int(clamp),
              ctypes.c_float(bound), ctypes.c_double(f_min), ctypes.byref(pe), ctypes.byref(pt))
     return int(bad), int(pe.value), int(pt.value)
+
+
+def check_walk_estimate(params, n, step, z0, bound, die):
+    """(violations, groups whose estimate the early exit shortened, live groups): see emu_check_walk_estimate in emu.cpp."""
+    params, B = _f64(params), len(params)
+    cut, live = ctypes.c_longlong(), ctypes.c_longlong()
+    fn = lib().emu_check_walk_estimate
+    fn.restype = ctypes.c_longlong
+    bad = fn(_ptr(params, ctypes.c_double), B, n, ctypes.c_double(step), ctypes.c_double(z0), ctypes.c_float(bound),
+             ctypes.c_float(die), ctypes.byref(cut), ctypes.byref(live))
+    return int(bad), int(cut.value), int(live.value)

@@ -120,6 +120,23 @@ def test_proven_empty_groups_in_the_x_fastest_layout(kind, n):
     assert bad == 0 and total > 0
 
 
+@pytest.mark.parametrize("n", [16, 20, 64])
+def test_walk_estimate_never_empties_a_live_group(n):
+    """The plan kernel orders the implicit kernels' work by the planes a walk really visits (footprint_walk).  Only the
+    order depends on it -- except that an estimate of 0 means "proven empty, never processed": it must be 0 exactly where
+    the culled plane count is, and never above it.  Small objects, big objects (the early exit cuts those), any tau."""
+    from sq_recovery_b200 import inputs as I
+    log2e = 1.4426950408889634
+    kl = 260 * log2e
+    bound = float(np.sqrt((1 + 40 / kl) * 1.002))
+    for seed, size_range, tau in ((1, I.SIZE_RANGE, 1.5), (2, I.DENSE_SIZE_RANGE, 1.5), (3, I.DENSE_SIZE_RANGE, 0.5), (4, (0.05, 1.0), 3.0)):
+        p = I.random_params(64, seed, size_range=size_range).double().numpy()
+        bad, cut, live = E.check_walk_estimate(p, n, 1 / (n - 1), 1e-4, bound, 32.0 / (tau * log2e))
+        assert bad == 0 and live > 0
+        if size_range == I.DENSE_SIZE_RANGE and tau == 1.5 and n == 64:
+            assert cut > 0.3 * live, (cut, live)            # objects that fill the grid: most groups leave early
+
+
 def test_emulated_zero_planes():
     """Axis-aligned rotations with t_z exactly on a grid plane (tests/golden/edge_zero_planes.npz, frozen from the reference):
     the reference's exact-zero fix-up fires on a whole z plane; the kernels' affine walk along z reproduces it through
