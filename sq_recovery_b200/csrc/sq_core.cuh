@@ -41,7 +41,8 @@ constexpr float kAbsFix = 1e-2f;          // |s| used when s == 0  (s^2 := 1e-4,
 #ifndef SQ_KACTIVE
 #define SQ_KACTIVE 24.0f
 #endif
-constexpr float kActive = SQ_KACTIVE;     // |log2 of the sigmoid odds| beyond which o(1-o) < 2^-kActive is dropped
+constexpr float kActive = SQ_KACTIVE;     // |log2 of the sigmoid odds| beyond which o(1-o) < 2^-kActive is dropped (ImplicitLoss at
+                                          // the training setting; implicit_active_bits() widens it for soft sigmoids)
 // ExplicitLoss (k = 5) walks a wide soft shell: thousands of points per sample sit at 2^-24 .. 2^-32, and their sum shows
 // at 0.2x the gradient tolerance (measured) -- it keeps the wider cut
 constexpr float kActiveExplicit = 32.0f;
@@ -810,7 +811,18 @@ SQ_HD bool column_zero_possible(const Sample& S, const float* bh) {
 // end of the walk, so gradient terms are accumulated twice -- sum x and sum P_c x with P_c the sum of T in front
 // of c -- and combined as U sum x - sum P x when the column ends.  P and U start at the first point that carries
 // gradient, which keeps the subtraction well conditioned.
-struct ImplicitParams { float kl; float tl; float bound; };     // k log2(e), tau log2(e), implicit_cull_bound(kl)
+struct ImplicitParams { float kl; float tl; float bound; float kact; };   // k log2(e), tau log2(e), implicit_cull_bound(kl),
+                                                                          // implicit_active_bits(kl, n)
+// The backward drops points whose weight o (1 - o) is below 2^-kact.  What is dropped adds up over the band of points between
+// that cut and the culling bound, and the band is as thick as the sigmoid is soft: (32 - kact) / kl in F, i.e. a few points
+// per column at k = 260 but tens at k = 20, more on finer grids.  kact = 24 at the reference's training setting (k = 260, 64
+// planes: the dropped sum is 0.03x the gradient tolerance) and grows with log2 of the band's point count relative to
+// that, up to the culling bound's 32 -- found by the fuzz: k = 20 on a 96^3 grid was 1.1x off with a fixed 24, 0.1x with 28.3.
+SQ_HD float implicit_active_bits(float kl, int n) {
+    const float rel = (260.0f * kLog2e / kl) * ((float)n / 64.0f);
+    const float bits = kActive + (rel > 1.0f ? log2f(rel) : 0.0f);
+    return bits < kImplicitCullBits ? bits : kImplicitCullBits;
+}
 
 #ifndef SQ_KDEEP
 #define SQ_KDEEP 32.0f
@@ -951,7 +963,7 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
     st.cssum += st.csl;
     st.T = ex2(st.csl);
     if (BWD) {
-        const bool active = (fabsf(p.x) < kActive) && (st.csl > -kDeep);
+        const bool active = (fabsf(p.x) < P.kact) && (st.csl > -kDeep);
         if (SQ_ANY(active)) {
 #if defined(SQ_BWD_HOOK) && defined(__CUDA_ARCH__)
             SQ_BWD_HOOK(active);                // debug builds: statistics of how many lanes carry gradient

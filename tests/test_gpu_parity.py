@@ -833,6 +833,24 @@ def test_objects_that_fill_the_grid(dev, S):
             assert abs(lf - ref.item()) <= LOSS_RTOL * abs(ref.item())
 
 
+def test_soft_sigmoid_on_a_fine_grid(dev, S):
+    """sigmoid_sharpness 20 on a 96^3 grid: the band of points between the backward's weight cut and the culling bound is tens of
+    planes thick instead of one or two, and what a fixed 2^-24 cut dropped there added up to 1.1x the gradient tolerance on a
+    small entry (tests/tools/parity_fuzz.py --seed 8, case 111).  The cut now widens with the band (implicit_active_bits)."""
+    from sq_recovery_b200 import inputs
+    R, tau, k = 96, 1.5, 20.0
+    true = inputs.random_params(2, 5111, size_range=(0.3, 0.4))
+    pred = inputs.perturbed_params(true, 5111, sigma=0.03)
+    with torch.no_grad():
+        img = O.ImplicitLoss(3 * R + 1, "cpu", 1.5, 260).depth_projection(true).float().unsqueeze(1)
+    oc = O.ImplicitLoss(R, "cpu", tau, k)
+    p = pred.clone().requires_grad_(True)
+    ref = oc(img, p); ref.backward()
+    l, gr = run(S.ImplicitLoss(R, dev, tau, k), img, pred, dev)
+    check(l, gr, ref.item(), p.grad.double().numpy(), rtol=0.5 * GRAD_RTOL, atol=0.5 * GRAD_ATOL, what="k = 20 on 96^3",
+          keep=unambiguous(oc, img, pred))
+
+
 def test_zero_planes(dev, S):
     """Axis-aligned rotations with t_z exactly on a grid plane (e.g. a position clamped to 1): the reference's exact-zero
     fix-up fires on a whole z plane -- the walk direction of the kernels (tests/golden/edge_zero_planes.npz, frozen from the
