@@ -812,15 +812,20 @@ SQ_HD bool column_zero_possible(const Sample& S, const float* bh) {
 // of c -- and combined as U sum x - sum P x when the column ends.  P and U start at the first point that carries
 // gradient, which keeps the subtraction well conditioned.
 struct ImplicitParams { float kl; float tl; float bound; float kact; };   // k log2(e), tau log2(e), implicit_cull_bound(kl),
-                                                                          // implicit_active_bits(kl, n)
-// The backward drops points whose weight o (1 - o) is below 2^-kact.  What is dropped adds up over the band of points between
-// that cut and the culling bound, and the band is as thick as the sigmoid is soft: (32 - kact) / kl in F, i.e. a few points
-// per column at k = 260 but tens at k = 20, more on finer grids.  kact = 24 at the reference's training setting (k = 260, 64
-// planes: the dropped sum is 0.03x the gradient tolerance) and grows with log2 of the band's point count relative to
-// that, up to the culling bound's 32 -- found by the fuzz: k = 20 on a 96^3 grid was 1.1x off with a fixed 24, 0.1x with 28.3.
-SQ_HD float implicit_active_bits(float kl, int n) {
-    const float rel = (260.0f * kLog2e / kl) * ((float)n / 64.0f);
-    const float bits = kActive + (rel > 1.0f ? log2f(rel) : 0.0f);
+                                                                          // implicit_active_bits(kl, n, batch)
+// The backward drops points whose weight o (1 - o) is below 2^-kact.  Two things decide how small that has to be:
+//  * what is dropped adds up over the band of points between the cut and the culling bound, and the band is as thick as the
+//    sigmoid is soft: (32 - kact) / kl in F, i.e. at most a point per column at k = 260 but tens at k = 20, more on finer
+//    grids -- found by the fuzz: k = 20 on a 96^3 grid was 1.1x the tolerance off with a fixed 24, 0.1x with 28.3;
+//  * one dropped point moves the gradient of the MEAN loss by up to 2^-kact kl |dF/dtheta| / (n^2 batch), which has to stay well
+//    below the ABSOLUTE tolerance 1e-6: on a 12^3 grid with three samples a 2^-24 point is 3e-7 (fuzz: 0.94x at k = 500).
+// kact = 24 at the reference's training setting (k = 260, 64 planes, batches of 8 and more: the dropped sum is 0.03x the
+// tolerance), more where either rule asks for it, up to the culling bound's 32.
+SQ_HD float implicit_active_bits(float kl, int n, int batch) {
+    const float band = (260.0f * kLog2e / kl) * ((float)n / 64.0f);
+    float bits = kActive + (band > 1.0f ? log2f(band) : 0.0f);
+    const float point = log2f(kl * 1e9f / ((float)n * (float)n * (float)(batch > 0 ? batch : 1)));     // 2^-bits kl 10 / (n^2 B) <= 1e-8
+    if (point > bits) bits = point;
     return bits < kImplicitCullBits ? bits : kImplicitCullBits;
 }
 
@@ -971,12 +976,12 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
             bool now = active;                  // lanes whose point is handled on the spot
 #if defined(SQ_BWD_COMPACT)
             if (QUEUE) {
+                const bool shell = fabsf(p.x) < kRefine;
                 const bool room = st.qn < kBwdDepth;
                 if (active && room) {
                     const int at = st.qn * st.q.stride;
                     st.q.cf[at] = p.cf;             // plane
                     st.q.pre[at] = st.psh;          // T in front of it since the first active point
-                    const bool shell = fabsf(p.x) < kRefine;
                     st.q.x[at] = shell ? p.x : p.eo * p.o * p.o;     // refined later: x; else the weight o (1 - o) itself
                     st.rmask |= (shell ? 1u : 0u) << st.qn;
                     ++st.qn;
@@ -1062,6 +1067,10 @@ SQ_HD float queue_depth_shift(const BwdQueue& q, int col, unsigned rmask, float 
     }
     return acc;
 }
+// (The points a full queue sent to the on-the-spot path all lie BEHIND the column's queued entries, so for them the
+// correction reduces to one factor, S_e -> S_e (1 - tau sum_p d_p).  Applying it -- the column's two-moment sums then have
+// to stay live across the refinement pass -- cost 2 us per call in spills for 4.8x -> 2.3x on the one fuzz case that
+// needs it (a column grazing a big object at tau = 3, more gradient points than queue slots): not taken)
 // 3. every entry: forward redone in fp32 for the ratios the backward needs (not amplified by k); weight o (1 - o) and
 // suffix weight from the queue.  sign = sign(depth - target) of the column.
 template <bool FIX>

@@ -1637,7 +1637,7 @@ static int implicit_loss_impl(const void* pred, int pred_dtype, int batch, int n
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Grid g = make_grid(n, step, z0);
     const Layout L = make_layout(n, grad_pred ? SQ_IMPB_CPT : SQ_IMPF_CPT);
-    const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, implicit_cull_bound(sharpness * kLog2e), implicit_active_bits(sharpness * kLog2e, n)};
+    const ImplicitParams P{sharpness * kLog2e, tau * kLog2e, implicit_cull_bound(sharpness * kLog2e), implicit_active_bits(sharpness * kLog2e, n, batch)};
     if (depth_out)      // the column kernel writes the depth only where a column group can hold occupancy
         SQ_TRY(cudaMemsetAsync(depth_out, 0, sizeof(float) * (size_t)batch * n * n, st));
 #ifdef SQ_SKIP_COLUMN      // timing experiment: without the column kernel nobody restores the control block

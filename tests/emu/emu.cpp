@@ -32,7 +32,7 @@ double emu_log2_acc(double m) { return log2_acc(m, default_tabs()); }
 int emu_implicit(const double* pred, int B, int n, double step, double z0, const float* target, float tau, float k,
                  double* loss_out, double* grad /*[B,12] or null*/, float* depth_out /*or null*/) {
     Grid g = make_grid(n, step, z0);
-    ImplicitParams P{k * kLog2e, tau * kLog2e, implicit_cull_bound(k * kLog2e), implicit_active_bits(k * kLog2e, n)};
+    ImplicitParams P{k * kLog2e, tau * kLog2e, implicit_cull_bound(k * kLog2e), implicit_active_bits(k * kLog2e, n, B)};
     double total = 0.0;
     for (int b = 0; b < B; ++b) {
         double p[12]; for (int i = 0; i < 12; ++i) p[i] = pred[12 * b + i];
