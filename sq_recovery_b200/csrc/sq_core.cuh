@@ -774,13 +774,30 @@ SQ_HD void xfast_group_footprint(int n, int group, float& cx, float& cy, float& 
 
 #if defined(__CUDA_ARCH__)
 #define SQ_ANY(p) __any_sync(0xffffffffu, (p))
+#define SQ_BALLOT(p) __ballot_sync(0xffffffffu, (p))
 #define SQ_WARP_MAX(v) __reduce_max_sync(0xffffffffu, (v))
 #define SQ_WARP_MIN(v) __reduce_min_sync(0xffffffffu, (v))
 #else
 #define SQ_ANY(p) (p)
+#define SQ_BALLOT(p) ((p) ? 1u : 0u)          // host build: a "warp" of one lane
 #define SQ_WARP_MAX(v) (v)
 #define SQ_WARP_MIN(v) (v)
 #endif
+// bits of the lanes below this one (host build: none)
+SQ_HD unsigned lanes_below() {
+#if defined(__CUDA_ARCH__)
+    unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
+#else
+    return 0u;
+#endif
+}
+SQ_HD int popcount(unsigned m) {
+#if defined(__CUDA_ARCH__)
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
 
 // union over the warp of the lanes' ranges; (0, -1) when every lane's range is empty
 SQ_HD void warp_range(int n, int& c_lo, int& c_hi) {
@@ -844,40 +861,78 @@ struct ColGrad {       // two-moment accumulators of one column
 // (tau/n) sum_c cs_c is carried along and used when the depth is tiny (relative error < 0.4% there).
 // [c_lo, c_hi]: the (warp-uniform) z range to walk, from column_range() / warp_range().
 // running state of one column walk
-// Per-lane queue of gradient-carrying points (SQ_BWD_COMPACT), structure of arrays; entry e of this lane sits at
-// index e * stride (stride 32 in the kernels: one column of the warp's arrays per lane; 1 in the host build).
+// The warp's pool of gradient-carrying points (SQ_BWD_COMPACT), structure of arrays, `cap` slots shared by the warp's 32
+// columns.  During the walk the lanes whose point carries gradient append to it together (two ballots per plane that has
+// any): points near the surface (|x| < kRefine, re-evaluated in fp64 later) fill the pool from the FRONT, the others from the
+// BACK, so after the walk the two lists are already compact -- entries [0, nr) and (top, cap - 1] -- and are dealt out to the
+// lanes by index: no per-lane counts, no scan, no index list.  A column that grazes the surface for dozens of planes simply
+// takes more of the pool (it was a 15-deep queue per lane until round 2's last third; columns with more gradient points than
+// that fell back to the unrefined on-the-spot path -- the one parity outlier of the fuzz).  Only when a whole plane's new
+// points do not fit any more (more than `cap` gradient points in one 32-column group, or more than 255 of them near the
+// surface) do those points take the on-the-spot path.
+//
+// An entry's plane index is a small integer in a float (or cf0 < 1 for plane 0): its low 13 mantissa bits are free and carry
+// the lane of the entry's column (5 bits) and, for front entries, the previous front entry of the same column (8 bits,
+// kNoLink = none) -- the chain queue_suffix_weight() follows.  Grids beyond 1024 planes get no pool (cap = 0).
 struct BwdQueue {
-    float* cf;       // plane "index" of the point
-    float* pre;      // sum of T in front of it since the column's first gradient-carrying point; later: its suffix weight
-    float* x;        // the weight o (1 - o) = eo o^2 of the point; for entries in rmask the log2 odds x = k log2(e) (F - 1)
+    float* cf;       // plane "index" of the point | tag (entry_cf / entry_lane / entry_link)
+    float* pre;      // sum of T in front of it since its column's first gradient-carrying point
+    float* x;        // the weight o (1 - o) = eo o^2 of the point; for front entries the log2 odds x = k log2(e) (F - 1)
                      // the scan used, replaced by the weight at the fp64-refined x in queue_refine_entry()
-    float* d;        // refined entries: occupancy correction o(x refined) - o(x scan)
-    int stride;
+    float* d;        // front entries: occupancy correction o(x refined) - o(x scan)
+    int cap;         // slots (kernels: kBwdPool; host build: settable, to exercise the overflow path)
+    int lane;        // this thread's lane (host build: the column's slot in its group of 32)
+    unsigned where;  // kernels: shared-memory address of cf[0] (32-byte aligned; pre, x, d follow at kBwdPool floats each) | lane
 };
+constexpr int kNoLink = 255;
+constexpr unsigned kTagMask = 0x1fffu;
+constexpr int kPoolMaxPlanes = 1024;
+
+SQ_HD unsigned f32_bits(float v) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(v);
+#else
+    unsigned u; memcpy(&u, &v, 4); return u;
+#endif
+}
+SQ_HD float bits_f32(unsigned u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float v; memcpy(&v, &u, 4); return v;
+#endif
+}
+SQ_HD float entry_cf(const Sample& S, float tagged) {
+    const float cf = bits_f32(f32_bits(tagged) & ~kTagMask);
+    return cf < 1.0f ? S.cf0 : cf;                       // plane 0: cf0 is not an integer, its low bits were not free
+}
+SQ_HD int entry_lane(float tagged) { return (int)(f32_bits(tagged) & 31u); }
+SQ_HD int entry_link(float tagged) { return (int)((f32_bits(tagged) >> 5) & 255u); }
 
 struct ColState {
     float csl, cssum, tsum, psh, seen, T;
-    // SQ_BWD_COMPACT: this lane's queue, entries queued, whether a point had to be handled on the spot because the
-    // queue was full, and which entries get the fp64 re-evaluation (|x| < kRefine)
+    // SQ_BWD_COMPACT: the warp's pool, front entries so far and the next free back slot (both warp-uniform), this column's
+    // latest front entry, whether a point of this column had to be handled on the spot because the pool was full
     BwdQueue q;
-    int qn;
+    int nr, top, head;
     bool spilled;
-    unsigned rmask;
 };
 
 // SQ_BWD_COMPACT.  The backward block runs for the whole warp as soon as ONE lane carries gradient, and the surface
 // crosses the 32 columns of a patch on different planes: 5.7 of 32 lanes do on average (tools/timeline.py).  So during
-// the walk a gradient-carrying lane only notes (plane, prefix of T) in a small shared-memory queue; after the walk --
-// when the column's suffix weight U and the sign of (depth - target) are known -- the queued points of all 32 columns
+// the walk a gradient-carrying lane only notes (plane, prefix of T) in the warp's shared-memory pool; after the walk --
+// when the column's suffix weight U and the sign of (depth - target) are known -- the pooled points of all 32 columns
 // are dealt out evenly to the lanes, which redo the forward for their point and run the backward once, weighted,
-// straight into the item's sums.  A lane whose queue is full falls back to the on-the-spot two-moment path.
+// straight into the item's sums.  Points that find the pool full fall back to the on-the-spot two-moment path.
 #if !defined(SQ_NO_BWD_COMPACT) && !defined(SQ_BWD_COMPACT)
 #define SQ_BWD_COMPACT 1
 #endif
 #ifndef SQ_BWD_DEPTH
-#define SQ_BWD_DEPTH 15       // 15 (not 16): five blocks' queues fit one SM's shared memory (sqloss.cu SQ_IMPB_MINB)
+#define SQ_BWD_DEPTH 15       // pool slots per lane; 15 (not 16): five blocks' pools fit one SM's shared memory (sqloss.cu SQ_IMPB_MINB)
 #endif
 constexpr int kBwdDepth = SQ_BWD_DEPTH;
+constexpr int kBwdPool = kBwdDepth * 32;      // slots of a warp's pool
+
 
 // geometry + forward chain + occupancy of one plane (independent of the scan state: two planes can be in flight)
 struct Plane { Fwd f; float x, eo, o, cf; };
@@ -969,28 +1024,52 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
     st.T = ex2(st.csl);
     if (BWD) {
         const bool active = (fabsf(p.x) < P.kact) && (st.csl > -kDeep);
-        if (SQ_ANY(active)) {
+        const unsigned ma = SQ_BALLOT(active);
+        if (ma) {
 #if defined(SQ_BWD_HOOK) && defined(__CUDA_ARCH__)
             SQ_BWD_HOOK(active);                // debug builds: statistics of how many lanes carry gradient
 #endif
             bool now = active;                  // lanes whose point is handled on the spot
+            bool any_now = true;                // warp-uniform: does any lane have one
 #if defined(SQ_BWD_COMPACT)
             if (QUEUE) {
-                const bool shell = fabsf(p.x) < kRefine;
-                const bool room = st.qn < kBwdDepth;
-                if (active && room) {
-                    const int at = st.qn * st.q.stride;
-                    st.q.cf[at] = p.cf;             // plane
-                    st.q.pre[at] = st.psh;          // T in front of it since the first active point
-                    st.q.x[at] = shell ? p.x : p.eo * p.o * p.o;     // refined later: x; else the weight o (1 - o) itself
-                    st.rmask |= (shell ? 1u : 0u) << st.qn;
-                    ++st.qn;
-                    st.seen = 1.0f;
+                // all active lanes of this plane append together, in lane order: front slots for the points near the
+                // surface, back slots for the others
+                const bool shell = active && fabsf(p.x) < kRefine;
+                const unsigned ms = SQ_BALLOT(shell), mp = ma ^ ms;
+                const int nr1 = st.nr + popcount(ms), top1 = st.top - popcount(mp);
+                if (nr1 <= top1 + 1 && nr1 < kNoLink) {        // warp-uniform: they all fit
+                    if (active) {
+#if defined(__CUDA_ARCH__)
+                        // `where` = the pool's shared-memory address | this lane: one register, opaque to the compiler --
+                        // left to itself it rebuilds address, lane and lane mask from special registers at every append
+                        // (three S2R and six more instructions, measured 3 k cycles per warp)
+                        const unsigned lane_ = st.q.where & 31u;
+                        const int rank = popcount((shell ? ms : mp) & ((1u << lane_) - 1u));
+                        const int at = shell ? st.nr + rank : st.top - rank;
+                        const unsigned tag = lane_ | ((unsigned)(shell ? st.head : kNoLink) << 5);
+                        const unsigned addr = (st.q.where & ~31u) + 4u * (unsigned)at;
+                        asm volatile("st.shared.b32 [%0], %1;\n\tst.shared.f32 [%0 + %4], %2;\n\tst.shared.f32 [%0 + %5], %3;"
+                                     :: "r"(addr), "r"((f32_bits(p.cf) & ~kTagMask) | tag), "f"(st.psh),
+                                        "f"(shell ? p.x : p.eo * p.o * p.o), "n"(4 * kBwdPool), "n"(8 * kBwdPool) : "memory");
+#else
+                        const int rank = popcount((shell ? ms : mp) & lanes_below());
+                        const int at = shell ? st.nr + rank : st.top - rank;
+                        const unsigned tag = (unsigned)st.q.lane | ((unsigned)(shell ? st.head : kNoLink) << 5);
+                        st.q.cf[at] = bits_f32((f32_bits(p.cf) & ~kTagMask) | tag);    // plane | lane | previous front entry of the column
+                        st.q.pre[at] = st.psh;                            // T in front of it since the first active point
+                        st.q.x[at] = shell ? p.x : p.eo * p.o * p.o;      // refined later: x; else the weight o (1 - o) itself
+#endif
+                        st.head = shell ? at : st.head;
+                        st.seen = 1.0f;
+                    }
+                    st.nr = nr1; st.top = top1;
+                    now = false; any_now = false;
+                } else {
+                    st.spilled = st.spilled || active;
                 }
-                now = active && !room;
-                st.spilled = st.spilled || now;
             }
-            if (SQ_ANY(now))
+            if (any_now)
 #endif
             {
 #if defined(__CUDA_ARCH__)
@@ -1027,7 +1106,7 @@ SQ_HD void queue_store_refined(const BwdQueue& q, int at, float x0, float x1) {
 SQ_HD void queue_refine_entry(const Sample& S, double step, float kl, const BwdQueue& q, int at,
                               double b0, double b1, double b2, const RefTabs& tb) {
     const float x0 = q.x[at];
-    queue_store_refined(q, at, x0, refined_x(S, step, kl, b0, b1, b2, q.cf[at], tb));
+    queue_store_refined(q, at, x0, refined_x(S, step, kl, b0, b1, b2, entry_cf(S, q.cf[at]), tb));
 }
 // 2. suffix weight of entry e of a column, S_e = U - prefix_e, corrected to first order for the occupancy changes of the
 // column's refined entries.  T_c = exp(-tau cs_c) and cs_c sums the occupancies at or in front of c, so with
@@ -1035,22 +1114,19 @@ SQ_HD void queue_refine_entry(const Sample& S, double step, float kl, const BwdQ
 //   S_e -> S_e - tau ( S_e sum_{p <= e} d_p  +  sum_{p > e} d_p S_p ).
 // The occupancy the scan saw carries the fp32 chain's error in x (~1e-4 at k = 260), and through tau cs it reaches the
 // weight of EVERY point behind; measured (tests/emu, profiles/parity_sweep_r02.json) this is the larger part of the
-// fp32 gradient error.  Evaluated per dealt entry by a loop over the column's refined entries (one to three, typically:
-// the planes where the column crosses the surface); `col` = index of the column's entry 0 in the queue arrays.
-SQ_HD int lowest_bit(unsigned m) {
-#if defined(__CUDA_ARCH__)
-    return __ffs((int)m) - 1;
-#else
-    return __builtin_ctz(m);
-#endif
-}
-SQ_HD float queue_suffix_weight(const BwdQueue& q, int col, int e, unsigned rmask, float U, float tau) {
-    const float Se = U - q.pre[col + e * q.stride];
-    float a = 0.f, b = 0.f;                                  // sum of d over refined entries at or before e; sum of d S behind e
-    for (unsigned m = rmask; m; m &= m - 1u) {
-        const int ei = lowest_bit(m), at = col + ei * q.stride;
-        const float d = q.d[at];
-        if (ei <= e) a += d; else b = fmaf(d, U - q.pre[at], b);
+// fp32 gradient error.  Evaluated per dealt entry by a loop over the front entries of the entry's column (one to three,
+// typically: the planes where the column crosses the surface), which are chained through `meta` from the column's latest
+// one (`head`) back; the walk goes down the planes, so "at or before e" is "plane index not below e's".
+SQ_HD float queue_suffix_weight(const BwdQueue& q, int at, int head, float U, float tau) {
+    // (plane order is read off the tagged values: the tag sits below the plane's bits, and two entries of one column are on
+    // different planes unless they are the same entry)
+    const float Se = U - q.pre[at];
+    const unsigned cfe = f32_bits(q.cf[at]) | kTagMask;
+    float a = 0.f, b = 0.f;                                  // sum of d over front entries at or before e; sum of d S behind e
+    for (int r = head; r != kNoLink; ) {
+        const float tagged = q.cf[r], d = q.d[r], Sr = U - q.pre[r];
+        if ((f32_bits(tagged) | kTagMask) >= cfe) a += d; else b = fmaf(d, Sr, b);
+        r = entry_link(tagged);
     }
     return Se - tau * fmaf(a, Se, b);
 }
@@ -1059,18 +1135,13 @@ SQ_HD float queue_suffix_weight(const BwdQueue& q, int col, int e, unsigned rmas
 // At 1e-7 it is invisible in one pixel, but it has the sign of the MUFU lg2 bias on every surface pixel, and for an object
 // that fills the image and a prediction close to the target (loss ~ 3e-3) it is 2e-5 of the loss (measured); the loss
 // tolerance is rtol 1e-5.  Returns sum d_p S_p for one column (its owner adds sign * tau / n * this to the loss).
-SQ_HD float queue_depth_shift(const BwdQueue& q, int col, unsigned rmask, float U) {
+SQ_HD float queue_depth_shift(const BwdQueue& q, int head, float U) {
     float acc = 0.f;
-    for (unsigned m = rmask; m; m &= m - 1u) {
-        const int at = col + lowest_bit(m) * q.stride;
-        acc = fmaf(q.d[at], U - q.pre[at], acc);
-    }
+    for (int r = head; r != kNoLink; r = entry_link(q.cf[r])) acc = fmaf(q.d[r], U - q.pre[r], acc);
     return acc;
 }
-// (The points a full queue sent to the on-the-spot path all lie BEHIND the column's queued entries, so for them the
-// correction reduces to one factor, S_e -> S_e (1 - tau sum_p d_p).  Applying it -- the column's two-moment sums then have
-// to stay live across the refinement pass -- cost 2 us per call in spills for 4.8x -> 2.3x on the one fuzz case that
-// needs it (a column grazing a big object at tau = 3, more gradient points than queue slots): not taken)
+// (The points a full pool sends to the on-the-spot path get neither the refinement nor this correction; with 480 slots per
+// 32-column group that takes more gradient points than any workload of the parity fuzz has.)
 // 3. every entry: forward redone in fp32 for the ratios the backward needs (not amplified by k); weight o (1 - o) and
 // suffix weight from the queue.  sign = sign(depth - target) of the column.
 template <bool FIX>
@@ -1093,16 +1164,18 @@ SQ_HD void queue_entry_backward(const Sample& S, const float* bh, const float* b
 #endif
 
 template <bool BWD, bool FIX = true, bool QUEUE = false>
-// QUEUE (SQ_BWD_COMPACT): bwd_q / U_out / qn_out / spilled_out / rmask_out are used (see ColState); colgrad11 then holds
-// only what was handled on the spot.
+// QUEUE (SQ_BWD_COMPACT): bwd_q / U_out / nr_io / top_io / spilled_out / head_out are used (see ColState; nr_io, top_io: the
+// pool's front count and next free back slot, in and out -- the kernels start every column group at 0 and cap - 1, the host
+// build carries them from column to column of a group); colgrad11 then holds only what was handled on the spot.
 SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams& P,
                             const float* bh, const float* bl, int c_lo, int c_hi, int lane_lo, float* colgrad11,
-                            const BwdQueue* bwd_q = nullptr, float* U_out = nullptr, int* qn_out = nullptr,
-                            bool* spilled_out = nullptr, unsigned* rmask_out = nullptr) {
+                            const BwdQueue* bwd_q = nullptr, float* U_out = nullptr, int* nr_io = nullptr, int* top_io = nullptr,
+                            bool* spilled_out = nullptr, int* head_out = nullptr) {
     // planes in front of the range: o = 0, cs = 0, T = 1 each
     ColState st;
-    if (QUEUE) st.q = *bwd_q; else { st.q.cf = st.q.pre = st.q.x = st.q.d = nullptr; st.q.stride = 0; }
-    st.qn = 0; st.spilled = false; st.rmask = 0u;
+    if (QUEUE) { st.q = *bwd_q; st.nr = *nr_io; st.top = *top_io; }
+    else { st.q.cf = st.q.pre = st.q.x = st.q.d = nullptr; st.q.cap = 0; st.q.lane = 0; st.q.where = 0u; st.nr = 0; st.top = -1; }
+    st.spilled = false; st.head = kNoLink;
     st.csl = 0.f;                                     // -tau log2(e) cs
     st.T = 1.0f;                                      // 2^csl
     st.tsum = (float)(g.n - 1 - c_hi);
@@ -1158,7 +1231,7 @@ SQ_HD float implicit_column(const Sample& S, const Grid& g, const ImplicitParams
     st.cssum = fmaf(nb, st.csl, st.cssum);
     if (BWD) {
         const float U = fmaf(nb * st.seen, st.T, st.psh);
-        if (QUEUE) { *U_out = U; *qn_out = st.qn; *spilled_out = st.spilled; *rmask_out = st.rmask; }
+        if (QUEUE) { *U_out = U; *nr_io = st.nr; *top_io = st.top; *spilled_out = st.spilled; *head_out = st.head; }
         for (int i = 0; i < 3; ++i) {
             colgrad11[i]     = fmaf(U, cg.gs0[i], -cg.gs1[i]);
             colgrad11[3 + i] = fmaf(U, cg.gz0[i], -cg.gz1[i]);

@@ -727,9 +727,9 @@ __device__ unsigned long long g_phase[8];
 #ifndef SQ_EARLY_MARGIN      // measured (profiles/tune_r02.txt run k): margins 1..3 are 1-2 us SLOWER per call than none -> off
 #define SQ_EARLY_MARGIN 0
 #endif
-// dynamic shared memory of the fwd+bwd kernel, per warp: 4 queue arrays + 11 x 32 column values + the deal-out list
-constexpr size_t kImplicitBwdSmemPerWarp = (size_t)kBwdDepth * 32 * (4 * sizeof(float) + sizeof(unsigned short)) + 11 * 32 * sizeof(float);
-static_assert(kImplicitBwdSmemPerWarp % 16 == 0, "per-warp regions stay 16-byte aligned");
+// dynamic shared memory of the fwd+bwd kernel, per warp: the pool's 4 float arrays + 11 x 32 column values
+constexpr size_t kImplicitBwdSmemPerWarp = (size_t)kBwdPool * 4 * sizeof(float) + 11 * 32 * sizeof(float);
+static_assert(kImplicitBwdSmemPerWarp % 32 == 0, "per-warp regions stay 32-byte aligned (BwdQueue::where carries the lane in its low bits)");
 
 template <bool BWD, int THREADS, int MINB, int CPTMAX>      // CPTMAX: upper limit of L.cpt
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -739,21 +739,20 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                 const int* __restrict__ col_off, float* __restrict__ partials, float* __restrict__ depth_out) {
     __shared__ Sample Ssh[THREADS / 32];
 #if SQ_TILE_ALIAS && defined(SQ_BWD_COMPACT)
-    // the fwd+bwd kernel's reduction tile lives in the warp's queue arrays, which are dead by the time the item's sums
+    // the fwd+bwd kernel's reduction tile lives in the warp's pool arrays, which are dead by the time the item's sums
     // are put there (one column group per item only): shared memory for 5 blocks per SM
     static_assert(!BWD || CPTMAX == 1, "SQ_TILE_ALIAS needs one column group per work item");
-    static_assert(4 * kBwdDepth * 32 >= kRedFloats, "queue arrays too small to hold the tile");
+    static_assert(4 * kBwdPool >= kRedFloats, "pool arrays too small to hold the tile");
     __shared__ __align__(16) float tiles_static[BWD ? 1 : THREADS / 32][kRedFloats];
 #else
     __shared__ __align__(16) float tiles_static[THREADS / 32][kRedFloats];
 #endif
-#ifdef SQ_BWD_COMPACT       // per warp, in dynamic shared memory (BWD only; implicit_bwd_smem_bytes): the queued gradient-carrying
-                            // points (BwdQueue arrays), per-column data for them, the deal-out list
-    constexpr int kQN = kBwdDepth * 32;
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+#ifdef SQ_BWD_COMPACT       // per warp, in dynamic shared memory (BWD only; implicit_bwd_smem_bytes): the pool of gradient-carrying
+                            // points (BwdQueue arrays), per-column data for them
+    constexpr int kQN = kBwdPool;
+    extern __shared__ __align__(32) unsigned char dyn_smem[];
     float* const qbuf = reinterpret_cast<float*>(dyn_smem + (size_t)(threadIdx.x >> 5) * kImplicitBwdSmemPerWarp);      // [4][kQN]
     float* const colinfo_w = qbuf + 4 * kQN;                                                                         // [11][32]
-    unsigned short* const qmap_w = reinterpret_cast<unsigned short*>(colinfo_w + 11 * 32);                            // [kQN]
 #endif
 #if SQ_TILE_ALIAS && defined(SQ_BWD_COMPACT)
     float* const tile_w = BWD ? qbuf : tiles_static[threadIdx.x >> 5];
@@ -882,9 +881,12 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #ifndef SQ_FIXHOIST      // hoisting the exact-zero fix-up out of the walk (two copies of the loop): measured 1 us
                          // SLOWER per call once everything else was in place (profiles/tune_r01.txt) -> off
 #ifdef SQ_BWD_COMPACT
-                float U = 0.f; int qn = 0; bool spilled = false; unsigned rmask = 0u;
-                const BwdQueue qlane{qbuf + lane, qbuf + kQN + lane, qbuf + 2 * kQN + lane, qbuf + 3 * kQN + lane, 32};
-                depth = implicit_column<BWD, true, BWD>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg, &qlane, &U, &qn, &spilled, &rmask);
+                const int pool = g.n <= kPoolMaxPlanes ? kQN : 0;      // (the entries' tags need the plane index below 1024)
+                float U = 0.f; int nr = 0, top = pool - 1, head = kNoLink; bool spilled = false;
+                unsigned where = (unsigned)__cvta_generic_to_shared(qbuf) | (unsigned)lane;
+                asm volatile("" : "+r"(where));                       // kept in a register (sq_core.cuh plane_scan)
+                const BwdQueue qwarp{qbuf, qbuf + kQN, qbuf + 2 * kQN, qbuf + 3 * kQN, pool, lane, where};
+                depth = implicit_column<BWD, true, BWD>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg, &qwarp, &U, &nr, &top, &spilled, &head);
 #else
                 depth = implicit_column<BWD, true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg);
 #endif
@@ -928,15 +930,9 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                         loss_sum += fabsf(diff) - fabsf(tv);
                         wsg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
                     }
-                    if (wsg == 0.f) { qn = 0; rmask = 0u; }    // its points carry no gradient after all
-                    // entries to refine in fp64 first in the deal-out list, the others behind them: one scan for both counts
-                    const int nr = __popc(rmask);
-                    const int cnt = (nr << 16) | (qn - nr);
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t_; }
-                    const int last = __shfl_sync(0xffffffffu, incl, 31);
-                    const int total_r = last >> 16, total = total_r + (last & 0xffff);
+                    // the pool's front (to refine in fp64) and back entries are already compact lists: counts are warp-uniform.
+                    // (Entries of a column whose sign turned out 0 stay in the lists and contribute exactly 0.)
+                    const int total_r = nr, total = nr + (pool - 1 - top);
                     const bool any_spill = __any_sync(0xffffffffu, spilled && wsg != 0.f);
 #ifdef SQ_ITEMLOG
                     il_q += total + (any_spill ? 1000 : 0); il_qr += total_r;
@@ -958,42 +954,17 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                             ci[0 * 32 + lane] = bh[0]; ci[1 * 32 + lane] = bh[1]; ci[2 * 32 + lane] = bh[2];
                             ci[3 * 32 + lane] = bl[0]; ci[4 * 32 + lane] = bl[1]; ci[5 * 32 + lane] = bl[2];
                             ci[6 * 32 + lane] = wsg; ci[7 * 32 + lane] = dxy[0]; ci[8 * 32 + lane] = dxy[1];
-                            ci[9 * 32 + lane] = U; ci[10 * 32 + lane] = __uint_as_float(rmask);
-                            {
-                                int at_r = (incl - cnt) >> 16, at_p = total_r + ((incl - cnt) & 0xffff);
-                                for (int e = 0; e < qn; ++e) {
-                                    const unsigned short id = (unsigned short)((lane << 8) | e);
-                                    if ((rmask >> e) & 1u) qmap_w[at_r++] = id; else qmap_w[at_p++] = id;
-                                }
-                            }
+                            ci[9 * 32 + lane] = U; ci[10 * 32 + lane] = __int_as_float(head);
                             __syncwarp();
-                            const BwdQueue qwarp{qbuf, qbuf + kQN, qbuf + 2 * kQN, qbuf + 3 * kQN, 32};
                             SQ_COUNT_HOOK(6, total); SQ_COUNT_HOOK(7, total_r);
                             SQ_COUNT_HOOK(3, (total_r + 31) / 32); SQ_COUNT_HOOK(2, (total + 31) / 32);
                             SQ_PH(5);
                             // 1. the entries near the surface, dealt out evenly: x in fp64 (sq_core.cuh "fp64 refinement")
-                            // (SQ_REFINE_ILP2: two rounds in flight where there are that many -- measured 6 us SLOWER per call,
+                            // (two rounds in flight where there are that many: measured 6 us SLOWER per call,
                             // profiles/tune_r02.txt: the second chain's registers cost the walk its allocation)
-                            int jr = lane;
-#ifdef SQ_REFINE_ILP2
-                            for (; jr - lane + 32 < total_r; jr += 64) {
-                                const bool has1 = jr + 32 < total_r;
-                                const int m0 = qmap_w[jr], l0 = m0 >> 8, a0 = (m0 & 255) * 32 + l0;
-                                const int m1 = has1 ? qmap_w[jr + 32] : m0, l1 = m1 >> 8, a1 = (m1 & 255) * 32 + l1;
-                                const float x0 = qwarp.x[a0], x1 = qwarp.x[a1];
-                                const float r0 = refined_x(S, g.step, P.kl, f2d(ci[0 * 32 + l0]) + f2d(ci[3 * 32 + l0]),
-                                                           f2d(ci[1 * 32 + l0]) + f2d(ci[4 * 32 + l0]), f2d(ci[2 * 32 + l0]) + f2d(ci[5 * 32 + l0]),
-                                                           qwarp.cf[a0], tb);
-                                const float r1 = refined_x(S, g.step, P.kl, f2d(ci[0 * 32 + l1]) + f2d(ci[3 * 32 + l1]),
-                                                           f2d(ci[1 * 32 + l1]) + f2d(ci[4 * 32 + l1]), f2d(ci[2 * 32 + l1]) + f2d(ci[5 * 32 + l1]),
-                                                           qwarp.cf[a1], tb);
-                                queue_store_refined(qwarp, a0, x0, r0);
-                                if (has1) queue_store_refined(qwarp, a1, x1, r1);
-                            }
-#endif
-                            for (; jr < total_r; jr += 32) {
-                                const int m_ = qmap_w[jr], l_ = m_ >> 8, e_ = m_ & 255;
-                                queue_refine_entry(S, g.step, P.kl, qwarp, e_ * 32 + l_,
+                            for (int jr = lane; jr < total_r; jr += 32) {
+                                const int l_ = entry_lane(qwarp.cf[jr]);
+                                queue_refine_entry(S, g.step, P.kl, qwarp, jr,
                                                    f2d(ci[0 * 32 + l_]) + f2d(ci[3 * 32 + l_]), f2d(ci[1 * 32 + l_]) + f2d(ci[4 * 32 + l_]),
                                                    f2d(ci[2 * 32 + l_]) + f2d(ci[5 * 32 + l_]), tb);
                             }
@@ -1002,7 +973,7 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                             const float tau = P.tl * (float)kLn2;
 #ifdef SQ_DEPTH_SHIFT       // the refined occupancies' first-order effect on the rendered depth: measured below the loss's other
                             // fp32 errors on every workload (profiles/tune_r02.txt) and 2 us per call -> off
-                            if (rmask) loss_sum = fmaf(wsg * tau * g.inv_n, queue_depth_shift(qlane, 0, rmask, U), loss_sum);
+                            if (head != kNoLink) loss_sum = fmaf(wsg * tau * g.inv_n, queue_depth_shift(qwarp, head, U), loss_sum);
 #endif
 #ifndef SQ_EARLY_CLAIM
                             if (staged && wp.claim_finish()) pre.fetch(samples + L.sample_of(wp.next), lane);
@@ -1011,10 +982,13 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
                             // entry's column), forward redone, backward; two rounds in flight (two independent MUFU chains)
                             auto dealt = [&](int j, Bwd& bq, float& cfq, float& dx_, float& dy_) {
                                 const bool has = j < total;
-                                const int m_ = has ? qmap_w[j] : 0, l_ = m_ >> 8, e_ = m_ & 255, at = e_ * 32 + l_;
-                                // idle lane of the last round: a slot that may never have been written
-                                const float cf_ = has ? qwarp.cf[at] : 1.0f, x_ = has ? qwarp.x[at] : 0.0f;
-                                const float sw_ = has ? queue_suffix_weight(qwarp, l_, e_, __float_as_uint(ci[10 * 32 + l_]), ci[9 * 32 + l_], tau) : 0.0f;
+                                // front entries first, then the back ones from the pool's end; idle lane of the last round: a
+                                // slot that may never have been written
+                                const int at = has ? (j < total_r ? j : kQN - 1 - (j - total_r)) : 0;
+                                const float tagged = has ? qwarp.cf[at] : 1.0f, x_ = has ? qwarp.x[at] : 0.0f;
+                                const int l_ = entry_lane(tagged);      // (1.0f: lane 0, plane 1)
+                                const float cf_ = entry_cf(S, tagged);
+                                const float sw_ = has ? queue_suffix_weight(qwarp, at, __float_as_int(ci[10 * 32 + l_]), ci[9 * 32 + l_], tau) : 0.0f;
                                 const float cbh[3] = {ci[0 * 32 + l_], ci[1 * 32 + l_], ci[2 * 32 + l_]};
                                 const float cbl[3] = {ci[3 * 32 + l_], ci[4 * 32 + l_], ci[5 * 32 + l_]};
                                 queue_entry_backward<true>(S, cbh, cbl, cf_, x_, sw_, ci[6 * 32 + l_], has, bq);

@@ -17,12 +17,13 @@ static void acc_to_double(const Acc& a, double* d) {
     d[15] += a.ge[0]; d[16] += a.ge[1]; d[17] += a.loss;
 }
 
-static int g_emu_refine = 1, g_emu_queue = 1;
+static int g_emu_refine = 1, g_emu_queue = 1, g_emu_pool = kBwdPool;
 
 extern "C" {
 
-void emu_set_refine(int on) { g_emu_refine = on; }     // fp64 refinement of the queued points near the surface
+void emu_set_refine(int on) { g_emu_refine = on; }     // fp64 refinement of the pooled points near the surface
 void emu_set_queue(int on) { g_emu_queue = on; }       // 0: every gradient point on the spot (two-moment path)
+void emu_set_pool(int slots) { g_emu_pool = slots > 0 && slots <= kBwdPool ? slots : kBwdPool; }   // small: exercises the overflow path
 
 // accuracy probes of the fp64 primitives
 double emu_exp2_acc(double y) { return exp2_acc(y, default_tabs()); }
@@ -38,44 +39,61 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
         double p[12]; for (int i = 0; i < 12; ++i) p[i] = pred[12 * b + i];
         SampleFull S; prep_sample(p, true, g, S);
         double accd[kAccN] = {0};
-        for (int ib = 0; ib < n; ++ib) for (int ia = 0; ia < n; ++ia) {
-            float bh[3], bl[3], cg[11];
-            column_base(S, g, ia, ib, bh, bl);
-            int c_lo, c_hi;
-            column_range(S, g, P.bound, bh, c_lo, c_hi);
-            warp_range(n, c_lo, c_hi);
-            // the kernels' compacted backward, one column at a time: walk with a queue of gradient-carrying points, fp64
-            // refinement of the entries near the surface, corrected suffix weights, backward per entry
-            float qcf[kBwdDepth], qpre[kBwdDepth], qx[kBwdDepth], qd[kBwdDepth];
-            const BwdQueue q{qcf, qpre, qx, qd, 1};
-            float U = 0.f; int qn = 0; bool spilled = false; unsigned rmask = 0u;
-            const int own_lo = c_hi >= c_lo ? c_lo : n;
-            const float depth = !grad ? implicit_column<false>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg)
-                              : g_emu_queue ? implicit_column<true, true, true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg, &q, &U, &qn, &spilled, &rmask)
-                                            : implicit_column<true>(S, g, P, bh, bl, c_lo, c_hi, own_lo, cg);
-            const int row = n - 1 - ib, col = ia;
-            if (depth_out) depth_out[(size_t)b * n * n + row * n + col] = depth;
-            const float tgt = target ? target[(size_t)b * n * n + row * n + col] : 0.f;
-            const float diff = depth - tgt;
-            Acc a; acc_zero(a);
-            a.loss = fabsf(diff);
-            if (grad) {
-                const float w = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                const float dx = (float)(grid_coord(g, ia) - S.t[0]), dy = (float)(grid_coord(g, ib) - S.t[1]);
-                if (!g_emu_queue || spilled) implicit_fold(a, cg, w, dx, dy);
-                if (g_emu_queue && w != 0.f && qn > 0) {
-                    if (!g_emu_refine) rmask = 0u;
-                    const double b0 = (double)bh[0] + (double)bl[0], b1 = (double)bh[1] + (double)bl[1], b2 = (double)bh[2] + (double)bl[2];
-                    for (int e = 0; e < qn; ++e) if ((rmask >> e) & 1u) queue_refine_entry(S, g.step, P.kl, q, e, b0, b1, b2, default_tabs());
-                    a.loss += w * tau * g.inv_n * queue_depth_shift(q, 0, rmask, U);
-                    for (int e = 0; e < qn; ++e) {
-                        Bwd bq;
-                        queue_entry_backward<true>(S, bh, bl, qcf[e], qx[e], queue_suffix_weight(q, 0, e, rmask, U, tau), w, true, bq);
-                        acc_add_point(a, bq, qcf[e], dx, dy);
+        // The kernels' compacted backward, one group of 32 columns (raster order) at a time: the columns walk one after the
+        // other here, all appending to the group's pool of gradient-carrying points (front: the entries near the surface,
+        // refined in fp64; back: the others), then refinement, corrected suffix weights and the backward per pooled entry.
+        for (int g0 = 0; g0 < n * n; g0 += 32) {
+            float qcf[kBwdPool], qpre[kBwdPool], qx[kBwdPool], qd[kBwdPool];
+            BwdQueue q{qcf, qpre, qx, qd, n <= kPoolMaxPlanes ? g_emu_pool : 0, 0, 0u};
+            int nr = 0, top = q.cap - 1;
+            float bh[32][3], bl[32][3], U[32], w[32], dx[32], dy[32];
+            int head[32];
+            Acc a[32];
+            const int cols = n * n - g0 < 32 ? n * n - g0 : 32;
+            for (int L = 0; L < cols; ++L) {
+                const int ib = (g0 + L) / n, ia = (g0 + L) - ib * n;
+                float cg[11];
+                column_base(S, g, ia, ib, bh[L], bl[L]);
+                int c_lo, c_hi;
+                column_range(S, g, P.bound, bh[L], c_lo, c_hi);
+                warp_range(n, c_lo, c_hi);
+                U[L] = 0.f; head[L] = kNoLink; bool spilled = false;
+                q.lane = L;
+                const int own_lo = c_hi >= c_lo ? c_lo : n;
+                const float depth = !grad ? implicit_column<false>(S, g, P, bh[L], bl[L], c_lo, c_hi, own_lo, cg)
+                                  : g_emu_queue ? implicit_column<true, true, true>(S, g, P, bh[L], bl[L], c_lo, c_hi, own_lo, cg, &q, &U[L], &nr, &top, &spilled, &head[L])
+                                                : implicit_column<true>(S, g, P, bh[L], bl[L], c_lo, c_hi, own_lo, cg);
+                const int row = n - 1 - ib, col = ia;
+                if (depth_out) depth_out[(size_t)b * n * n + row * n + col] = depth;
+                const float tgt = target ? target[(size_t)b * n * n + row * n + col] : 0.f;
+                const float diff = depth - tgt;
+                acc_zero(a[L]);
+                a[L].loss = fabsf(diff);
+                w[L] = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                dx[L] = (float)(grid_coord(g, ia) - S.t[0]); dy[L] = (float)(grid_coord(g, ib) - S.t[1]);
+                if (grad && (!g_emu_queue || spilled)) implicit_fold(a[L], cg, w[L], dx[L], dy[L]);
+            }
+            if (grad && g_emu_queue) {
+                if (!g_emu_refine) {                               // front entries keep x: turn it into the weight, no correction
+                    for (int e = 0; e < nr; ++e) queue_store_refined(q, e, qx[e], qx[e]);
+                } else {
+                    for (int e = 0; e < nr; ++e) {
+                        const int L = entry_lane(qcf[e]);
+                        queue_refine_entry(S, g.step, P.kl, q, e, (double)bh[L][0] + (double)bl[L][0], (double)bh[L][1] + (double)bl[L][1],
+                                           (double)bh[L][2] + (double)bl[L][2], default_tabs());
                     }
                 }
+                for (int L = 0; L < cols; ++L) a[L].loss += w[L] * tau * g.inv_n * queue_depth_shift(q, head[L], U[L]);
+                const int np = q.cap - 1 - top;
+                for (int j = 0; j < nr + np; ++j) {
+                    const int at = j < nr ? j : q.cap - 1 - (j - nr), L = entry_lane(qcf[at]);
+                    const float cf = entry_cf(S, qcf[at]);
+                    Bwd bq;
+                    queue_entry_backward<true>(S, bh[L], bl[L], cf, qx[at], queue_suffix_weight(q, at, head[L], U[L], tau), w[L], true, bq);
+                    acc_add_point(a[L], bq, cf, dx[L], dy[L]);
+                }
             }
-            acc_to_double(a, accd);
+            for (int L = 0; L < cols; ++L) acc_to_double(a[L], accd);
         }
         total += accd[17] / ((double)n * n);
         if (grad) {

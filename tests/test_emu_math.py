@@ -157,3 +157,27 @@ def test_emulated_zero_planes():
         assert abs(l - g["implicit_per_sample"][i]) <= 1e-5 * g["implicit_per_sample"][i], i
         l, _ = E.explicit(g["true"][i:i + 1], g["pred"][i:i + 1], R + 1, 1 / R, 1e-4, want_grad=False)
         assert abs(l - g["explicit_per_sample"][i]) <= 1e-5 * g["explicit_per_sample"][i], i
+
+
+def test_emulated_pool_overflow_and_on_the_spot_paths():
+    """The warp's pool of gradient-carrying points (sq_core.cuh BwdQueue): with all 480 slots nothing overflows on these
+    inputs; with 8 slots per 32-column group most points take the on-the-spot two-moment path (no fp64 refinement, host libm
+    accuracy); with the pool off all do.  All three must agree with the reference within the tolerance, and the first two
+    must really have taken different paths."""
+    g = load_golden("random_s2_b4_r32.npz")
+    R = int(g["R"])
+    tgt = F.interpolate(torch.tensor(g["img"]), size=(R, R), mode="nearest")[:, 0].numpy()
+    lib = E.lib()
+    res = {}
+    try:
+        for name, (pool, queue) in (("full", (0, 1)), ("small", (8, 1)), ("off", (0, 0))):
+            lib.emu_set_pool(pool)
+            lib.emu_set_queue(queue)
+            l, gr, _ = E.implicit(g["pred_near"], tgt, R, 1 / (R - 1), 1e-4, 1.5, 260.0)
+            assert abs(l - g["implicit_t15_k260_near_loss"]) <= 1e-5 * g["implicit_t15_k260_near_loss"], name
+            assert tol(gr, g["implicit_t15_k260_near_grad"]) <= 1.0, name
+            res[name] = gr
+    finally:
+        lib.emu_set_pool(0)
+        lib.emu_set_queue(1)
+    assert not np.array_equal(res["full"], res["small"]) and not np.array_equal(res["small"], res["off"])

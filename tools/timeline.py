@@ -22,7 +22,8 @@ from sq_recovery_b200.functional import nearest_offsets
 defs = ["-DSQ_TIMELINE"] + [f"-D{d}" for d in sys.argv[1:]]
 out = "/tmp/libsq_timeline.so"
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-ftz=true", "-std=c++17",
-                       "-shared", "-Xcompiler", "-fPIC", "-o", out, os.path.join(ROOT, "sq_recovery_b200", "csrc", "sqloss.cu")] + defs)
+                       "-shared", "-Xcompiler", "-fPIC", "-o", out,
+                       os.path.join(ROOT, os.environ.get("SQ_SRC", os.path.join("sq_recovery_b200", "csrc")), "sqloss.cu")] + defs)
 h = ctypes.CDLL(out)
 for name, (res, args) in L0._PROTOS.items():
     fn = getattr(h, name); fn.restype, fn.argtypes = res, args
@@ -96,4 +97,4 @@ if "SQ_PHASES" in sys.argv[1:]:       # python tools/timeline.py SQ_PHASES: SM c
     tot = float(ph.sum())
     print(f"warp cycles per launch, all {len(buf)} warps: {tot / reps / 1e6:.2f} M  ({tot / reps / len(buf) / 1e3:.1f} k per warp)")
     for nme, c in zip(names, ph):
-        print(f"  {nme:52s} {100.0 * float(c) / tot:5.1f} %")
+        print(f"  {nme:52s} {100.0 * float(c) / tot:5.1f} %   {float(c) / reps / len(buf) / 1e3:6.2f} k cycles per warp")

@@ -24,11 +24,13 @@ dev = torch.device("cuda:0")
 
 
 def build(defs):
-    tag = defs.replace("=", "").replace(",", "_") or "default"
+    tag = defs.replace("=", "").replace(",", "_").replace("/", "_") or "default"
     out = f"/tmp/libsq_{tag}.so"
+    # "SRC=<dir>" among the definitions: build <dir>/sqloss.cu instead (A/B of two source trees on the same box)
+    src_dir = next((d[4:] for d in defs.split(",") if d.startswith("SRC=")), os.path.join("sq_recovery_b200", "csrc"))
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-ftz=true", "-std=c++17", "-shared",
-           "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-o", out, os.path.join(ROOT, "sq_recovery_b200", "csrc", "sqloss.cu")]
-    cmd += [f"-D{d}" for d in defs.split(",") if d]
+           "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-o", out, os.path.join(ROOT, src_dir, "sqloss.cu")]
+    cmd += [f"-D{d}" for d in defs.split(",") if d and not d.startswith("SRC=")]
     log = subprocess.run(cmd, capture_output=True, text=True)
     if log.returncode:
         print(log.stderr[-2000:]); raise SystemExit(1)
