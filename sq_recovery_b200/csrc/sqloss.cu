@@ -112,6 +112,8 @@ constexpr int kWarps = kThreads / 32;
 struct Layout {
     int n, patched, slots, cpt, rows_per_sample;
     int rows_shift;      // log2(rows_per_sample) when it is a power of two, else -1
+    int pw_shift;        // patched layout: log2(patches per row) when n / 8 is a power of two, else -1
+    int jq, jr;          // patched layout: rows_per_sample / (n / 8) and the remainder (per-step patch advance of ColIter)
     __host__ __device__ __forceinline__ void split(int item, int& b, int& chunk) const {
         if (rows_shift >= 0) { b = item >> rows_shift; chunk = item & (rows_per_sample - 1); }
         else { b = item / rows_per_sample; chunk = item - b * rows_per_sample; }
@@ -132,6 +134,13 @@ __host__ __device__ inline Layout make_layout(int n, int max_cpt) {
     L.rows_per_sample = (L.slots + per_item - 1) / per_item;
     L.rows_shift = -1;
     for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == L.rows_per_sample) L.rows_shift = sh;
+    L.pw_shift = -1; L.jq = L.jr = 0;
+    if (L.patched) {
+        const int pw = n >> 3;
+        for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == pw) L.pw_shift = sh;
+        L.jq = L.rows_per_sample / pw;
+        L.jr = L.rows_per_sample - L.jq * pw;
+    }
     return L;
 }
 
@@ -144,11 +153,11 @@ struct ColIter {
     __device__ __forceinline__ void init(const Layout& L, int first_group, int lane) {
         slot = first_group * 32 + lane;
         if (L.patched) {
-            const int pw = L.n >> 3, J = L.rows_per_sample;
-            pb = first_group / pw;                     // once per work item
+            const int pw = L.n >> 3;
+            pb = L.pw_shift >= 0 ? first_group >> L.pw_shift : first_group / pw;      // once per work item
             pa = first_group - pb * pw;
-            jq = J / pw;
-            jr = J - jq * pw;
+            jq = L.jq;
+            jr = L.jr;
             ia = (pa << 3) + (lane & 7);
             ib = (pb << 2) + (lane >> 3);
         } else {
