@@ -33,7 +33,10 @@ __device__ __forceinline__ float d2f(double a) { float y; asm volatile("cvt.rn.f
 __device__ __forceinline__ float i2f(int a) { float y; asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(y) : "r"(a)); return y; }
 __device__ __forceinline__ float fsel(float a, float b) { float y; asm volatile("{ .reg .pred p; setp.gt.f32 p, %1, %2; selp.f32 %0, %1, %2, p; }" : "=f"(y) : "f"(a), "f"(b)); return y; }
 
+__device__ __forceinline__ int popc(int a) { int y; asm volatile("popc.b32 %0, %1;" : "=r"(y) : "r"(a)); return y; }
+
 enum Op { EX2, LG2, RCP, MUFU_MIX, FFMA, FADD, FFMA2, FMNMX, FSEL, DFMA, D2F, I2F, SHFL,
+          POPC, EX2_POPC, VOTE, EX2_VOTE, REDUX, EX2_REDUX,     // what the pool appends of the column kernel add to the walk
           EX2_FFMA1, EX2_FFMA2, EX2_FFMA4, EX2_FFMA6, EX2_FFMA8, EX2_FFMA2X4, EX2_D2F, EX2_DFMA, EX2_FMNMX4, POW_CHAIN };
 
 // Each variant: ILP independent dependency chains, INNER steps per outer iteration.  "ops" counted per thread
@@ -76,6 +79,12 @@ __global__ void __launch_bounds__(256) bench_kernel(float* out, int iters, float
                 else if (OP == D2F) { v[j] = d2f(dv[j]); dv[j] += (double)k; acc += v[j]; }   // 1 cvt + 1 DADD + 1 FADD
                 else if (OP == I2F) { v[j] += i2f(iv[j]); iv[j] += k; }                        // 1 cvt + 1 FADD + 1 IADD
                 else if (OP == SHFL) v[j] = __shfl_xor_sync(0xffffffffu, v[j], 1);
+                else if (OP == POPC) iv[j] = popc(iv[j]) + k;                                  // 1 popc + 1 IADD
+                else if (OP == EX2_POPC) { v[j] = ex2f(v[j]); iv[j] = popc(iv[j]) + k; }
+                else if (OP == VOTE) iv[j] += (int)__ballot_sync(0xffffffffu, iv[j] & 1);      // 1 vote + setp + IADD
+                else if (OP == EX2_VOTE) { v[j] = ex2f(v[j]); iv[j] += (int)__ballot_sync(0xffffffffu, iv[j] & 1); }
+                else if (OP == REDUX) iv[j] = __reduce_add_sync(0xffffffffu, iv[j] & 3) + k;   // 1 redux + LOP + IADD
+                else if (OP == EX2_REDUX) { v[j] = ex2f(v[j]); iv[j] = __reduce_add_sync(0xffffffffu, iv[j] & 3) + k; }
                 else if (OP == EX2_FFMA1) { v[j] = ex2f(v[j]); v[j] = ffma(v[j], c1, c2); }
                 else if (OP == EX2_FFMA2) { v[j] = ex2f(v[j]); v[j] = ffma(v[j], c1, c2); v[j] = ffma(v[j], c1, c2); }
                 else if (OP == EX2_FFMA4) { v[j] = ex2f(v[j]);
@@ -163,6 +172,7 @@ int main(int argc, char** argv) {
     RUN(RCP, 1, 1, 0)
     RUN(FADD, 0, 1, 0) RUN(FFMA2, 0, 2, 0) RUN(FMNMX, 0, 0, 1) RUN(FSEL, 0, 0, 2)
     RUN(DFMA, 0, 0, 1) RUN(D2F, 0, 1, 2) RUN(I2F, 0, 1, 2) RUN(SHFL, 0, 0, 1)
+    RUN(POPC, 0, 0, 2) RUN(EX2_POPC, 1, 0, 2) RUN(VOTE, 0, 0, 3) RUN(EX2_VOTE, 1, 0, 3) RUN(REDUX, 0, 0, 3) RUN(EX2_REDUX, 1, 0, 3)
     RUN(EX2_FFMA1, 1, 1, 0) RUN(EX2_FFMA2, 1, 2, 0) RUN(EX2_FFMA4, 1, 4, 0) RUN(EX2_FFMA6, 1, 6, 0) RUN(EX2_FFMA8, 1, 8, 0)
     RUN(EX2_FFMA2X4, 1, 8, 0) RUN(EX2_D2F, 1, 1, 2) RUN(EX2_DFMA, 1, 0, 1) RUN(EX2_FMNMX4, 1, 0, 4) RUN(POW_CHAIN, 2, 2, 0)
     }

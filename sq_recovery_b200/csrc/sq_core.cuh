@@ -1037,7 +1037,10 @@ SQ_HD void plane_scan(const ImplicitParams& P, const Plane& p, ColState& st, Col
                 // surface, back slots for the others
                 const bool shell = active && fabsf(p.x) < kRefine;
                 const unsigned ms = SQ_BALLOT(shell), mp = ma ^ ms;
-                const int nr1 = st.nr + popcount(ms), top1 = st.top - popcount(mp);
+                // (POPC runs on the MUFU pipe at the MUFU rate -- csrc/peaks.cu EX2_POPC -- but taking the two counts from one
+                // REDUX of packed flags instead, which does not, measured no faster: profiles/tune_r02.txt run q)
+                const int cnt_r = popcount(ms), cnt_p = popcount(mp);
+                const int nr1 = st.nr + cnt_r, top1 = st.top - cnt_p;
                 if (nr1 <= top1 + 1 && nr1 < kNoLink) {        // warp-uniform: they all fit
                     if (active) {
 #if defined(__CUDA_ARCH__)
