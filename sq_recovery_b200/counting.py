@@ -24,8 +24,9 @@ _h = None
 #   refinement round  ex2, rcp + 9 fp64<->fp32 conversions                                                       = 11
 #   column group      11 conversions of the fp64 column base + 2 int->double grid coordinates + 3 int->float     = 16
 #   work item         sqrt (culling) + 3 conversions of the range bounds + 2 int->float grid coordinates         = 6
-# Validated against ncu (sm__inst_executed_pipe_xu of the committed capture): the model is 6-10 % below the hardware
-# count (profiles/implicit_kernel_ncu_summary_r02.json), i.e. the reported fraction is slightly conservative.
+# Validated against ncu (sm__inst_executed_pipe_xu of the committed capture): the model is 10 % below the hardware
+# count (profiles/implicit_kernel_ncu_summary_r02.json) -- most of the difference are the POPCs of the pool appends, which
+# share the pipe (profiles/peaks_r02.json EX2_POPC) but are overhead, not work -- i.e. the reported fraction is conservative.
 XU_PER_EVENT = {"plane_steps": 11, "spot_backward_blocks": 5, "dealout_rounds": 13, "refine_rounds": 11,
                 "column_groups": 16, "items": 6}
 NAMES = ("plane_steps", "spot_backward_blocks", "dealout_rounds", "refine_rounds", "items", "column_groups",

@@ -873,7 +873,8 @@ struct ColGrad {       // two-moment accumulators of one column
 //
 // An entry's plane index is a small integer in a float (or cf0 < 1 for plane 0): its low 13 mantissa bits are free and carry
 // the lane of the entry's column (5 bits) and, for front entries, the previous front entry of the same column (8 bits,
-// kNoLink = none) -- the chain queue_suffix_weight() follows.  Grids beyond 1024 planes get no pool (cap = 0).
+// kNoLink = none) -- the chain queue_suffix_weight() follows.  Grids beyond 1024 planes, or whose plane 0 sits a whole step or
+// more from the origin (cf0 >= 1: not a grid the reference's classes build), get no pool (cap = 0).
 struct BwdQueue {
     float* cf;       // plane "index" of the point | tag (entry_cf / entry_lane / entry_link)
     float* pre;      // sum of T in front of it since its column's first gradient-carrying point

@@ -890,7 +890,8 @@ implicit_kernel(const SampleFull* __restrict__ samples, Grid g, Layout L, Implic
 #ifndef SQ_FIXHOIST      // hoisting the exact-zero fix-up out of the walk (two copies of the loop): measured 1 us
                          // SLOWER per call once everything else was in place (profiles/tune_r01.txt) -> off
 #ifdef SQ_BWD_COMPACT
-                const int pool = g.n <= kPoolMaxPlanes ? kQN : 0;      // (the entries' tags need the plane index below 1024)
+                // (the entries' tags sit in the plane index's low mantissa bits: small integers, and plane 0's own "index" below 1)
+                const int pool = (g.n <= kPoolMaxPlanes && S.cf0 < 1.0f) ? kQN : 0;
                 float U = 0.f; int nr = 0, top = pool - 1, head = kNoLink; bool spilled = false;
                 unsigned where = (unsigned)__cvta_generic_to_shared(qbuf) | (unsigned)lane;
                 asm volatile("" : "+r"(where));                       // kept in a register (sq_core.cuh plane_scan)

@@ -44,7 +44,7 @@ int emu_implicit(const double* pred, int B, int n, double step, double z0, const
         // refined in fp64; back: the others), then refinement, corrected suffix weights and the backward per pooled entry.
         for (int g0 = 0; g0 < n * n; g0 += 32) {
             float qcf[kBwdPool], qpre[kBwdPool], qx[kBwdPool], qd[kBwdPool];
-            BwdQueue q{qcf, qpre, qx, qd, n <= kPoolMaxPlanes ? g_emu_pool : 0, 0, 0u};
+            BwdQueue q{qcf, qpre, qx, qd, (n <= kPoolMaxPlanes && S.cf0 < 1.0f) ? g_emu_pool : 0, 0, 0u};
             int nr = 0, top = q.cap - 1;
             float bh[32][3], bl[32][3], U[32], w[32], dx[32], dy[32];
             int head[32];
