@@ -13,6 +13,8 @@ Cases
   random_*.npz   seeded randsq()+randquat() inputs (visu.py:55-56, quaternion.py:139-145), SURVEY 8d
   edge.npz       params outside the clamps, on the clamp boundary, axis-aligned q with t on a grid
                  plane (zero fix-up path, classes.py:126,171-173), non-unit q, fp64 inputs
+  edge_grazing.npz   one big object on a 24^3 grid at tau = 3 whose columns graze the surface for most of their length
+                 (the parity fuzz's seed 14 case 68: dozens of gradient-carrying points per column)
 """
 from __future__ import annotations
 
@@ -186,6 +188,24 @@ def zero_plane_cases(rc):
     print("zero planes: implicit", float(out["implicit_loss"]), "explicit", float(out["explicit_loss"]))
 
 
+def grazing_case(rc):
+    """The one configuration of the parity fuzz (tests/tools/parity_fuzz.py --seed 14, case 68) that was outside the gradient
+    tolerance until the kernels pooled the gradient points of a column group: a single object that fills a 24^3 grid, tau = 3,
+    sigmoid sharpness 260, depth image at 73 x 73; its columns graze the surface for up to all 24 planes."""
+    R = 24
+    true = torch.tensor([[0.5378291606903076, 0.3434811234474182, 0.5789921283721924, 0.2919308543205261, 0.46377694606781006,
+                          0.6156783699989319, 0.5951224565505981, 0.6020408272743225,
+                          0.9947512745857239, -0.03643030673265457, -0.09445077925920486, -0.014893271960318089]])
+    pred = torch.tensor([[0.48910823464393616, 0.41221243143081665, 0.7377411723136902, 0.24222418665885925, 0.4850635826587677,
+                          0.5418038368225098, 0.5384869575500488, 0.6187753677368164,
+                          0.9637041687965393, -0.2668421268463135, 0.008339019492268562, 0.00011745292431442067]])
+    img = synthetic_depth(rc, true, 73, 0)
+    out = {"pred": pred.numpy(), "true": true.numpy(), "img": img.numpy(), "R": np.array(R), "tau": np.array(3.0), "k": np.array(260.0)}
+    out["implicit_loss"], out["implicit_grad"] = _grad(rc.ImplicitLoss(R, CPU, 3.0, 260), img, pred)
+    np.savez_compressed(os.path.join(OUT, "edge_grazing.npz"), **out)
+    print("grazing: implicit", float(out["implicit_loss"]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -194,6 +214,7 @@ def main():
     random_cases(rc)
     edge_cases(rc)
     zero_plane_cases(rc)
+    grazing_case(rc)
 
 
 if __name__ == "__main__":

@@ -181,3 +181,27 @@ def test_emulated_pool_overflow_and_on_the_spot_paths():
         lib.emu_set_pool(0)
         lib.emu_set_queue(1)
     assert not np.array_equal(res["full"], res["small"]) and not np.array_equal(res["small"], res["off"])
+
+
+def test_emulated_grazing_columns_need_the_whole_pool():
+    """tests/golden/edge_grazing.npz: a single object that fills a 24^3 grid at tau = 3, whose columns graze the surface for
+    most of their 24 planes (the parity fuzz's seed 14 case 68).  With the whole pool every gradient point is refined and the
+    gradient is within the tolerance; with a pool of 16 slots per 32 columns -- most points then take the unrefined
+    on-the-spot path, as the columns beyond 15 points did with the per-lane queues of the first two thirds of round 2 -- it is
+    not."""
+    g = load_golden("edge_grazing.npz")
+    R, tau, k = int(g["R"]), float(g["tau"]), float(g["k"])
+    tgt = F.interpolate(torch.tensor(g["img"]).float(), size=(R, R), mode="nearest")[:, 0].numpy()
+    lib = E.lib()
+    try:
+        lib.emu_set_pool(0)
+        l, gr, _ = E.implicit(g["pred"], tgt, R, 1 / (R - 1), 1e-4, tau, k)
+        assert abs(l - g["implicit_loss"]) <= 1e-5 * g["implicit_loss"]
+        full = tol(gr, g["implicit_grad"])
+        lib.emu_set_pool(16)
+        _, gr, _ = E.implicit(g["pred"], tgt, R, 1 / (R - 1), 1e-4, tau, k)
+        small = tol(gr, g["implicit_grad"])
+    finally:
+        lib.emu_set_pool(0)
+    assert full <= 1.0, full
+    assert small > 1.3 * full and small > 1.0, (small, full)

@@ -851,6 +851,16 @@ def test_soft_sigmoid_on_a_fine_grid(dev, S):
           keep=unambiguous(oc, img, pred))
 
 
+def test_grazing_columns(dev, S):
+    """One object that fills a 24^3 grid at tau = 3 (tests/golden/edge_grazing.npz, frozen from the reference): its columns graze
+    the surface for most of their planes -- dozens of gradient-carrying points per column.  The parity fuzz's one outlier (4.6x
+    the tolerance) while those points sat in 15-deep per-lane queues; the warp-shared pool takes them all."""
+    g = load_golden("edge_grazing.npz")
+    img = torch.tensor(g["img"]).float()
+    l, gr = run(S.ImplicitLoss(int(g["R"]), dev, float(g["tau"]), float(g["k"])), img, g["pred"], dev)
+    check(l, gr, g["implicit_loss"], g["implicit_grad"], what="grazing columns")
+
+
 def test_zero_planes(dev, S):
     """Axis-aligned rotations with t_z exactly on a grid plane (e.g. a position clamped to 1): the reference's exact-zero
     fix-up fires on a whole z plane -- the walk direction of the kernels (tests/golden/edge_zero_planes.npz, frozen from the

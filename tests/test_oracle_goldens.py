@@ -135,6 +135,15 @@ def test_zero_plane_cases():
     close(O.ImplicitLoss(R, "cpu", 1.5, 260).per_sample(img, pred).numpy(), g["implicit_per_sample"])
 
 
+def test_grazing_case():
+    """One big object on a 24^3 grid at tau = 3 (oracle/make_goldens.py:grazing_case, the parity fuzz's former outlier)."""
+    g = load_golden("edge_grazing.npz")
+    pred, img = torch.tensor(g["pred"]), torch.tensor(g["img"]).float()
+    for form in ("batch", "loop"):
+        l, gr = grad_of(O.ImplicitLoss(int(g["R"]), "cpu", float(g["tau"]), float(g["k"]), form=form), img, pred)
+        close(l, g["implicit_loss"]); close(gr, g["implicit_grad"], rtol=1e-9, atol=1e-12)
+
+
 def test_quaternion_helpers():
     q = torch.tensor([0.699625, 0.378123, -0.090419, -0.599476], dtype=torch.float64)
     assert torch.equal(O.conjugate(q), torch.tensor([-0.699625, -0.378123, 0.090419, -0.599476], dtype=torch.float64))
