@@ -25,6 +25,14 @@ void emu_set_refine(int on) { g_emu_refine = on; }     // fp64 refinement of the
 void emu_set_queue(int on) { g_emu_queue = on; }       // 0: every gradient point on the spot (two-moment path)
 void emu_set_pool(int slots) { g_emu_pool = slots > 0 && slots <= kBwdPool ? slots : kBwdPool; }   // small: exercises the overflow path
 
+// the pool entries' tags (sq_core.cuh BwdQueue): plane index | lane | link packed into one float and taken apart again.
+// Returns 0 when plane, lane and link all survive the round trip (cf0 = the sample's "index" of plane 0, below 1).
+int emu_tag_roundtrip(float cf, float cf0, int lane, int link) {
+    Sample S{}; S.cf0 = cf0;
+    const float tagged = bits_f32((f32_bits(cf) & ~kTagMask) | (unsigned)lane | ((unsigned)link << 5));
+    return (entry_cf(S, tagged) != cf) | ((entry_lane(tagged) != lane) << 1) | ((entry_link(tagged) != link) << 2);
+}
+
 // accuracy probes of the fp64 primitives
 double emu_exp2_acc(double y) { return exp2_acc(y, default_tabs()); }
 double emu_log2_acc(double m) { return log2_acc(m, default_tabs()); }

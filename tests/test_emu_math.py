@@ -205,3 +205,17 @@ def test_emulated_grazing_columns_need_the_whole_pool():
         lib.emu_set_pool(0)
     assert full <= 1.0, full
     assert small > 1.3 * full and small > 1.0, (small, full)
+
+
+def test_pool_entry_tags_round_trip():
+    """Lane and link ride in the 13 low mantissa bits of an entry's plane index: every plane of grids up to 1024, plane 0's
+    non-integer index (restored from the sample), every lane, links up to "none" (255)."""
+    import ctypes
+    lib = E.lib()
+    lib.emu_tag_roundtrip.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int]
+    for cf0 in (0.0, 1e-4 * 63, 1e-4 * 1023, 0.5):
+        for c in list(range(1, 40)) + [63, 64, 127, 128, 255, 256, 511, 512, 1000, 1023]:
+            for lane, link in ((0, 0), (31, 255), (17, 254), (5, 129)):
+                assert lib.emu_tag_roundtrip(float(c), cf0, lane, link) == 0, (c, cf0, lane, link)
+        for lane, link in ((0, 0), (31, 255), (9, 77)):
+            assert lib.emu_tag_roundtrip(np.float32(cf0), np.float32(cf0), lane, link) == 0, (cf0, lane, link)      # plane 0
