@@ -91,8 +91,8 @@ if "SQ_PHASES" in sys.argv[1:]:       # python tools/timeline.py SQ_PHASES: SM c
                                   P(loss), None, P(grad), None, P(scratch), nb, torch.cuda.current_stream().cuda_stream) == 0
     torch.cuda.synchronize()
     assert h.sq_debug_phases(ph.ctypes.data_as(ctypes.c_void_p), 0) == 0
-    names = ["item set-up (sample, pixels, fp32 base, ranges)", "exact base + z walk", "claim issue, signs, counts scan, queue look-up",
-             "fp64 refinement", "deal-out backward", "column values + deal-out list, folding into the tile",
+    names = ["item set-up (sample, pixels, fp32 base, ranges)", "exact base + z walk", "claim issue, signs, work-queue look-up",
+             "fp64 refinement", "deal-out backward", "column values, folding into the tile",
              "item epilogue (reduction, partial row)", "waiting for the next item (claim, sample), loop ends"]
     tot = float(ph.sum())
     print(f"warp cycles per launch, all {len(buf)} warps: {tot / reps / 1e6:.2f} M  ({tot / reps / len(buf) / 1e3:.1f} k per warp)")
