@@ -530,7 +530,7 @@ def run_gpu(args):
                        "around the launch, eager: includes ~3 us of launch latency).  Issued ops = events counted by the "
                        "counting build of the same sources (libsqloss_count.so) on these inputs x the per-event MUFU cost read "
                        "off the kernel source (sq_recovery_b200/counting.py); the committed ncu capture holds the hardware count "
-                       "for comparison.  The kernel skips grid points whose occupancy is below 2^-40, stops a column once its "
+                       "for comparison.  The kernel skips grid points whose occupancy is below 2^-32, stops a column once its "
                        "transmittance is gone and evaluates F with 8 MUFU ops instead of 10, so issued ops are far fewer than "
                        "the reference algorithm's 16 per grid point (`reference_algorithm_equivalent`)")
         roof["peak_source"] = (f"{peak['source']}: {peak['mufu_per_clk_sm']:.2f} MUFU/clk/SM x {peak['sms']} SMs x "
