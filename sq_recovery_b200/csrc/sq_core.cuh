@@ -632,10 +632,10 @@ SQ_HD void finalize_sample(const SampleFull& S, const Grid& g, const double* acc
 // has to be walked over the z range where it can be inside the box |s_i| < bound; the rest is accounted for in closed
 // form with o = 0.
 //   bits = 128: 2^that overflows and o is 0 EXACTLY in this kernel's own fp32 arithmetic -- culling changes nothing.
-//   bits = 40 (ImplicitLoss, kImplicitCullBits): the dropped occupancies sum to < n 2^-40 = 6e-11 per column, 400 times
-//   below the fp32 resolution of cs wherever cs matters (cs > 1e-7 is needed for a depth above 1e-16); their gradient
-//   weight o (1 - o) < 2^-40 is below the 2^-kActive cut the backward applies anyway.  The box edge shrinks from 1.159
-//   to 1.053 at k = 260: 25 % fewer points to evaluate.
+//   bits = 32 (ImplicitLoss, kImplicitCullBits; 40 until round 2): the dropped occupancies sum to < n 2^-32 = 1.5e-8 per
+//   column, below the fp32 resolution of cs wherever cs matters (cs > 1e-7 is needed for a depth above 1e-16); their
+//   gradient weight o (1 - o) < 2^-32 is below the 2^-kact cut the backward applies anyway.  The box edge shrinks from
+//   1.159 (bits = 128) to 1.042 at k = 260: a quarter fewer points to evaluate.
 SQ_HD float cull_bound(float kl) { return sqrtf((1.0f + 128.0f / kl) * 1.002f); }
 #ifndef SQ_IMPLICIT_CULL_BITS
 #define SQ_IMPLICIT_CULL_BITS 32.0f
