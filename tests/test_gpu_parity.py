@@ -503,6 +503,12 @@ def test_dataset_generator(dev, S, tmp_path):
     assert imgs.shape == (3, 1, 256, 256) and imgs.dtype == torch.float32
     assert 0.0 <= imgs.min().item() and imgs.max().item() < 1.0 and 0.02 < (imgs > 0).float().mean().item() < 0.6
     assert torch.equal(imgs[:, 0], S.ImplicitLoss(256, dev, 1.5, 260).depth_projection(p.to(dev)))
+    with torch.no_grad():                                               # one image against the oracle's render of the same label
+        ref = O.ImplicitLoss(256, "cpu", 1.5, 260).depth_projection(p[2:3])
+    np.testing.assert_allclose(imgs[2, 0].cpu().double().numpy(), ref[0].numpy(), rtol=0, atol=3e-5)
+    # and the label file the reference's parse_csv reads back gives the parameters that were rendered
+    rows = make_dataset.parse_rows(make_dataset.label_rows(p.numpy(), [f"synth/{i:06d}.bmp" for i in range(3)]))
+    np.testing.assert_allclose(np.stack(rows), p.numpy(), rtol=0, atol=1e-6)
 
 
 def test_fused_heads_match_torch_heads(dev, S):
